@@ -1,0 +1,147 @@
+/* yms_b200.h -- C ABI of libyms_b200.so: the B200 (sm_100a) kernels of the YOLO-MS / YOLOv8
+ * inference hot path (forward -> DFL decode -> class-aware NMS).
+ *
+ * Boundary rules:
+ *   - extern "C", plain pointers and sizes, no torch types; every pointer is DEVICE memory
+ *     unless the parameter name starts with host_.
+ *   - stream-ordered and re-entrant per stream: no allocation, no host synchronisation;
+ *     `stream` is a cudaStream_t passed as void*.
+ *   - every entry point returns 0 on success, a negative YMS_E_* code for argument errors or
+ *     a positive cudaError_t; yms_last_error() returns a thread-local message.
+ *   - there is NO CPU implementation behind any of these symbols.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository rafaelghiorzi/YOLO-MS).
+ */
+#ifndef YMS_B200_H_
+#define YMS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YMS_ABI_VERSION 1
+
+#define YMS_E_ARG        (-1)   /* invalid argument                                   */
+#define YMS_E_UNSUPPORTED (-2)  /* shape / dtype outside what the kernels implement    */
+#define YMS_E_WORKSPACE  (-3)   /* workspace too small                                 */
+#define YMS_E_DRIVER     (-4)   /* CUDA driver entry point (tensor map encode) failed  */
+
+#define YMS_DTYPE_F32  0
+#define YMS_DTYPE_BF16 1
+
+int         yms_abi_version(void);
+const char* yms_last_error(void);
+/* Number of kernel launches issued through this library by the calling process. */
+long long   yms_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution unit: y = act(conv(x, W) + b) (+ residual), NHWC bf16 activations.
+ * Replaces Conv.forward (yolov8/model/components.py:69-77: Conv2d(bias=False) -> BatchNorm2d
+ * (eval, eps 1e-3) -> SiLU) with BN folded into W/b by the host, the in-place residual of
+ * Bottleneck.forward (components.py:87-93) and the biased 1x1 nn.Conv2d that ends each head
+ * branch (yolov8/model/yolov8_head.py:86,101).  The tensors may be channel slices of wider
+ * buffers (pixel stride != channels), which is how torch.cat / slicing in C2f.forward
+ * (components.py:108-122) and Neck.forward (yolov8_neck.py:76-92) become pointer arithmetic.
+ * Implementation: tcgen05.mma (TMEM accumulators) implicit GEMM, operands staged by TMA.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct yms_conv_params {
+    /* problem */
+    int32_t batch, in_h, in_w;        /* input spatial size                                       */
+    int32_t c_in, c_out;              /* channels of the (slice of the) input / output            */
+    int32_t ksize;                    /* 1 or 3 (padding = ksize/2)                                */
+    int32_t stride;                   /* 1 or 2                                                   */
+    int32_t act;                      /* 0 = identity, 1 = SiLU                                   */
+    int32_t out_dtype;                /* YMS_DTYPE_BF16 or YMS_DTYPE_F32                           */
+    /* second input source (K-concatenation: conv over cat[x, x2], or conv(x + x2) when
+       weights are repeated); c_in2 = 0 disables it.  Same spatial size as x.               */
+    int32_t c_in2;
+    int32_t reserved0;
+    /* tensors */
+    const void* x;   int64_t x_pixel_stride;      /* bf16, elements between consecutive pixels   */
+    const void* x2;  int64_t x2_pixel_stride;
+    void*       y;   int64_t y_pixel_stride;      /* bf16 or f32                                 */
+    const void* residual; int64_t res_pixel_stride; /* bf16 [.., c_out] added after act, or NULL  */
+    const void* weight;   /* bf16 [ksize*ksize][c_out][c_in + c_in2]  (tap-major, K contiguous)   */
+    const float* bias;    /* f32 [c_out]                                                          */
+} yms_conv_params;
+
+typedef struct yms_conv_plan yms_conv_plan;   /* opaque: encoded tensor maps + launch geometry */
+
+int yms_conv_plan_create(const yms_conv_params* p, yms_conv_plan** plan);
+int yms_conv_plan_run(const yms_conv_plan* plan, void* stream);
+int yms_conv_plan_destroy(yms_conv_plan* plan);
+/* 2*MACs of the plan and the algorithmic bytes (inputs + outputs + weights) it moves. */
+int yms_conv_plan_cost(const yms_conv_plan* plan, double* flops, double* bytes);
+
+/* Stem: first layer backbone.conv0 (yolov8/model/yolov8_backbone.py:39, 3x3 stride 2 on the
+ * NCHW fp32 image, components.py:69-77) -> NHWC bf16.  weight f32 [c_out][3][3][3] with BN
+ * folded, bias f32 [c_out]. */
+int yms_stem_conv(const float* x_nchw, int batch, int in_h, int in_w, int c_out,
+                  const float* weight, const float* bias,
+                  void* y_nhwc_bf16, int64_t y_pixel_stride, void* stream);
+
+/* Depthwise k x k (k in 3,5,7,9; stride 1; pad k/2) + folded BN + SiLU, NHWC bf16.
+ * Conv(c, c, k, 1, k//2, groups=c) of components.py:69-77 as used by the repo-local MS-Block.
+ * weight f32 [k*k][c] (tap-major), bias f32 [c]. */
+int yms_dwconv(const void* x, int64_t x_pixel_stride, int batch, int h, int w, int channels, int ksize,
+               const float* weight, const float* bias, void* y, int64_t y_pixel_stride, void* stream);
+
+/* SPPF pooling (components.py:141-146): x1 = maxpool5(x), x2 = maxpool5(x1), x3 = maxpool5(x2)
+ * (5x5, stride 1, pad 2), written as channel slots 1..3 of the concat buffer whose slot 0
+ * already holds x.  buf: bf16 [B,H,W,4*c] (pixel stride given). */
+int yms_sppf_pool(void* buf, int64_t pixel_stride, int batch, int h, int w, int c, void* stream);
+
+/* Nearest x2 upsample (components.py:159-160) written into a channel slice of the concat
+ * buffer the next C2f reads (yolov8_neck.py:77-83).  x: bf16 [B,h,w,c] -> y[B,2h,2w,c]. */
+int yms_upsample2x(const void* x, int64_t x_pixel_stride, int batch, int h, int w, int c,
+                   void* y, int64_t y_pixel_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Head decode: replaces the eval branch of Head.forward (yolov8/model/yolov8_head.py:127-144),
+ * Head.make_anchors (:146-158) and DFL.forward (components.py:176-191, 16 bins).
+ * raw_i: [B, H_i*W_i, 64+nc] channel-last (box logits first), f32 or bf16.
+ * pred : f32 [B, A, 4+nc] = (cx, cy, w, h, sigmoid(cls)) in input pixels, A = sum H_i*W_i.
+ * If cand_boxes != NULL also emits what the reference post-process derives per anchor
+ * (tools/test.py:166-179): xyxy box, best class score, best class (lowest index on ties).
+ * ------------------------------------------------------------------------------------------ */
+int yms_head_decode(const void* raw0, const void* raw1, const void* raw2, int raw_dtype,
+                    int batch, const int32_t* host_hw /* h0,w0,h1,w1,h2,w2 */, int num_classes,
+                    const float* host_strides /* 3 */, float* pred,
+                    float* cand_boxes /* [B,A,4] or NULL */, float* cand_scores /* [B,A] */,
+                    int32_t* cand_labels /* [B,A] */, void* stream);
+
+/* Candidate selection of the reference post-process on an arbitrary prediction tensor
+ * (yolov8/tools/test.py:166-179 == tools/train.py:64-72): pred f32 [B,A,4+nc] ->
+ * xyxy boxes, per-anchor max class score and argmax (first max). */
+int yms_select_candidates(const float* pred, int batch, int anchors, int num_classes,
+                          float* boxes, float* scores, int32_t* labels, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched class-aware NMS: replaces the confidence filter + per-class loop around
+ * torchvision.ops.nms (yolov8/tools/test.py:181-218 == tools/train.py:74-106).
+ * boxes f32 [B,N,4] xyxy, scores f32 [B,N], labels i32 [B,N] in [0, num_classes);
+ * n_valid i32 [B] (entries >= n_valid[b] ignored) or NULL.  A box takes part iff
+ * score > conf_thr (strict, fp32).  Suppression iff (double)IoU_fp32 > iou_thr between boxes
+ * of the same label; output order = label ascending, then score descending, ties by index.
+ * keep i32 [B,N]: indices into the N axis (first keep_count[b] valid, rest -1).
+ * Limits: N <= 2^20, num_classes <= 2047.
+ * ------------------------------------------------------------------------------------------ */
+size_t yms_nms_workspace_bytes(int batch, int n);
+int yms_nms_batched(const float* boxes, const float* scores, const int32_t* labels,
+                    const int32_t* n_valid, int batch, int n, int num_classes,
+                    float conf_thr, double iou_thr, int32_t* keep, int32_t* keep_count,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gather kept detections into padded [B, max_det, 6] = (x1,y1,x2,y2,score,label) rows. */
+int yms_gather_detections(const float* boxes, const float* scores, const int32_t* labels,
+                          const int32_t* keep, const int32_t* keep_count, int batch, int n,
+                          int max_det, float* dets, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YMS_B200_H_ */

@@ -1,0 +1,263 @@
+// CUDA-core kernels around the GEMM convolutions: stem conv, SPPF pooling, nearest upsample,
+// depthwise k x k.  All activations are NHWC bf16 with an explicit pixel stride so that
+// outputs land directly inside the channel slice of the concat buffer that consumes them.
+#include "common.cuh"
+
+namespace yms {
+namespace {
+
+// =====================================================================================
+// Stem: backbone.conv0 (yolov8_backbone.py:39), 3x3 stride 2 pad 1 on the NCHW fp32 image,
+// folded BN + SiLU, NHWC bf16 out.  One thread = one output pixel x CO_T output channels.
+// The 27 input taps are read once into registers; weights are broadcast from shared memory.
+// =====================================================================================
+template <int CO_T>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, int in_h, int in_w, int c_out,
+                                                        const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ y, long long y_ps) {
+    extern __shared__ float s_w[];                 // [27][c_out] then bias[c_out]
+    const int out_h = in_h >> 1, out_w = in_w >> 1;
+    for (int i = threadIdx.x; i < 27 * c_out; i += blockDim.x) {
+        // wgt is [c_out][ci][ky][kx]; store as [(ci*9+ky*3+kx)][c_out]
+        int co = i % c_out, t = i / c_out;
+        s_w[i] = wgt[co * 27 + t];
+    }
+    float* s_b = s_w + 27 * c_out;
+    for (int i = threadIdx.x; i < c_out; i += blockDim.x) s_b[i] = bias[i];
+    __syncthreads();
+
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;
+    const int b = blockIdx.z;
+    if (ox >= out_w) return;
+    float in[27];
+    const float* xb = x + (size_t)b * 3 * in_h * in_w;
+    #pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+        #pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy + ky - 1;
+            #pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox + kx - 1;
+                float v = 0.f;
+                if (iy >= 0 && iy < in_h && ix >= 0 && ix < in_w) v = __ldg(xb + ((size_t)ci * in_h + iy) * in_w + ix);
+                in[ci * 9 + ky * 3 + kx] = v;
+            }
+        }
+    __nv_bfloat16* yo = y + ((size_t)(b * out_h + oy) * out_w + ox) * y_ps;
+    for (int c0 = 0; c0 < c_out; c0 += CO_T) {
+        float acc[CO_T];
+        #pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = s_b[c0 + j];
+        #pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const float v = in[t];
+            const float* wr = s_w + t * c_out + c0;
+            #pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+        uint32_t pk[CO_T / 2];
+        #pragma unroll
+        for (int j = 0; j < CO_T / 2; ++j) pk[j] = pack_bf16x2(silu_f(acc[2 * j]), silu_f(acc[2 * j + 1]));
+        #pragma unroll
+        for (int j = 0; j < CO_T / 8; ++j)
+            *reinterpret_cast<uint4*>(yo + c0 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+}
+
+// =====================================================================================
+// SPPF pooling (components.py:141-146).  Chained 5x5/s1/p2 max pools with -inf padding equal
+// single 5x5, 9x9 and 13x13 windows clipped at the border; max is exact in bf16, so the
+// results are bit-identical to the chained form.  One thread = one pixel x 8 channels (16 B);
+// separable: vertical running max over rows is recomputed per thread from L1/L2-resident data
+// (the map is 20x20..40x40 pixels).  Writes slots 1..3 of the concat buffer.
+// =====================================================================================
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+    uint4 r;
+    __nv_bfloat162* ra = reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162* rb = reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) rr[i] = __hmax2(ra[i], rb[i]);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* buf, long long ps, int h, int w, int c) {
+    const int groups = c >> 3;
+    const long long total = (long long)h * w * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    const int px = (int)((idx / groups) % w);
+    const int py = (int)(idx / ((long long)groups * w));
+    __nv_bfloat16* base = buf + (size_t)b * h * w * ps + g * 8;
+    const uint32_t ninf2 = 0xff80ff80u;            // bf16 -inf pair
+    uint4 m5 = make_uint4(ninf2, ninf2, ninf2, ninf2), m9 = m5, m13 = m5;
+    for (int dy = -6; dy <= 6; ++dy) {
+        const int yy = py + dy;
+        if (yy < 0 || yy >= h) continue;
+        const int ady = dy < 0 ? -dy : dy;
+        uint4 r5 = make_uint4(ninf2, ninf2, ninf2, ninf2), r9 = r5, r13 = r5;
+        for (int dx = -6; dx <= 6; ++dx) {
+            const int xx = px + dx;
+            if (xx < 0 || xx >= w) continue;
+            const int adx = dx < 0 ? -dx : dx;
+            const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)yy * w + xx) * ps);
+            r13 = max_bf16x8(r13, v);
+            if (adx <= 4) r9 = max_bf16x8(r9, v);
+            if (adx <= 2) r5 = max_bf16x8(r5, v);
+        }
+        m13 = max_bf16x8(m13, r13);
+        if (ady <= 4) m9 = max_bf16x8(m9, r9);
+        if (ady <= 2) m5 = max_bf16x8(m5, r5);
+    }
+    __nv_bfloat16* o = base + ((size_t)py * w + px) * ps;
+    *reinterpret_cast<uint4*>(o + c) = m5;
+    *reinterpret_cast<uint4*>(o + 2 * c) = m9;
+    *reinterpret_cast<uint4*>(o + 3 * c) = m13;
+}
+
+// =====================================================================================
+// Nearest x2 upsample (components.py:159-160) into a channel slice.  One thread = one INPUT
+// pixel x 8 channels: one 16 B load, four 16 B stores.
+// =====================================================================================
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
+                                                         int h, int w, int c, __nv_bfloat16* __restrict__ y, long long yps) {
+    const int groups = c >> 3;
+    const long long total = (long long)h * w * groups;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (idx >= total) return;
+    const int g = (int)(idx % groups);
+    const int px = (int)((idx / groups) % w);
+    const int py = (int)(idx / ((long long)groups * w));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * h + py) * w + px) * xps + g * 8));
+    __nv_bfloat16* o = y + ((size_t)(b * 2 * h + 2 * py) * (2 * w) + 2 * px) * yps + g * 8;
+    *reinterpret_cast<uint4*>(o) = v;
+    *reinterpret_cast<uint4*>(o + yps) = v;
+    *reinterpret_cast<uint4*>(o + (size_t)2 * w * yps) = v;
+    *reinterpret_cast<uint4*>(o + (size_t)2 * w * yps + yps) = v;
+}
+
+// =====================================================================================
+// Depthwise k x k (stride 1, pad k/2) + folded BN + SiLU, NHWC bf16 (MS-Block branches).
+// A CTA computes a TH x TW output tile for 8*CG channels: the (TH+k-1) x (TW+k-1) halo tile
+// is staged in shared memory with 16-byte loads, weights in shared memory as fp32, fp32
+// accumulate.  One thread = one output pixel x 8 channels.
+// =====================================================================================
+constexpr int kDwTW = 16, kDwTH = 8;       // 128 output pixels per channel group
+constexpr int kDwCG = 2;                   // channel groups (of 8) per CTA -> 256 threads
+
+template <int K>
+__global__ void __launch_bounds__(kDwTW * kDwTH * kDwCG) dwconv_kernel(
+    const __nv_bfloat16* __restrict__ x, long long xps, int h, int w, int c,
+    const float* __restrict__ wgt, const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, long long yps) {
+    constexpr int R = K / 2, IW = kDwTW + K - 1, IH = kDwTH + K - 1;
+    __shared__ uint4 s_in[kDwCG][IH][IW];
+    __shared__ float s_w[K * K][kDwCG * 8];
+    __shared__ float s_b[kDwCG * 8];
+    const int tiles_x = ceil_div(w, kDwTW);
+    const int tx0 = (blockIdx.x % tiles_x) * kDwTW, ty0 = (blockIdx.x / tiles_x) * kDwTH;
+    const int c0 = blockIdx.y * (kDwCG * 8);
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < K * K * kDwCG * 8; i += blockDim.x) {
+        int ch = i % (kDwCG * 8), t = i / (kDwCG * 8);
+        s_w[t][ch] = (c0 + ch < c) ? wgt[(size_t)t * c + c0 + ch] : 0.f;
+    }
+    if (tid < kDwCG * 8) s_b[tid] = (c0 + tid < c) ? bias[c0 + tid] : 0.f;
+    const __nv_bfloat16* xb = x + (size_t)b * h * w * xps;
+    for (int i = tid; i < kDwCG * IH * IW; i += blockDim.x) {
+        const int g = i / (IH * IW), r = (i / IW) % IH, q = i % IW;
+        const int yy = ty0 + r - R, xx = tx0 + q - R;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w && c0 + g * 8 < c)
+            v = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)yy * w + xx) * xps + c0 + g * 8));
+        s_in[g][r][q] = v;
+    }
+    __syncthreads();
+    const int g = tid / (kDwTW * kDwTH);
+    const int lx = tid % kDwTW, ly = (tid / kDwTW) % kDwTH;
+    const int ox = tx0 + lx, oy = ty0 + ly;
+    if (ox >= w || oy >= h || c0 + g * 8 >= c) return;
+    float acc[8];
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_b[g * 8 + j];
+    #pragma unroll
+    for (int ky = 0; ky < K; ++ky)
+        #pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const uint4 v = s_in[g][ly + ky][lx + kx];
+            const float* wr = &s_w[ky * K + kx][g * 8];
+            acc[0] = fmaf(bf16_lo(v.x), wr[0], acc[0]); acc[1] = fmaf(bf16_hi(v.x), wr[1], acc[1]);
+            acc[2] = fmaf(bf16_lo(v.y), wr[2], acc[2]); acc[3] = fmaf(bf16_hi(v.y), wr[3], acc[3]);
+            acc[4] = fmaf(bf16_lo(v.z), wr[4], acc[4]); acc[5] = fmaf(bf16_hi(v.z), wr[5], acc[5]);
+            acc[6] = fmaf(bf16_lo(v.w), wr[6], acc[6]); acc[7] = fmaf(bf16_hi(v.w), wr[7], acc[7]);
+        }
+    uint4 o;
+    o.x = pack_bf16x2(silu_f(acc[0]), silu_f(acc[1]));
+    o.y = pack_bf16x2(silu_f(acc[2]), silu_f(acc[3]));
+    o.z = pack_bf16x2(silu_f(acc[4]), silu_f(acc[5]));
+    o.w = pack_bf16x2(silu_f(acc[6]), silu_f(acc[7]));
+    *reinterpret_cast<uint4*>(y + ((size_t)(b * h + oy) * w + ox) * yps + c0 + g * 8) = o;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+}  // namespace yms
+
+using namespace yms;
+
+extern "C" int yms_stem_conv(const float* x, int batch, int in_h, int in_w, int c_out, const float* weight,
+                             const float* bias, void* y, int64_t y_ps, void* stream) {
+    if (batch <= 0 || in_h <= 0 || in_w <= 0 || (in_h & 1) || (in_w & 1)) return fail(YMS_E_ARG, "stem: bad image size");
+    if (c_out <= 0 || (c_out % 16) != 0 || c_out > 256) return fail(YMS_E_UNSUPPORTED, "stem: c_out must be a multiple of 16 (<= 256)");
+    if (!x || !weight || !bias || !y || !aligned16(y) || (y_ps % 8) != 0) return fail(YMS_E_ARG, "stem: bad pointers/strides");
+    dim3 grid(ceil_div(in_w / 2, 128), in_h / 2, batch);
+    size_t smem = (size_t)28 * c_out * sizeof(float);
+    stem_conv_kernel<16><<<grid, 128, smem, (cudaStream_t)stream>>>(x, in_h, in_w, c_out, weight, bias,
+                                                                    reinterpret_cast<__nv_bfloat16*>(y), y_ps);
+    return check_launch("stem_conv_kernel");
+}
+
+extern "C" int yms_sppf_pool(void* buf, int64_t ps, int batch, int h, int w, int c, void* stream) {
+    if (batch <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8) != 0) return fail(YMS_E_ARG, "sppf: bad sizes (c % 8 == 0)");
+    if (!buf || !aligned16(buf) || (ps % 8) != 0 || ps < 4 * (int64_t)c) return fail(YMS_E_ARG, "sppf: bad buffer");
+    long long total = (long long)h * w * (c / 8);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    sppf_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(buf), ps, h, w, c);
+    return check_launch("sppf_pool_kernel");
+}
+
+extern "C" int yms_upsample2x(const void* x, int64_t xps, int batch, int h, int w, int c, void* y, int64_t yps, void* stream) {
+    if (batch <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8) != 0) return fail(YMS_E_ARG, "upsample: bad sizes (c % 8 == 0)");
+    if (!x || !y || !aligned16(x) || !aligned16(y) || (xps % 8) != 0 || (yps % 8) != 0) return fail(YMS_E_ARG, "upsample: bad pointers/strides");
+    long long total = (long long)h * w * (c / 8);
+    dim3 grid((unsigned)((total + 255) / 256), batch);
+    upsample2x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), xps, h, w, c,
+                                                             reinterpret_cast<__nv_bfloat16*>(y), yps);
+    return check_launch("upsample2x_kernel");
+}
+
+extern "C" int yms_dwconv(const void* x, int64_t xps, int batch, int h, int w, int channels, int ksize,
+                          const float* weight, const float* bias, void* y, int64_t yps, void* stream) {
+    if (batch <= 0 || h <= 0 || w <= 0 || channels <= 0 || (channels % 8) != 0) return fail(YMS_E_ARG, "dwconv: bad sizes (c % 8 == 0)");
+    if (!x || !y || !weight || !bias || !aligned16(x) || !aligned16(y) || (xps % 8) != 0 || (yps % 8) != 0)
+        return fail(YMS_E_ARG, "dwconv: bad pointers/strides");
+    dim3 grid(ceil_div(w, kDwTW) * ceil_div(h, kDwTH), ceil_div(channels, kDwCG * 8), batch);
+    const int threads = kDwTW * kDwTH * kDwCG;
+    auto xs = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto ys = reinterpret_cast<__nv_bfloat16*>(y);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ksize) {
+        case 3: dwconv_kernel<3><<<grid, threads, 0, st>>>(xs, xps, h, w, channels, weight, bias, ys, yps); break;
+        case 5: dwconv_kernel<5><<<grid, threads, 0, st>>>(xs, xps, h, w, channels, weight, bias, ys, yps); break;
+        case 7: dwconv_kernel<7><<<grid, threads, 0, st>>>(xs, xps, h, w, channels, weight, bias, ys, yps); break;
+        case 9: dwconv_kernel<9><<<grid, threads, 0, st>>>(xs, xps, h, w, channels, weight, bias, ys, yps); break;
+        default: return fail(YMS_E_UNSUPPORTED, "dwconv: ksize must be 3, 5, 7 or 9");
+    }
+    return check_launch("dwconv_kernel");
+}

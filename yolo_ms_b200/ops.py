@@ -1,0 +1,237 @@
+"""Torch-facing operators over the C ABI of libyms_b200.so.
+
+PyTorch is plumbing here (device memory + streams).  Every function launches hand-written
+sm_100a kernels on ``torch.cuda.current_stream()``; there is no CPU or eager fallback --
+CPU tensors raise ``YmsError``.
+
+The public post-process operators are also registered as torch custom ops under the
+``yms_b200::`` namespace (``torch.ops.yms_b200.nms_batched`` etc.).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, YmsError, check
+
+__all__ = ["ConvPlan", "stem_conv", "dwconv", "sppf_pool", "upsample2x", "head_decode",
+           "select_candidates", "nms_batched", "gather_detections", "YmsError"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise YmsError("yolo_ms_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+def _pixel_stride(t: torch.Tensor) -> int:
+    """t is a channel-last [..., C] view whose leading dims are contiguous pixels."""
+    if t.stride(-1) != 1:
+        raise YmsError("channel dimension must be contiguous")
+    return t.stride(-2)
+
+
+class ConvPlan:
+    """One convolution unit bound to fixed NHWC bf16 buffers (tensor maps encoded once).
+
+    x, y, x2, residual are [B, H, W, C] views (channel slices of wider buffers allowed).
+    weight: bf16 [k*k, c_out, c_in (+ c_in2)], bias: f32 [c_out].
+    """
+
+    def __init__(self, x, weight, bias, y, ksize=1, stride=1, act=True, residual=None, x2=None):
+        _need_cuda(x, weight, bias, y, residual, x2)
+        if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or bias.dtype != torch.float32:
+            raise YmsError("conv: x/weight must be bf16 and bias f32")
+        if y.dtype not in (torch.bfloat16, torch.float32):
+            raise YmsError("conv: y must be bf16 or f32")
+        b, h, w, c_in = x.shape
+        c_out = y.shape[-1]
+        c_in2 = 0 if x2 is None else x2.shape[-1]
+        if tuple(weight.shape) != (ksize * ksize, c_out, c_in + c_in2) or not weight.is_contiguous():
+            raise YmsError(f"conv: weight must be contiguous [{ksize * ksize},{c_out},{c_in + c_in2}], got {tuple(weight.shape)}")
+        if tuple(y.shape[:3]) != (b, h // stride, w // stride):
+            raise YmsError("conv: output spatial shape mismatch")
+        p = ConvParams()
+        p.batch, p.in_h, p.in_w, p.c_in, p.c_out = b, h, w, c_in, c_out
+        p.ksize, p.stride, p.act = ksize, stride, int(bool(act))
+        p.out_dtype = _lib.DTYPE_BF16 if y.dtype == torch.bfloat16 else _lib.DTYPE_F32
+        p.c_in2 = c_in2
+        p.x, p.x_pixel_stride = x.data_ptr(), _pixel_stride(x)
+        if x2 is not None:
+            p.x2, p.x2_pixel_stride = x2.data_ptr(), _pixel_stride(x2)
+        p.y, p.y_pixel_stride = y.data_ptr(), _pixel_stride(y)
+        if residual is not None:
+            p.residual, p.res_pixel_stride = residual.data_ptr(), _pixel_stride(residual)
+        p.weight, p.bias = weight.data_ptr(), bias.data_ptr()
+        self._keep = (x, weight, bias, y, residual, x2)      # keep the storages alive
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        check(self._lib.yms_conv_plan_create(C.byref(p), C.byref(self._h)), "yms_conv_plan_create")
+        fl, by = C.c_double(), C.c_double()
+        self._lib.yms_conv_plan_cost(self._h, C.byref(fl), C.byref(by))
+        self.flops, self.bytes = fl.value, by.value
+
+    def run(self) -> None:
+        check(self._lib.yms_conv_plan_run(self._h, _stream()), "yms_conv_plan_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.yms_conv_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torch.Tensor) -> None:
+    """x f32 NCHW [B,3,H,W]; weight f32 [c_out,3,3,3] (BN folded); y bf16 [B,H/2,W/2,c_out]."""
+    _need_cuda(x, weight, bias, y)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[1] != 3:
+        raise YmsError("stem: x must be contiguous f32 [B,3,H,W]")
+    b, _, h, w = x.shape
+    check(_lib.load().yms_stem_conv(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(),
+                                    y.data_ptr(), _pixel_stride(y), _stream()), "yms_stem_conv")
+
+
+def dwconv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torch.Tensor, ksize: int) -> None:
+    """Depthwise kxk + bias + SiLU.  x,y bf16 [B,H,W,C]; weight f32 [k*k, C]; bias f32 [C]."""
+    _need_cuda(x, weight, bias, y)
+    b, h, w, c = x.shape
+    check(_lib.load().yms_dwconv(x.data_ptr(), _pixel_stride(x), b, h, w, c, ksize, weight.data_ptr(), bias.data_ptr(),
+                                 y.data_ptr(), _pixel_stride(y), _stream()), "yms_dwconv")
+
+
+def sppf_pool(buf: torch.Tensor, c: int) -> None:
+    """buf bf16 [B,H,W,>=4c]: slot 0 holds x; writes the 5/9/13 max pools into slots 1..3."""
+    _need_cuda(buf)
+    b, h, w, _ = buf.shape
+    check(_lib.load().yms_sppf_pool(buf.data_ptr(), _pixel_stride(buf), b, h, w, c, _stream()), "yms_sppf_pool")
+
+
+def upsample2x(x: torch.Tensor, y: torch.Tensor) -> None:
+    _need_cuda(x, y)
+    b, h, w, c = x.shape
+    check(_lib.load().yms_upsample2x(x.data_ptr(), _pixel_stride(x), b, h, w, c, y.data_ptr(), _pixel_stride(y),
+                                     _stream()), "yms_upsample2x")
+
+
+def head_decode(raw: Sequence[torch.Tensor], strides: Sequence[float], num_classes: int,
+                with_candidates: bool = False):
+    """raw: 3 tensors [B,H_i,W_i,64+nc] (channel-last, contiguous, f32 or bf16).
+    Returns pred [B,A,4+nc] f32 (and (boxes_xyxy, scores, labels) when with_candidates)."""
+    _need_cuda(*raw)
+    if len(raw) != 3:
+        raise YmsError("head_decode expects 3 scales")
+    dt = raw[0].dtype
+    if dt not in (torch.float32, torch.bfloat16) or any(r.dtype != dt or not r.is_contiguous() for r in raw):
+        raise YmsError("head_decode: raw tensors must be contiguous and share dtype f32/bf16")
+    b = raw[0].shape[0]
+    no = 64 + num_classes
+    hw = (C.c_int32 * 6)()
+    a = 0
+    for i, r in enumerate(raw):
+        if r.shape[0] != b or r.shape[-1] != no:
+            raise YmsError("head_decode: bad raw shape")
+        hw[2 * i], hw[2 * i + 1] = r.shape[1], r.shape[2]
+        a += r.shape[1] * r.shape[2]
+    st = (C.c_float * 3)(*[float(s) for s in strides])
+    dev = raw[0].device
+    pred = torch.empty((b, a, 4 + num_classes), dtype=torch.float32, device=dev)
+    if with_candidates:
+        boxes = torch.empty((b, a, 4), dtype=torch.float32, device=dev)
+        scores = torch.empty((b, a), dtype=torch.float32, device=dev)
+        labels = torch.empty((b, a), dtype=torch.int32, device=dev)
+        ptrs = (boxes.data_ptr(), scores.data_ptr(), labels.data_ptr())
+    else:
+        boxes = scores = labels = None
+        ptrs = (None, None, None)
+    check(_lib.load().yms_head_decode(raw[0].data_ptr(), raw[1].data_ptr(), raw[2].data_ptr(),
+                                      _lib.DTYPE_F32 if dt == torch.float32 else _lib.DTYPE_BF16, b, hw, num_classes, st,
+                                      pred.data_ptr(), *ptrs, _stream()), "yms_head_decode")
+    return (pred, (boxes, scores, labels)) if with_candidates else pred
+
+
+def select_candidates(pred: torch.Tensor):
+    """pred f32 [B,A,4+nc] -> (xyxy [B,A,4], best score [B,A], best class [B,A] int32)."""
+    _need_cuda(pred)
+    if pred.dtype != torch.float32 or pred.dim() != 3:
+        raise YmsError("select_candidates: pred must be f32 [B,A,4+nc]")
+    pred = pred.contiguous()
+    b, a, no = pred.shape
+    boxes = torch.empty((b, a, 4), dtype=torch.float32, device=pred.device)
+    scores = torch.empty((b, a), dtype=torch.float32, device=pred.device)
+    labels = torch.empty((b, a), dtype=torch.int32, device=pred.device)
+    check(_lib.load().yms_select_candidates(pred.data_ptr(), b, a, no - 4, boxes.data_ptr(), scores.data_ptr(),
+                                            labels.data_ptr(), _stream()), "yms_select_candidates")
+    return boxes, scores, labels
+
+
+def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, conf_thr: float, iou_thr: float,
+                num_classes: int, n_valid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """boxes f32 [B,N,4] xyxy, scores f32 [B,N], labels int32 [B,N].
+    Returns (keep int32 [B,N] padded with -1, keep_count int32 [B])."""
+    _need_cuda(boxes, scores, labels, n_valid)
+    if boxes.dtype != torch.float32 or scores.dtype != torch.float32 or labels.dtype != torch.int32:
+        raise YmsError("nms_batched: dtypes must be f32/f32/int32")
+    boxes, scores, labels = boxes.contiguous(), scores.contiguous(), labels.contiguous()
+    b, n = scores.shape
+    keep = torch.empty((b, n), dtype=torch.int32, device=boxes.device)
+    count = torch.empty((b,), dtype=torch.int32, device=boxes.device)
+    lib = _lib.load()
+    ws_bytes = lib.yms_nms_workspace_bytes(b, n)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=boxes.device)
+    nv = None
+    if n_valid is not None:
+        nv = n_valid.to(torch.int32).contiguous()
+    # float(np.float32(conf)): the reference compares fp32 scores with the Python scalar cast to fp32
+    conf32 = float(torch.tensor(conf_thr, dtype=torch.float32))
+    check(lib.yms_nms_batched(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(),
+                              None if nv is None else nv.data_ptr(), b, n, num_classes, conf32, float(iou_thr),
+                              keep.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "yms_nms_batched")
+    return keep, count
+
+
+def gather_detections(boxes, scores, labels, keep, count, max_det: int) -> torch.Tensor:
+    """-> f32 [B, max_det, 6] rows (x1,y1,x2,y2,score,label); unused rows have label -1."""
+    _need_cuda(boxes, scores, labels, keep, count)
+    b, n = scores.shape
+    dets = torch.empty((b, max_det, 6), dtype=torch.float32, device=boxes.device)
+    check(_lib.load().yms_gather_detections(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr(),
+                                            count.data_ptr(), b, n, max_det, dets.data_ptr(), _stream()),
+          "yms_gather_detections")
+    return dets
+
+
+# ---------------------------------------------------------------------------------------------
+# torch custom-op registration (thin shims over the functions above)
+# ---------------------------------------------------------------------------------------------
+def _register():
+    try:
+        from torch.library import custom_op
+    except Exception:  # pragma: no cover
+        return
+
+    @custom_op("yms_b200::nms_batched", mutates_args=(), device_types="cuda")
+    def _nms(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, conf_thr: float, iou_thr: float,
+             num_classes: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        return nms_batched(boxes, scores, labels, conf_thr, iou_thr, num_classes)
+
+    @custom_op("yms_b200::select_candidates", mutates_args=(), device_types="cuda")
+    def _sel(pred: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        return select_candidates(pred)
+
+    @custom_op("yms_b200::head_decode", mutates_args=(), device_types="cuda")
+    def _dec(raw0: torch.Tensor, raw1: torch.Tensor, raw2: torch.Tensor, strides: Sequence[float],
+             num_classes: int) -> torch.Tensor:
+        return head_decode((raw0, raw1, raw2), strides, num_classes)
+
+
+_register()
