@@ -27,13 +27,33 @@ def width_params(version: str):
 
 
 _CALIBRATING = False
+# When True the oracle keeps the reference's algorithm but applies the PRODUCT'S numeric contract
+# (DESIGN.md): BN folded into the weights in fp32, weights and every stored activation rounded to
+# bf16, fp32 accumulation, fp32 head logits / decode.  The CUDA path must agree with this variant
+# to ~1e-2 END TO END, which makes wiring bugs visible that the bf16-vs-fp32 noise floor would hide.
+EMULATE_BF16 = False
 
 
-def conv_unit(sd, p, x, stride=1, act=True):
-    """Conv2d(bias=False) -> BN(eval, eps 1e-3) -> SiLU.  components.py:69-77."""
+def _bf16(t):
+    return t.to(torch.bfloat16).float()
+
+
+def conv_unit(sd, p, x, stride=1, act=True, residual=None, first=False):
+    """Conv2d(bias=False) -> BN(eval, eps 1e-3) -> SiLU (+ residual).  components.py:69-77, :91-92."""
     w = sd[p + ".conv.weight"]
     k = w.shape[-1]
     groups = x.shape[1] // w.shape[1]
+    if EMULATE_BF16 and not _CALIBRATING:
+        scale = sd[p + ".bn.weight"] / torch.sqrt(sd[p + ".bn.running_var"] + BN_EPS)
+        wf = w * scale.view(-1, 1, 1, 1)
+        bf = sd[p + ".bn.bias"] - sd[p + ".bn.running_mean"] * scale
+        if not (first or groups > 1):       # stem and depthwise kernels keep fp32 weights
+            wf = _bf16(wf)
+        y = F.conv2d(x, wf, bf, stride, k // 2, 1, groups)
+        y = F.silu(y) if act else y
+        if residual is not None:
+            y = y + residual
+        return _bf16(y)
     y = F.conv2d(x, w, None, stride, k // 2, 1, groups)
     if _CALIBRATING:  # test-weight generation only: set running stats from this batch
         yd = y.double()
@@ -41,7 +61,8 @@ def conv_unit(sd, p, x, stride=1, act=True):
         sd[p + ".bn.running_var"] = yd.var((0, 2, 3), unbiased=False).clamp_min(1e-6).float()
     y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"],
                      sd[p + ".bn.weight"], sd[p + ".bn.bias"], False, 0.0, BN_EPS)
-    return F.silu(y) if act else y
+    y = F.silu(y) if act else y
+    return y if residual is None else y + residual
 
 
 def _count(sd, prefix):
@@ -61,8 +82,7 @@ def c2f(sd, p, x):
     outs = [x1, x2]
     for j in range(_count(sd, p + ".m")):
         t = conv_unit(sd, f"{p}.m.{j}.conv1", x1)
-        t = conv_unit(sd, f"{p}.m.{j}.conv2", t)
-        x1 = t + x1
+        x1 = conv_unit(sd, f"{p}.m.{j}.conv2", t, residual=x1)      # x += x_in (components.py:91-92)
         outs.insert(0, x1)
     return conv_unit(sd, p + ".conv2", torch.cat(outs, 1))
 
@@ -105,7 +125,7 @@ def sppf(sd, p, x):
 
 def backbone(sd, x, taps=None):
     """yolov8_backbone.py:54-74."""
-    x = conv_unit(sd, "backbone.conv0", x, 2)
+    x = conv_unit(sd, "backbone.conv0", x, 2, first=True)
     if taps is not None:
         taps["backbone.conv0"] = x
     x = conv_unit(sd, "backbone.conv1", x, 2)
@@ -138,7 +158,8 @@ def head_raw(sd, feats):
         for name in ("box", "cls"):
             t = conv_unit(sd, f"head.{name}.{i}.0", f)
             t = conv_unit(sd, f"head.{name}.{i}.1", t)
-            t = F.conv2d(t, sd[f"head.{name}.{i}.2.weight"], sd[f"head.{name}.{i}.2.bias"])
+            wl = sd[f"head.{name}.{i}.2.weight"]
+            t = F.conv2d(t, _bf16(wl) if EMULATE_BF16 else wl, sd[f"head.{name}.{i}.2.bias"])
             branch.append(t)
         out.append(torch.cat(branch, 1))
     return out
@@ -184,6 +205,16 @@ def calibrate_bn(sd, x):
     finally:
         _CALIBRATING = False
     return sd
+
+
+def forward_bf16_contract(sd, x, strides=(8.0, 16.0, 32.0), return_parts=False):
+    """Same algorithm under the product's numeric contract (see EMULATE_BF16)."""
+    global EMULATE_BF16
+    EMULATE_BF16 = True
+    try:
+        return forward(sd, x, strides, return_parts)
+    finally:
+        EMULATE_BF16 = False
 
 
 def forward(sd, x, strides=(8.0, 16.0, 32.0), return_parts=False):

@@ -1,0 +1,274 @@
+"""-m gpu: every kernel through the C ABI against its reference, on the B200 box."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+from gpu_util import DEV, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from yolo_ms_b200 import ops as _ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _ops
+
+
+# name, B, H, W, cin, cout, k, stride, act, res, cin2, out_f32, slices
+CONV_CASES = [
+    ("1x1_64_64", 2, 40, 40, 64, 64, 1, 1, 1, 0, 0, 0, 0),
+    ("1x1_tailM", 1, 20, 20, 64, 64, 1, 1, 1, 0, 0, 0, 0),
+    ("1x1_16_16", 2, 16, 16, 16, 16, 1, 1, 1, 0, 0, 0, 0),
+    ("1x1_48_96", 2, 16, 16, 48, 96, 1, 1, 1, 0, 0, 0, 0),
+    ("1x1_80_80_f32", 2, 20, 20, 80, 80, 1, 1, 0, 0, 0, 1, 1),
+    ("1x1_768_512", 2, 20, 20, 768, 512, 1, 1, 1, 0, 0, 0, 0),
+    ("1x1_576_288", 1, 20, 20, 576, 288, 1, 1, 1, 0, 0, 0, 1),       # several N tiles, c_out % 64 != 0
+    ("1x1_two_src_odd", 2, 20, 20, 48, 80, 1, 1, 1, 0, 32, 0, 1),
+    ("3x3_64_64_res", 2, 40, 40, 64, 64, 3, 1, 1, 1, 0, 0, 0),
+    ("3x3_288_288_res", 1, 20, 20, 288, 288, 3, 1, 1, 1, 0, 0, 1),
+    ("3x3_128_80_w20", 2, 20, 20, 128, 80, 3, 1, 1, 0, 0, 0, 0),
+    ("3x3_32_32_w160", 1, 160, 160, 32, 32, 3, 1, 1, 0, 0, 0, 0),
+    ("3x3s2_64_128", 2, 80, 80, 64, 128, 3, 2, 1, 0, 0, 0, 0),
+    ("3x3s2_384_576", 1, 20, 20, 384, 576, 3, 2, 1, 0, 0, 0, 0),
+    ("3x3s2_slices", 2, 40, 40, 128, 128, 3, 2, 1, 0, 0, 0, 1),
+    ("3x3s2_odd_out", 1, 24, 40, 64, 64, 3, 2, 1, 0, 0, 0, 0),
+    ("3x3_f32_320", 1, 64, 64, 64, 64, 3, 1, 0, 0, 0, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm_matches_torch_fp32(ops, case):
+    """tcgen05 implicit-GEMM conv vs a plain PyTorch fp32 conv of the same (bf16-rounded) operands.
+    Tolerance: bf16 output rounding (2^-9) -> rel-L2 <= 4e-3; fp32 outputs <= 1e-5."""
+    name, B, H, W, cin, cout, k, s, act, res, cin2, f32, sl = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    pad_c = 24 if sl else 0
+
+    def mk(c, h, w):
+        full = torch.randn(B, h, w, c + pad_c, generator=g).to(DEV).to(torch.bfloat16)
+        return full[..., 8:8 + c] if sl else full
+
+    x = mk(cin, H, W)
+    x2 = mk(cin2, H, W) if cin2 else None
+    ktot = cin + cin2
+    wt = (torch.randn(cout, ktot, k, k, generator=g) / (ktot * k * k) ** 0.5).to(DEV).to(torch.bfloat16)
+    bias = (torch.randn(cout, generator=g) * 0.5).to(DEV)
+    Ho, Wo = H // s, W // s
+    r = mk(cout, Ho, Wo) if res else None
+    yfull = torch.full((B, Ho, Wo, cout + pad_c), 7.0, device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+    y = yfull[..., 8:8 + cout] if sl else yfull
+    wpk = wt.permute(2, 3, 0, 1).reshape(k * k, cout, ktot).contiguous()
+    ops.ConvPlan(x, wpk, bias, y, ksize=k, stride=s, act=bool(act), residual=r, x2=x2).run()
+    xin = x.float() if x2 is None else torch.cat([x.float(), x2.float()], -1)
+    ref = F.conv2d(xin.permute(0, 3, 1, 2), wt.float(), bias, stride=s, padding=k // 2)
+    ref = F.silu(ref) if act else ref
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    ref = ref.permute(0, 2, 3, 1)
+    assert rel_l2(y, ref) < (1e-5 if f32 else 4e-3)
+    if sl:   # neighbours of the channel slice must be untouched (concat-by-pointer contract)
+        assert bool((yfull[..., :8] == 7).all() and (yfull[..., 8 + cout:] == 7).all())
+
+
+def test_conv_rejects_cpu_and_bad_shapes(ops):
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16)
+    with pytest.raises(ops.YmsError):
+        ops.ConvPlan(x, torch.zeros(1, 64, 64, dtype=torch.bfloat16), torch.zeros(64), x.clone())
+    xg = torch.zeros(1, 8, 8, 60, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(ops.YmsError):   # channels % 8
+        ops.ConvPlan(xg, torch.zeros(1, 64, 60, dtype=torch.bfloat16, device=DEV), torch.zeros(64, device=DEV),
+                     torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV))
+
+
+@pytest.mark.parametrize("cout", [16, 32, 48])
+def test_stem_conv(ops, cout):
+    g = torch.Generator().manual_seed(cout)
+    x = torch.randn(2, 3, 64, 96, generator=g).to(DEV)
+    w = (torch.randn(cout, 3, 3, 3, generator=g) * 0.3).to(DEV)
+    b = (torch.randn(cout, generator=g) * 0.2).to(DEV)
+    y = torch.empty(2, 32, 48, cout, device=DEV, dtype=torch.bfloat16)
+    ops.stem_conv(x, w, b, y)
+    ref = F.silu(F.conv2d(x, w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert rel_l2(y, ref) < 4e-3
+
+
+def test_sppf_pool_is_exact(ops):
+    g = torch.Generator().manual_seed(1)
+    for (h, w, c) in ((20, 24, 64), (5, 3, 8), (40, 40, 32)):
+        buf = torch.zeros(2, h, w, 4 * c, device=DEV, dtype=torch.bfloat16)
+        buf[..., :c] = torch.randn(2, h, w, c, generator=g).to(DEV).to(torch.bfloat16)
+        ops.sppf_pool(buf, c)
+        x0 = buf[..., :c].float().permute(0, 3, 1, 2)
+        x1 = F.max_pool2d(x0, 5, 1, 2); x2 = F.max_pool2d(x1, 5, 1, 2); x3 = F.max_pool2d(x2, 5, 1, 2)
+        ref = torch.cat([x0, x1, x2, x3], 1).permute(0, 2, 3, 1)
+        assert bool((buf.float() == ref).all())
+
+
+def test_upsample_into_slice_is_exact(ops):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 10, 12, 64, generator=g).to(DEV).to(torch.bfloat16)
+    ybuf = torch.zeros(2, 20, 24, 96, device=DEV, dtype=torch.bfloat16)
+    ops.upsample2x(x, ybuf[..., :64])
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert bool((ybuf[..., :64].float() == ref).all()) and bool((ybuf[..., 64:] == 0).all())
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+def test_dwconv(ops, k):
+    g = torch.Generator().manual_seed(k)
+    for (h, w_, c) in ((20, 20, 64), (37, 45, 24)):
+        x = torch.randn(2, h, w_, c, generator=g).to(DEV).to(torch.bfloat16)
+        wt = (torch.randn(c, 1, k, k, generator=g) / k).to(DEV)
+        b = (torch.randn(c, generator=g) * 0.2).to(DEV)
+        y = torch.empty(2, h, w_, c, device=DEV, dtype=torch.bfloat16)
+        ops.dwconv(x, wt.reshape(c, k * k).t().contiguous(), b, y, k)
+        ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), wt, b, padding=k // 2, groups=c)).permute(0, 2, 3, 1)
+        assert rel_l2(y, ref) < 4e-3
+
+
+# ----------------------------------------------------------------------------------------------
+# decode / candidate selection vs the oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("sizes,nc", [(((20, 24), (10, 12), (5, 6)), 80), (((15, 15), (7, 9), (3, 5)), 3), (((2, 2), (1, 1), (1, 1)), 80)])
+def test_head_decode_matches_oracle(ops, dt, sizes, nc):
+    """fp32 decode; tolerance 1e-4 px * stride on boxes (expf ulps), 1e-6 on scores.  The emitted
+    candidates must be bit-identical to the reference selection applied to OUR prediction."""
+    from oracle import postprocess as P
+    from oracle import yolov8_oracle as O
+    g = torch.Generator().manual_seed(3)
+    B = 3
+    raw = [(torch.randn(B, 64 + nc, h, w, generator=g) * 2).to(dt).float() for h, w in sizes]
+    want = O.decode(raw, (8.0, 16.0, 32.0))
+    rawg = [r.permute(0, 2, 3, 1).contiguous().to(DEV).to(dt) for r in raw]
+    pred, (cb, cs, cl) = ops.head_decode(rawg, (8.0, 16.0, 32.0), nc, with_candidates=True)
+    assert pred.shape == want.shape
+    p = pred.cpu()
+    assert float((p[..., :4] - want[..., :4]).abs().max()) < 5e-3
+    assert float((p[..., 4:] - want[..., 4:]).abs().max()) < 2e-6
+    sb, ss, sl = ops.select_candidates(pred)
+    for i in range(B):
+        wb, ws, wl = P.select_candidates(p[i].numpy())
+        for b_, s_, l_ in ((cb, cs, cl), (sb, ss, sl)):
+            assert np.array_equal(b_[i].cpu().numpy(), wb)
+            assert np.array_equal(s_[i].cpu().numpy(), ws)
+            assert np.array_equal(l_[i].cpu().numpy().astype(np.int64), wl)
+    # zero strides -> zero boxes (reference default head.stride, yolov8_head.py:79)
+    z = ops.head_decode(rawg, (0.0, 0.0, 0.0), nc)
+    assert float(z[..., :4].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------
+# NMS: bit-exact keep lists
+# ----------------------------------------------------------------------------------------------
+def _nms(ops, boxes, scores, labels, conf, iou, nc, nv=None):
+    keep, cnt = ops.nms_batched(torch.from_numpy(boxes).to(DEV), torch.from_numpy(scores).to(DEV),
+                                torch.from_numpy(labels).to(DEV), conf, iou, nc,
+                                None if nv is None else torch.from_numpy(nv).to(DEV))
+    keep, cnt = keep.cpu().numpy(), cnt.cpu().numpy()
+    for i in range(keep.shape[0]):
+        assert (keep[i, cnt[i]:] == -1).all()
+    return [keep[i, :cnt[i]] for i in range(keep.shape[0])]
+
+
+@pytest.mark.parametrize("name", ["uniform", "clustered", "ties", "degenerate", "exact_thr"])
+def test_nms_matches_torchvision_goldens(ops, name):
+    g = np.load(os.path.join(GOLDEN, "nms_cases.npz"))
+    boxes, scores = g[f"{name}_boxes"], g[f"{name}_scores"]
+    labels = np.zeros((1, boxes.shape[0]), np.int32)
+    for thr in (0.45, 0.5, 1.0 / 3.0):
+        got = _nms(ops, boxes[None], scores[None], labels, -1.0, thr, 1)[0]
+        assert np.array_equal(got, g[f"{name}_keep_{thr:.4f}"]), (name, thr)
+
+
+def test_postprocess_matches_reference_golden(ops):
+    from yolo_ms_b200 import postprocess
+    g = np.load(os.path.join(GOLDEN, "post_n.npz"))
+    pred = torch.from_numpy(g["pred"]).to(DEV)
+    for tag in ("a", "b"):
+        conf, iou = g[f"thr_{tag}"]
+        res = postprocess(pred, float(conf), float(iou))
+        for i, (bx, sc, lb) in enumerate(res):
+            assert np.array_equal(bx.cpu().numpy(), g[f"boxes_{tag}{i}"])
+            assert np.array_equal(sc.cpu().numpy(), g[f"scores_{tag}{i}"])
+            assert np.array_equal(lb.cpu().numpy(), g[f"labels_{tag}{i}"])
+            assert lb.dtype == torch.int64
+
+
+@pytest.mark.parametrize("B,N,nc,mode", [(4, 1000, 80, "uni"), (3, 8400, 80, "clu"), (2, 30000, 80, "ties"),
+                                          (2, 3000, 1, "clu"), (2, 20000, 3, "clu"), (1, 1, 80, "uni"),
+                                          (2, 33, 5, "uni"), (2, 16385, 80, "uni")])
+def test_nms_random_ragged_matches_c_oracle(ops, B, N, nc, mode):
+    from oracle import postprocess as P
+    rng = np.random.default_rng(N + nc)
+    if mode == "clu" and N >= 100:
+        ctr = rng.uniform(0, 600, (B, N // 100 + 1, 2))
+        xy = np.repeat(ctr, 100, 1)[:, :N] + rng.normal(0, 6, (B, N, 2))
+    else:
+        xy = rng.uniform(0, 600, (B, N, 2))
+    wh = rng.uniform(4, 64, (B, N, 2))
+    boxes = np.concatenate([xy, xy + wh], -1).astype(np.float32)
+    scores = rng.uniform(0, 1, (B, N)).astype(np.float32)
+    if mode == "ties":
+        scores = (np.round(scores * 256) / 256).astype(np.float32)
+    labels = rng.integers(0, nc, (B, N)).astype(np.int32)
+    nv = rng.integers(N // 2, N + 1, (B,)).astype(np.int32)
+    got = _nms(ops, boxes, scores, labels, 0.25, 0.45, nc, nv)
+    for i in range(B):
+        want = P.class_nms_c(boxes[i, :nv[i]], scores[i, :nv[i]], labels[i, :nv[i]], 0.25, 0.45)
+        assert np.array_equal(got[i], want)
+
+
+def test_nms_edge_cases(ops):
+    boxes = np.array([[[0, 0, 10, 10], [0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 20, 20]]], np.float32)
+    scores = np.array([[0.25, 0.9, 0.8, 0.7]], np.float32)
+    labels = np.array([[0, 1, 1, 1]], np.int32)
+    # score == conf dropped (strict >); identical boxes of one class suppress; zero-area box survives (NaN IoU)
+    assert _nms(ops, boxes, scores, labels, 0.25, 0.45, 2)[0].tolist() == [1, 3]
+    # nothing above conf
+    assert _nms(ops, boxes, scores, labels, 0.95, 0.45, 2)[0].tolist() == []
+    # n_valid = 0 and out-of-range labels are ignored
+    assert _nms(ops, boxes, scores, labels, 0.1, 0.45, 2, np.array([0], np.int32))[0].tolist() == []
+    assert _nms(ops, boxes, scores, np.array([[0, 5, -1, 1]], np.int32), 0.1, 0.45, 2)[0].tolist() == [0, 3]
+    # iou threshold 1.0: nothing is ever suppressed (IoU <= 1)
+    assert _nms(ops, boxes, scores, labels, 0.1, 1.0, 2)[0].tolist() == [0, 1, 2, 3]
+    # empty batch / empty N
+    k, c = ops.nms_batched(torch.zeros(2, 0, 4, device=DEV), torch.zeros(2, 0, device=DEV),
+                           torch.zeros(2, 0, dtype=torch.int32, device=DEV), 0.25, 0.45, 80)
+    assert k.shape == (2, 0) and c.tolist() == [0, 0]
+
+
+def test_nms_full_size_properties(ops):
+    """BASELINE config 4 (30k boxes x batch 64 x 80 classes): size-independent properties --
+    idempotence, output ordering, no surviving same-class pair above the threshold -- plus the C
+    oracle on two images of the batch."""
+    from oracle import postprocess as P
+    from gpu_util import iou_xyxy
+    rng = np.random.default_rng(0)
+    B, N, nc = 64, 30000, 80
+    xy = rng.uniform(0, 600, (B, N, 2)); wh = rng.uniform(4, 64, (B, N, 2))
+    boxes = np.concatenate([xy, xy + wh], -1).astype(np.float32)
+    scores = rng.uniform(0, 1, (B, N)).astype(np.float32)
+    labels = rng.integers(0, nc, (B, N)).astype(np.int32)
+    got = _nms(ops, boxes, scores, labels, 0.25, 0.45, nc)
+    for i in (0, 63):
+        assert np.array_equal(got[i], P.class_nms_c(boxes[i], scores[i], labels[i], 0.25, 0.45))
+    for i in (5, 31):
+        k = got[i]
+        key = labels[i][k].astype(np.int64) * 4 - scores[i][k].astype(np.float64)     # label asc, score desc
+        assert (np.diff(key) >= 0).all()
+        assert (scores[i][k] > 0.25).all()
+        # idempotence: NMS over the survivors keeps all of them, in the same order
+        again = _nms(ops, boxes[i][k][None], scores[i][k][None], labels[i][k][None], 0.25, 0.45, nc)[0]
+        assert np.array_equal(again, np.arange(k.size))
+        # sampled pair check inside one class
+        sel = k[labels[i][k] == 7]
+        a, b = np.meshgrid(np.arange(sel.size), np.arange(sel.size))
+        m = a < b
+        assert (iou_xyxy(boxes[i][sel][a[m]], boxes[i][sel][b[m]]) <= 0.45 + 1e-6).all()

@@ -503,8 +503,19 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     }
     kp.tiles_x = ceil_div(kp.out_w, kp.tw);
     kp.tiles_y = ceil_div(kp.out_h, kp.th);
-    kp.n_tiles = ceil_div(q->c_out, 256);
-    kp.block_n = ((ceil_div(q->c_out, kp.n_tiles) + 15) / 16) * 16;
+    if (q->c_out <= 256) {
+        kp.n_tiles = 1;
+        kp.block_n = ((q->c_out + 15) / 16) * 16;
+    } else {
+        // several N tiles: every tile must be whole 64-channel store boxes (a partial box would
+        // spill into the next tile's channels); pick the width that pads c_out the least.
+        int best_pad = 1 << 30;
+        for (int bn = 64; bn <= 256; bn += 64) {
+            int padded = ceil_div(q->c_out, bn) * bn;
+            if (padded <= best_pad) { best_pad = padded; kp.block_n = bn; }
+        }
+        kp.n_tiles = ceil_div(q->c_out, kp.block_n);
+    }
     kp.c_out = q->c_out;
     kp.c_in1 = q->c_in; kp.c_in2 = q->c_in2;
     kp.kb1 = ceil_div(q->c_in, kBlockK); kp.kb2 = ceil_div(q->c_in2, kBlockK);

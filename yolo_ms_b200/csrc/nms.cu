@@ -315,7 +315,7 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     size_t smem = (size_t)tile * 8 + (size_t)(num_classes + 1) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * 8 + (kMaxClasses + 1) * 8);
         if (e != cudaSuccess) return fail((int)e, "nms: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }

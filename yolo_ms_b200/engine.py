@@ -1,0 +1,110 @@
+"""Program builder / executor: turns a module tree into a static list of kernel launches over
+pre-allocated NHWC bf16 buffers and replays it (CUDA graph) per call.
+
+Data layout in HBM
+------------------
+* activations: NHWC bf16, one buffer per tensor, EXCEPT that every tensor that the reference
+  concatenates (C2f's [b_n..b_1,x1,x2], SPPF's [x,x1,x2,x3], the neck's [up(x),skip] /
+  [conv(x),skip]) is produced directly inside its channel slice of the concat buffer --
+  producers get a strided view (pixel stride = concat width), so torch.cat never runs.
+* weights: BN folded in fp32, then packed bf16 [tap][c_out][c_in] (K contiguous) = the B operand
+  tiles TMA fetches; bias fp32.
+* head raw logits: fp32 [B,H,W,64+nc] per scale (box | cls), decode output fp32 [B,A,4+nc].
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import YmsError
+
+BN_EPS_DEFAULT = 1e-3
+
+
+def fold_conv_bn(weight: torch.Tensor, bn_w, bn_b, bn_mean, bn_var, eps: float):
+    """conv(bias=False)+BN(eval) -> (weight', bias') in fp32 (components.py:69-77 of the reference)."""
+    scale = bn_w.float() / torch.sqrt(bn_var.float() + eps)
+    return weight.float() * scale.view(-1, 1, 1, 1), bn_b.float() - bn_mean.float() * scale
+
+
+def pack_weight(w: torch.Tensor) -> torch.Tensor:
+    """[c_out, c_in, k, k] fp32 -> bf16 [k*k, c_out, c_in] (tap-major, K contiguous)."""
+    co, ci, k, _ = w.shape
+    return w.permute(2, 3, 0, 1).reshape(k * k, co, ci).contiguous().to(torch.bfloat16)
+
+
+class Program:
+    """A recorded sequence of launches over static buffers."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.steps: List[Callable[[], None]] = []
+        self.plans: List[ops.ConvPlan] = []
+        self._keep: list = []
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches = 0
+        self.flops = 0.0
+        self.bytes = 0.0
+
+    # ---- buffers -------------------------------------------------------------------------
+    def buf(self, b: int, h: int, w: int, c: int, dtype=torch.bfloat16) -> torch.Tensor:
+        t = torch.empty((b, h, w, c), dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def hold(self, *ts):
+        self._keep.extend(ts)
+
+    # ---- ops -------------------------------------------------------------------------------
+    def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None):
+        plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
+        self.plans.append(plan)
+        self.hold(weight_packed, bias)
+        self.steps.append(plan.run)
+        self.launches += 1
+        self.flops += plan.flops
+        self.bytes += plan.bytes
+        return y
+
+    def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0):
+        self.steps.append(fn)
+        self.launches += 1
+        self.bytes += nbytes
+        self.flops += flops
+
+    # ---- execution ---------------------------------------------------------------------------
+    def run_eager(self):
+        for s in self.steps:
+            s()
+
+    def capture(self):
+        """Warm up once, then capture the step list into a CUDA graph."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.run_eager()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager()
+        self.graph = g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager()
+
+
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """API adaptation for stand-alone sub-modules (NOT on the YOLOv8.forward hot path, where the
+    stem kernel reads the NCHW fp32 image directly)."""
+    if not x.is_cuda:
+        raise YmsError("yolo_ms_b200 modules run on CUDA tensors only (no CPU fallback)")
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 3, 1, 2).float()

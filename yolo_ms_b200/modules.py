@@ -1,0 +1,520 @@
+"""Drop-in module classes: same constructor / forward API and the same state_dict keys as the
+reference's ``yolov8`` package, executed by hand-written sm_100a kernels.
+
+Reference API mirrored here (paths relative to rafaelghiorzi/YOLO-MS):
+  YOLOv8(version, num_classes, dfl_ch=16)            yolov8/yolov8.py:8-31
+  Backbone(version, in_channels=3, shortcut=True)    yolov8/model/yolov8_backbone.py:34-74
+  Neck(version)                                      yolov8/model/yolov8_neck.py:55-94
+  Head(version, ch=16, num_classes=80), .stride      yolov8/model/yolov8_head.py:73-158
+  Conv / Bottleneck / C2f / SPPF / Upsample / DFL / yolo_params
+                                                     yolov8/model/components.py:69-209
+plus the repo-local ``MSBlock`` (``block='ms'``), which the reference only sketches
+(annotations.md:66-133).
+
+The modules own ordinary ``nn.Parameter``s / BN buffers (so ``state_dict`` round-trips with
+reference checkpoints); ``forward`` compiles, per input shape, a static launch program
+(engine.Program) from the *current* parameter values with BN folded, and replays it.  There is
+no CPU path and no autograd: a CPU input raises ``YmsError``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import YmsError
+from .engine import Program, fold_conv_bn, nchw_f32_to_nhwc_bf16, nhwc_to_nchw_f32, pack_weight
+
+_VERSIONS = {  # depth, width, ratio  (components.py:193-209)
+    "n": (1 / 3, 1 / 4, 2.0), "s": (1 / 3, 1 / 2, 2.0), "m": (2 / 3, 3 / 4, 1.5),
+    "l": (1.0, 1.0, 1.0), "x": (1.0, 1.25, 1.0),
+}
+
+
+def yolo_params(version):
+    if version not in _VERSIONS:
+        raise ValueError(f"Unknown YOLOv8 version: {version}")
+    return _VERSIONS[version]
+
+
+class _Compiled(nn.Module):
+    """Mixin: per-shape program cache that is dropped whenever parameters may have changed."""
+
+    def _programs(self) -> Dict:
+        cache = self.__dict__.get("_yms_cache")
+        if cache is None:
+            cache = {}
+            self.__dict__["_yms_cache"] = cache
+        return cache
+
+    def refresh(self):
+        """Drop compiled programs (call after modifying parameters in place)."""
+        for m in self.modules():
+            m.__dict__.pop("_yms_cache", None)
+        return self
+
+    def _apply(self, fn, *a, **k):
+        self.refresh()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self.refresh()
+        return super().load_state_dict(*a, **k)
+
+    def train(self, mode: bool = True):
+        return super().train(mode)
+
+
+def _device_of(m: nn.Module) -> torch.device:
+    return next(m.parameters()).device
+
+
+# =============================================================================================
+# building blocks
+# =============================================================================================
+class Conv(_Compiled):
+    """conv(bias=False) + BN(eps 1e-3, momentum 0.03) + SiLU  (components.py:69-77)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, groups=1, activation=True):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=False, groups=groups)
+        self.bn = nn.BatchNorm2d(out_channels, eps=0.001, momentum=0.03)
+        self.activation = nn.SiLU(inplace=True) if activation else nn.Identity()
+
+    # ---- weight preparation --------------------------------------------------------------
+    def folded(self):
+        return fold_conv_bn(self.conv.weight.detach(), self.bn.weight.detach(), self.bn.bias.detach(),
+                            self.bn.running_mean, self.bn.running_var, self.bn.eps)
+
+    @property
+    def has_act(self):
+        return isinstance(self.activation, nn.SiLU)
+
+    def emit(self, P: Program, x, out=None, residual=None, x2=None, dup_k=False):
+        """x: NHWC bf16 view.  dup_k: weights repeated over both sources (conv(x + x2))."""
+        conv = self.conv
+        k, s = conv.kernel_size[0], conv.stride[0]
+        if conv.padding[0] != k // 2:
+            raise YmsError("Conv: only padding = kernel_size // 2 is implemented")
+        w, b = self.folded()
+        bsz, h, wd, _ = x.shape
+        co = conv.out_channels
+        if out is None:
+            out = P.buf(bsz, h // s, wd // s, co)
+        if conv.groups == 1:
+            if dup_k:
+                w = torch.cat([w, w], 1)
+            P.conv(pack_weight(w), b.contiguous(), x, out, ksize=k, stride=s, act=self.has_act, residual=residual, x2=x2)
+        elif conv.groups == conv.in_channels == co and s == 1 and self.has_act and residual is None and x2 is None:
+            wk = w.reshape(co, k * k).t().contiguous()          # [k*k, C]
+            bb = b.contiguous()
+            P.hold(wk, bb)
+            P.add(lambda: ops.dwconv(x, wk, bb, out, k), nbytes=4.0 * bsz * h * wd * co, flops=2.0 * bsz * h * wd * co * k * k)
+        else:
+            raise YmsError("Conv: only groups=1 or depthwise stride-1 convolutions are implemented")
+        return out
+
+    def forward(self, x):
+        return _run_standalone(self, (x,), lambda P, xs: (self.emit(P, xs[0]),))[0]
+
+
+class Bottleneck(_Compiled):
+    """Two 3x3 Conv units + residual (components.py:80-93)."""
+
+    def __init__(self, in_channels, out_channels, shortcut=True):
+        super().__init__()
+        self.conv1 = Conv(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.conv2 = Conv(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.shortcut = shortcut
+
+    def emit(self, P, x, out=None):
+        t = self.conv1.emit(P, x)
+        return self.conv2.emit(P, t, out=out, residual=x if self.shortcut else None)
+
+    def forward(self, x):
+        return _run_standalone(self, (x,), lambda P, xs: (self.emit(P, xs[0]),))[0]
+
+
+class C2f(_Compiled):
+    """components.py:96-122.  Concat order [b_n, ..., b_1, x1, x2]; the FIRST half is chained;
+    bottlenecks always keep their shortcut (the reference never forwards `shortcut`)."""
+
+    def __init__(self, in_channels, out_channels, num_bottlenecks, shortcut=True):
+        super().__init__()
+        self.mid_channels = out_channels // 2
+        self.num_bottlenecks = num_bottlenecks
+        self.conv1 = Conv(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
+        self.m = nn.ModuleList([Bottleneck(self.mid_channels, self.mid_channels) for _ in range(num_bottlenecks)])
+        self.conv2 = Conv((num_bottlenecks + 2) * out_channels // 2, out_channels, kernel_size=1, stride=1, padding=0)
+
+    def emit(self, P, x, out=None):
+        n, h = self.num_bottlenecks, self.mid_channels
+        b, hh, ww, _ = x.shape
+        cat = P.buf(b, hh, ww, (n + 2) * h)
+        self.conv1.emit(P, x, out=cat[..., n * h:(n + 2) * h])
+        cur = cat[..., n * h:(n + 1) * h]
+        for j, blk in enumerate(self.m):
+            dst = cat[..., (n - 1 - j) * h:(n - j) * h]
+            blk.emit(P, cur, out=dst)
+            cur = dst
+        return self.conv2.emit(P, cat, out=out)
+
+    def forward(self, x):
+        return _run_standalone(self, (x,), lambda P, xs: (self.emit(P, xs[0]),))[0]
+
+
+class MSBlock(_Compiled):
+    """Repo-local MS-Block (NOT in the reference; after arXiv 2308.05480).  in_conv 1x1
+    (C_in -> 3c, c = C_out/2); branch 0 identity; branch i>=1: (x_i + y_{i-1}) -> L x
+    [1x1 c->2c, depthwise kxk, 1x1 2c->c]; concat; out_conv 1x1 (3c -> C_out)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, layers_num=1):
+        super().__init__()
+        c = out_channels // 2
+        self.mid_channels = c
+        self.kernel_size = kernel_size
+        self.in_conv = Conv(in_channels, 3 * c, kernel_size=1, stride=1, padding=0)
+        branches = []
+        for _ in range(2):
+            layers = []
+            for _ in range(layers_num):
+                layer = nn.Module()
+                layer.pw1 = Conv(c, 2 * c, kernel_size=1, stride=1, padding=0)
+                layer.dw = Conv(2 * c, 2 * c, kernel_size=kernel_size, stride=1, padding=kernel_size // 2, groups=2 * c)
+                layer.pw2 = Conv(2 * c, c, kernel_size=1, stride=1, padding=0)
+                layers.append(layer)
+            branches.append(nn.ModuleList(layers))
+        self.branches = nn.ModuleList(branches)
+        self.out_conv = Conv(3 * c, out_channels, kernel_size=1, stride=1, padding=0)
+
+    def emit(self, P, x, out=None):
+        c = self.mid_channels
+        b, hh, ww, _ = x.shape
+        y = self.in_conv.emit(P, x)                         # [x0 | x1 | x2]
+        tail = P.buf(b, hh, ww, 2 * c)                      # [y1 | y2]
+        prev = y[..., :c]
+        for bi, layers in enumerate(self.branches):
+            xi = y[..., (bi + 1) * c:(bi + 2) * c]
+            t = None
+            for li, layer in enumerate(layers):
+                if li == 0:   # conv(x_i + y_{i-1}) = K-concatenated GEMM with repeated weights
+                    e = layer.pw1.emit(P, xi, x2=prev, dup_k=True)
+                else:
+                    e = layer.pw1.emit(P, t)
+                d = layer.dw.emit(P, e)
+                dst = tail[..., bi * c:(bi + 1) * c] if li == len(layers) - 1 else None
+                t = layer.pw2.emit(P, d, out=dst)
+            prev = t
+        return self.out_conv.emit(P, y[..., :c], out=out, x2=tail)
+
+    def forward(self, x):
+        return _run_standalone(self, (x,), lambda P, xs: (self.emit(P, xs[0]),))[0]
+
+
+class SPPF(_Compiled):
+    """components.py:125-150."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=5):
+        super().__init__()
+        if kernel_size != 5:
+            raise YmsError("SPPF: only kernel_size=5 is implemented")
+        hidden = in_channels // 2
+        self.conv1 = Conv(in_channels, hidden, kernel_size=1, stride=1, padding=0)
+        self.conv2 = Conv(hidden * 4, out_channels, kernel_size=1, stride=1, padding=0)
+        self.m = nn.MaxPool2d(kernel_size=kernel_size, stride=1, padding=kernel_size // 2)
+
+    def emit(self, P, x, out=None):
+        b, hh, ww, _ = x.shape
+        hc = self.conv1.conv.out_channels
+        cat = P.buf(b, hh, ww, 4 * hc)
+        self.conv1.emit(P, x, out=cat[..., :hc])
+        P.add(lambda: ops.sppf_pool(cat, hc), nbytes=2.0 * 4 * b * hh * ww * hc)
+        return self.conv2.emit(P, cat, out=out)
+
+    def forward(self, x):
+        return _run_standalone(self, (x,), lambda P, xs: (self.emit(P, xs[0]),))[0]
+
+
+class Upsample(nn.Module):
+    """Nearest x2 (components.py:153-160)."""
+
+    def __init__(self, scale_factor=2, mode="nearest"):
+        super().__init__()
+        if scale_factor != 2 or mode != "nearest":
+            raise YmsError("Upsample: only nearest x2 is implemented")
+        self.scale_factor, self.mode = scale_factor, mode
+
+    def emit(self, P, x, out):
+        P.add(lambda: ops.upsample2x(x, out), nbytes=2.0 * 5 * x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3])
+        return out
+
+    def forward(self, x):
+        xin = nchw_f32_to_nhwc_bf16(x)
+        b, h, w, c = xin.shape
+        y = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+        ops.upsample2x(xin, y)
+        return nhwc_to_nchw_f32(y)
+
+
+class DFL(nn.Module):
+    """Holds the frozen 0..15 projection (state_dict key ``head.dfl.conv.weight``,
+    components.py:162-174).  The softmax-expectation itself is fused into the head-decode kernel."""
+
+    def __init__(self, ch=16):
+        super().__init__()
+        self.ch = ch
+        self.conv = nn.Conv2d(ch, 1, kernel_size=1, bias=False).requires_grad_(False)
+        self.conv.weight.data[:] = torch.arange(ch, dtype=torch.float).view(1, ch, 1, 1)
+
+    def forward(self, x):
+        raise YmsError("DFL runs fused inside yms_head_decode; call Head(...) in eval mode")
+
+
+def _slot(block: str, cin: int, cout: int, n: int, k: int):
+    if block == "c2f":
+        return C2f(cin, cout, num_bottlenecks=n)
+    if block == "ms":
+        return MSBlock(cin, cout, kernel_size=k, layers_num=n)
+    raise ValueError(f"unknown block type {block!r} (expected 'c2f' or 'ms')")
+
+
+# =============================================================================================
+# backbone / neck / head / model
+# =============================================================================================
+class Backbone(_Compiled):
+    def __init__(self, version, in_channels=3, shortcut=True, block="c2f"):
+        super().__init__()
+        d, w, r = yolo_params(version)
+        c1, c2, c3, c4, c5 = int(64 * w), int(128 * w), int(256 * w), int(512 * w), int(512 * w * r)
+        self.conv0 = Conv(in_channels, c1, kernel_size=3, stride=2, padding=1)
+        self.conv1 = Conv(c1, c2, kernel_size=3, stride=2, padding=1)
+        self.conv3 = Conv(c2, c3, kernel_size=3, stride=2, padding=1)
+        self.conv5 = Conv(c3, c4, kernel_size=3, stride=2, padding=1)
+        self.conv7 = Conv(c4, c5, kernel_size=3, stride=2, padding=1)
+        self.c2f_2 = _slot(block, c2, c2, int(3 * d), 3)
+        self.c2f_4 = _slot(block, c3, c3, int(6 * d), 3)
+        self.c2f_6 = _slot(block, c4, c4, int(6 * d), 5)
+        self.c2f_8 = _slot(block, c5, c5, int(3 * d), 7)
+        self.sppf = SPPF(c5, c5, kernel_size=5)
+        self.out_channels = (c3, c4, c5)
+
+    def emit(self, P, image_nchw, outs=(None, None, None)):
+        """image_nchw: the static f32 NCHW input tensor.  outs: optional destination views."""
+        b, cin, h, w = image_nchw.shape
+        if cin != 3:
+            raise YmsError("Backbone: the stem kernel expects 3 input channels")
+        if h % 32 or w % 32:
+            raise YmsError("input height and width must be multiples of 32")   # reference: torch.cat raises
+        w0, b0 = self.conv0.folded()
+        w0, b0 = w0.contiguous(), b0.contiguous()
+        y0 = P.buf(b, h // 2, w // 2, self.conv0.conv.out_channels)
+        P.hold(w0, b0)
+        P.add(lambda: ops.stem_conv(image_nchw, w0, b0, y0), nbytes=4.0 * image_nchw.numel() + 2.0 * y0.numel(),
+              flops=2.0 * y0.numel() * 27)
+        x = self.conv1.emit(P, y0)
+        x = self.c2f_2.emit(P, x)
+        x = self.conv3.emit(P, x)
+        p3 = self.c2f_4.emit(P, x, out=outs[0])
+        x = self.conv5.emit(P, p3)
+        p4 = self.c2f_6.emit(P, x, out=outs[1])
+        x = self.conv7.emit(P, p4)
+        x = self.c2f_8.emit(P, x)
+        p5 = self.sppf.emit(P, x, out=outs[2])
+        return p3, p4, p5
+
+    def forward(self, x):
+        prog, io = _get_program(self, (x,), lambda P, xs: self.emit(P, xs[0]), image_input=True)
+        io["inputs"][0].copy_(x)
+        prog.run()
+        return tuple(nhwc_to_nchw_f32(t) for t in io["outputs"])
+
+
+class Neck(_Compiled):
+    def __init__(self, version, block="c2f"):
+        super().__init__()
+        d, w, r = yolo_params(version)
+        c3, c4, c5 = int(256 * w), int(512 * w), int(512 * w * r)
+        n = int(3 * d)
+        self.up = Upsample()
+        self.c2f_1 = _slot(block, int(512 * w * (1 + r)), c4, n, 5)
+        self.c2f_2 = _slot(block, int(768 * w), c3, n, 3)
+        self.c2f_3 = _slot(block, int(768 * w), c4, n, 5)
+        self.c2f_4 = _slot(block, int(512 * w * (1 + r)), c5, n, 7)
+        self.conv1 = Conv(c3, c3, kernel_size=3, stride=2, padding=1)
+        self.conv2 = Conv(c4, c4, kernel_size=3, stride=2, padding=1)
+        self.channels = (c3, c4, c5)
+
+    def alloc(self, P, b, h3, w3):
+        """Concat buffers of yolov8_neck.py:76-92; returns the slices the backbone must fill."""
+        c3, c4, c5 = self.channels
+        h4, w4, h5, w5 = h3 // 2, w3 // 2, h3 // 4, w3 // 4
+        cat1 = P.buf(b, h4, w4, c5 + c4)        # [up(P5) | P4]
+        cat2 = P.buf(b, h3, w3, c4 + c3)        # [up(res2) | P3]
+        cat3 = P.buf(b, h4, w4, c3 + c4)        # [conv1(out1) | res2]
+        cat4 = P.buf(b, h5, w5, c4 + c5)        # [conv2(out2) | P5]
+        self.__dict__["_cats"] = (cat1, cat2, cat3, cat4)
+        return cat2[..., c4:], cat1[..., c5:], cat4[..., c4:]
+
+    def emit(self, P):
+        c3, c4, c5 = self.channels
+        cat1, cat2, cat3, cat4 = self.__dict__.pop("_cats")
+        self.up.emit(P, cat4[..., c4:], cat1[..., :c5])
+        res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:])
+        self.up.emit(P, res2, cat2[..., :c4])
+        out1 = self.c2f_2.emit(P, cat2)
+        self.conv1.emit(P, out1, out=cat3[..., :c3])
+        out2 = self.c2f_3.emit(P, cat3)
+        self.conv2.emit(P, out2, out=cat4[..., :c4])
+        out3 = self.c2f_4.emit(P, cat4)
+        return out1, out2, out3
+
+    def forward(self, x_res_1, x_res_2, x):
+        def build(P, xs):
+            b, h3, w3, _ = xs[0].shape
+            dsts = self.alloc(P, b, h3, w3)
+            for d, s in zip(dsts, xs):
+                P.add((lambda d=d, s=s: d.copy_(s)))      # API adaptation for the stand-alone neck only
+            return self.emit(P)
+        return _run_standalone(self, (x_res_1, x_res_2, x), build)
+
+
+class Head(_Compiled):
+    def __init__(self, version, ch=16, num_classes=80):
+        super().__init__()
+        self.ch = ch
+        self.coordinates = self.ch * 4
+        self.num_classes = num_classes
+        self.no = self.coordinates + num_classes
+        self.stride = torch.zeros(3)                     # plain attribute, like the reference (:79)
+        d, w, r = yolo_params(version)
+        chans = (int(256 * w), int(512 * w), int(512 * w * r))
+
+        def branch(cin, cout):
+            return nn.Sequential(Conv(cin, cout, kernel_size=3, stride=1, padding=1),
+                                 Conv(cout, cout, kernel_size=3, stride=1, padding=1),
+                                 nn.Conv2d(cout, cout, kernel_size=1, stride=1))
+
+        self.box = nn.ModuleList([branch(c, self.coordinates) for c in chans])
+        self.cls = nn.ModuleList([branch(c, num_classes) for c in chans])
+        self.dfl = DFL()                                  # the reference ignores `ch` here too (:113)
+
+    def emit(self, P, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """-> 3 fp32 raw tensors [B,H,W,64+nc] (box | cls), yolov8_head.py:119-122."""
+        if self.ch != 16:
+            raise RuntimeError("DFL is fixed to 16 bins (the reference builds DFL() with its default ch)")
+        raws = []
+        for i, f in enumerate(feats):
+            b, h, w, _ = f.shape
+            raw = P.buf(b, h, w, self.no, dtype=torch.float32)
+            for seq, lo, hi in ((self.box[i], 0, self.coordinates), (self.cls[i], self.coordinates, self.no)):
+                t = seq[0].emit(P, f)
+                t = seq[1].emit(P, t)
+                last = seq[2]
+                wl = pack_weight(last.weight.detach().float())
+                bl = last.bias.detach().float().contiguous()
+                P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False)
+            raws.append(raw)
+        return raws
+
+    def _stride_list(self):
+        st = self.stride
+        key = (id(st), getattr(st, "_version", 0))
+        cached = self.__dict__.get("_stride_cache")
+        if cached is None or cached[0] != key:
+            vals = [float(v) for v in (st.tolist() if torch.is_tensor(st) else st)]
+            cached = (key, vals)
+            self.__dict__["_stride_cache"] = cached
+        return cached[1]
+
+    def decode(self, raws):
+        return ops.head_decode(raws, self._stride_list(), self.num_classes)
+
+    def forward(self, x):
+        raws = _run_standalone(self, tuple(x), lambda P, xs: tuple(self.emit(P, xs)), raw_out=True)
+        if self.training:
+            return [r.permute(0, 3, 1, 2) for r in raws]
+        return self.decode([r.contiguous() for r in raws])
+
+
+class YOLOv8(_Compiled):
+    """yolov8/yolov8.py:8-31.  eval: [B, A, 4+nc] fp32; train: list of 3 raw [B, 64+nc, H, W]."""
+
+    def __init__(self, version: str, num_classes: int, dfl_ch: int = 16, block: str = "c2f"):
+        super().__init__()
+        self.backbone = Backbone(version, block=block)
+        self.neck = Neck(version, block=block)
+        self.head = Head(version=version, num_classes=num_classes, ch=dfl_ch)
+
+    def _build(self, P, xs):
+        img = xs[0]
+        b, _, h, w = img.shape
+        outs = self.neck.alloc(P, b, h // 8, w // 8)
+        ps = self.backbone.emit(P, img, outs=outs)
+        feats = self.neck.emit(P)
+        self.__dict__["_taps"] = {"p": ps, "n": feats}      # NHWC bf16 views, for the parity tests
+        return tuple(self.head.emit(P, feats))
+
+    def forward_raw(self, x):
+        """Run the network; returns the program's static fp32 raw head buffers [B,H,W,64+nc]."""
+        prog, io = _get_program(self, (x,), self._build, image_input=True)
+        io["inputs"][0].copy_(x)
+        prog.run()
+        return io["outputs"]
+
+    def forward(self, x):
+        raws = self.forward_raw(x)
+        if self.head.training:
+            return [r.permute(0, 3, 1, 2).clone() for r in raws]
+        return self.head.decode(raws)
+
+    @torch.no_grad()
+    def detect(self, x, conf_thresh: float = 0.25, iou_thresh: float = 0.45):
+        """Fused forward + decode + class-aware NMS (the reference's tools/test.py:160-218 per
+        batch).  Returns (boxes [B,A,4], scores [B,A], labels [B,A], keep [B,A], count [B])."""
+        raws = self.forward_raw(x)
+        pred, (boxes, scores, labels) = ops.head_decode(raws, self.head._stride_list(), self.head.num_classes,
+                                                        with_candidates=True)
+        keep, count = ops.nms_batched(boxes, scores, labels, conf_thresh, iou_thresh, self.head.num_classes)
+        return boxes, scores, labels, keep, count
+
+
+# =============================================================================================
+# program cache
+# =============================================================================================
+def _get_program(module: _Compiled, xs: Tuple[torch.Tensor, ...], build, image_input=False):
+    for x in xs:
+        if not torch.is_tensor(x) or not x.is_cuda:
+            raise YmsError("yolo_ms_b200 modules run on CUDA tensors only (no CPU fallback)")
+    dev = xs[0].device
+    if _device_of(module) != dev:
+        raise YmsError("module parameters and input live on different devices")
+    key = tuple(tuple(x.shape) for x in xs) + (str(dev),)
+    cache = module._programs()
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    with torch.no_grad():
+        P = Program(dev)
+        if image_input:
+            ins = [torch.empty(tuple(x.shape), dtype=torch.float32, device=dev) for x in xs]
+        else:
+            ins = [torch.empty((x.shape[0], x.shape[2], x.shape[3], x.shape[1]), dtype=torch.bfloat16, device=dev) for x in xs]
+        P.hold(*ins)
+        outs = build(P, ins)
+        P.capture()
+    hit = (P, {"inputs": ins, "outputs": list(outs)})
+    cache[key] = hit
+    return hit
+
+
+def _run_standalone(module, xs, build, raw_out=False):
+    """Stand-alone sub-module call with the reference's NCHW fp32 tensors at the boundary."""
+    prog, io = _get_program(module, tuple(xs), build)
+    for dst, x in zip(io["inputs"], xs):
+        dst.copy_(x.permute(0, 2, 3, 1))
+    prog.run()
+    if raw_out:
+        return io["outputs"]
+    return tuple(nhwc_to_nchw_f32(t) for t in io["outputs"])
