@@ -168,10 +168,24 @@ def dump_nms():
     np.savez_compressed(os.path.join(GOLD, "nms_cases.npz"), **out)
 
 
+def dump_bn_fixtures():
+    """BN running statistics of the calibrated synthetic weights (seed 1) for bench.py / smoke():
+    yolo_ms_b200/synth_bn/bn_{version}_{block}_seed1.npz."""
+    from yolo_ms_b200 import synth
+    os.makedirs(synth.BN_DIR, exist_ok=True)
+    for v in ("n", "s", "m"):
+        for blk in ("c2f", "ms"):
+            sd = W.calibrated_state_dict(v, seed=1, block=blk)
+            stats = {k: t.numpy() for k, t in sd.items() if k.endswith(("running_mean", "running_var"))}
+            np.savez_compressed(synth.bn_fixture_path(v, blk, 1), **stats)
+            print("bn fixture", v, blk, len(stats))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     dump_manifests()
+    dump_bn_fixtures()
     dump_model("n", 2, 64, 96, seed=1)
     dump_model("s", 1, 64, 64, seed=2)
     dump_post()

@@ -44,6 +44,7 @@ class Program:
         self.plans: List[ops.ConvPlan] = []
         self._keep: list = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.eager_prefix = 0          # leading steps that read caller-owned memory: never captured
         self.launches = 0
         self.flops = 0.0
         self.bytes = 0.0
@@ -80,7 +81,7 @@ class Program:
             s()
 
     def capture(self):
-        """Warm up once, then capture the step list into a CUDA graph."""
+        """Warm up once, then capture steps[eager_prefix:] into a CUDA graph."""
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -88,11 +89,14 @@ class Program:
         torch.cuda.current_stream(self.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run_eager()
+            for s in self.steps[self.eager_prefix:]:
+                s()
         self.graph = g
 
     def run(self):
         if self.graph is not None:
+            for s in self.steps[:self.eager_prefix]:
+                s()
             self.graph.replay()
         else:
             self.run_eager()

@@ -300,9 +300,10 @@ class Backbone(_Compiled):
         self.sppf = SPPF(c5, c5, kernel_size=5)
         self.out_channels = (c3, c4, c5)
 
-    def emit(self, P, image_nchw, outs=(None, None, None)):
-        """image_nchw: the static f32 NCHW input tensor.  outs: optional destination views."""
-        b, cin, h, w = image_nchw.shape
+    def emit(self, P, image, outs=(None, None, None)):
+        """image: ImageSlot holding the caller's f32 NCHW tensor (read in place by the stem kernel,
+        which therefore stays outside the CUDA graph).  outs: optional destination views."""
+        b, cin, h, w = image.shape
         if cin != 3:
             raise YmsError("Backbone: the stem kernel expects 3 input channels")
         if h % 32 or w % 32:
@@ -311,8 +312,10 @@ class Backbone(_Compiled):
         w0, b0 = w0.contiguous(), b0.contiguous()
         y0 = P.buf(b, h // 2, w // 2, self.conv0.conv.out_channels)
         P.hold(w0, b0)
-        P.add(lambda: ops.stem_conv(image_nchw, w0, b0, y0), nbytes=4.0 * image_nchw.numel() + 2.0 * y0.numel(),
+        assert not P.steps, "the stem must be the first step of the program"
+        P.add(lambda: ops.stem_conv(image.tensor, w0, b0, y0), nbytes=4.0 * b * cin * h * w + 2.0 * y0.numel(),
               flops=2.0 * y0.numel() * 27)
+        P.eager_prefix = 1
         x = self.conv1.emit(P, y0)
         x = self.c2f_2.emit(P, x)
         x = self.conv3.emit(P, x)
@@ -326,7 +329,7 @@ class Backbone(_Compiled):
 
     def forward(self, x):
         prog, io = _get_program(self, (x,), lambda P, xs: self.emit(P, xs[0]), image_input=True)
-        io["inputs"][0].copy_(x)
+        io["inputs"][0].bind(x)
         prog.run()
         return tuple(nhwc_to_nchw_f32(t) for t in io["outputs"])
 
@@ -459,7 +462,7 @@ class YOLOv8(_Compiled):
     def forward_raw(self, x):
         """Run the network; returns the program's static fp32 raw head buffers [B,H,W,64+nc]."""
         prog, io = _get_program(self, (x,), self._build, image_input=True)
-        io["inputs"][0].copy_(x)
+        io["inputs"][0].bind(x)
         prog.run()
         return io["outputs"]
 
@@ -483,6 +486,19 @@ class YOLOv8(_Compiled):
 # =============================================================================================
 # program cache
 # =============================================================================================
+class ImageSlot:
+    """The caller's NCHW fp32 image batch, rebound on every call (no staging copy)."""
+
+    def __init__(self, x: torch.Tensor):
+        self.shape = tuple(x.shape)
+        self.tensor = None
+        self.bind(x)
+
+    def bind(self, x: torch.Tensor):
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        self.tensor = x
+
 def _get_program(module: _Compiled, xs: Tuple[torch.Tensor, ...], build, image_input=False):
     for x in xs:
         if not torch.is_tensor(x) or not x.is_cuda:
@@ -498,10 +514,11 @@ def _get_program(module: _Compiled, xs: Tuple[torch.Tensor, ...], build, image_i
     with torch.no_grad():
         P = Program(dev)
         if image_input:
-            ins = [torch.empty(tuple(x.shape), dtype=torch.float32, device=dev) for x in xs]
+            ins = [ImageSlot(x) for x in xs]
         else:
             ins = [torch.empty((x.shape[0], x.shape[2], x.shape[3], x.shape[1]), dtype=torch.bfloat16, device=dev) for x in xs]
-        P.hold(*ins)
+        if not image_input:
+            P.hold(*ins)
         outs = build(P, ins)
         P.capture()
     hit = (P, {"inputs": ins, "outputs": list(outs)})
