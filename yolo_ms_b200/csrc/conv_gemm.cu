@@ -16,8 +16,9 @@
 //   * persistent CTAs (one per SM), static round-robin tile scheduler, warp-specialised:
 //       warp 0     TMA producer            (smem full/empty mbarrier ring, 3..8 stages)
 //       warp 1     tcgen05.mma issuer      (one elected lane), owns the TMEM allocation
-//       warps 2-5  epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> swizzled smem
-//                  -> TMA store (or direct fp32 stores for the head's raw logits)
+//       warps 2-9  epilogue (2 warps per TMEM lane quadrant, 32 columns each per 64-column chunk):
+//                  tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> swizzled smem -> TMA store
+//                  (or direct fp32 stores for the head's raw logits)
 //     two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "common.cuh"
 
@@ -35,7 +36,9 @@ constexpr int kBlockK = 64;                    // bf16 channels per k-block = on
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kStageOutBytes = kBlockM * 128;           // 16 KB epilogue staging (64 bf16 ch per row)
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                // TMEM columns between the two accumulator stages
 constexpr int kSmemLimit = 232448;             // 227 KB
@@ -151,7 +154,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+// SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op per element (tanh.approx.f32, abs err 2^-11)
+__device__ __forceinline__ float silu_from_half(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(=1024 B: 8 rows x 128 B)>>4 <<32 | 1<<46 | SW128(2)<<61
@@ -203,11 +212,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         if (!p.out_f32) prefetch_tmap(&tm_y);
         if (p.has_res) prefetch_tmap(&tm_res);
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); mbar_init(res_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); mbar_init(res_bar(s), 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    for (int i = threadIdx.x; i < p.bias_pad; i += kThreads) s_bias[i] = (i < p.c_out) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.bias_pad; i += kThreads) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -280,13 +289,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 2..9) =================
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                  // which 32 columns of every 64-column chunk
         const int row = quad * 32 + lane;                  // tile row == accumulator lane
         const bool leader = (threadIdx.x == 64);
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t chunk_ctr = 0;
-        uint32_t res_phase[2] = {0u, 0u};
+        uint32_t res_phase0 = 0u, res_phase1 = 0u;
         const int n_chunks = (p.block_n + 63) >> 6;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t);
@@ -295,16 +305,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride);
             // fp32 path: this thread's output pixel
-            const int lty = row / p.tw, ltx = row - lty * p.tw;
-            const bool row_ok = (row < p.tw * p.th) && (tc.x0 + ltx < p.out_w) && (tc.y0 + lty < p.out_h);
             float* yrow = nullptr;
-            if (p.out_f32 && row_ok)
-                yrow = p.y_f32 + ((size_t)((size_t)tc.img * p.out_h + tc.y0 + lty) * p.out_w + tc.x0 + ltx) * p.y_ps;
-
+            if (p.out_f32) {
+                const int lty = row / p.tw, ltx = row - lty * p.tw;
+                if ((row < p.tw * p.th) && (tc.x0 + ltx < p.out_w) && (tc.y0 + lty < p.out_h))
+                    yrow = p.y_f32 + ((size_t)((size_t)tc.img * p.out_h + tc.y0 + lty) * p.out_w + tc.x0 + ltx) * p.y_ps;
+            }
             for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
                 const int buf = chunk_ctr & 1u;
                 const uint32_t s_out = smem_out0 + buf * kStageOutBytes;
                 const int cbase = ch * 64;                           // column inside the N tile
+                const int c0 = cbase + half * 32;
+                const bool active = c0 < p.block_n;                  // warp-uniform
                 if (!p.out_f32) {
                     if (leader) tma_store_wait_read<1>();           // staging buffer `buf` no longer being read
                     epi_bar_sync();
@@ -313,28 +325,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                             mbar_expect_tx(res_bar(buf), a_bytes);
                             tma_load_4d(s_out, &tm_res, res_bar(buf), n0 + cbase, tc.x0, tc.y0, tc.img);
                         }
-                        mbar_wait(res_bar(buf), res_phase[buf]);
-                        res_phase[buf] ^= 1u;
+                        const uint32_t ph = buf ? res_phase1 : res_phase0;
+                        mbar_wait(res_bar(buf), ph);
+                        if (buf) res_phase1 ^= 1u; else res_phase0 ^= 1u;
                     }
                 }
-                #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int c0 = cbase + half * 32;
-                    if (c0 >= p.block_n) break;
-                    uint32_t v[32];
+                uint32_t v[32];
+                if (active) {
                     tmem_ld32(t_row + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (ch == n_chunks - 1 && (half == 1 || c0 + 32 >= p.block_n)) {
-                        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(acc));
-                    }
+                }
+                if (ch == n_chunks - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                if (active) {
                     float f[32];
-                    #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]) + s_bias[n0 + c0 + j];
-                        f[j] = p.act ? silu_f(x) : x;
+                    const float4* bq = reinterpret_cast<const float4*>(s_bias + n0 + c0);
+                    if (p.act) {
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 hb = bq[j];                 // 0.5 * bias
+                            f[4 * j + 0] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 0]), 0.5f, hb.x));
+                            f[4 * j + 1] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, hb.y));
+                            f[4 * j + 2] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, hb.z));
+                            f[4 * j + 3] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, hb.w));
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = bq[j];
+                            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+                            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+                            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                        }
                     }
                     if (p.out_f32) {
                         if (yrow) {
