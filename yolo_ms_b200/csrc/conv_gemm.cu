@@ -20,11 +20,10 @@
 //                  tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> swizzled smem -> TMA store
 //                  (or direct fp32 stores for the head's raw logits)
 //     two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-#include "common.cuh"
+#include "conv_plan.h"
 
-#include <cuda.h>
-#include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -32,141 +31,14 @@ namespace yms {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                    // bf16 channels per k-block = one 128 B swizzle row
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kStageOutBytes = kBlockM * 128;           // 16 KB epilogue staging (64 bf16 ch per row)
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
+using namespace tc;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                // TMEM columns between the two accumulator stages
 constexpr int kSmemLimit = 232448;             // 227 KB
-
-struct ConvKernelParams {
-    int tiles_x, tiles_y, batch;               // M tiling (output space)
-    int tw, th;                                // output pixels per tile (tw*th <= 128)
-    int out_w, out_h;
-    int n_tiles, block_n, c_out;
-    int kb1, kb2, c_in1, c_in2;                // 64-channel blocks per tap of source 1 / 2
-    int taps, ksize, stride;
-    int act, out_f32, has_res;
-    int num_stages, total_tiles;
-    int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
-    const float* bias;
-    float* y_f32; long long y_ps;
-};
-
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-// Bounded wait: a protocol bug must fault the launch (trap) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-// SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op per element (tanh.approx.f32, abs err 2^-11)
-__device__ __forceinline__ float silu_from_half(float h) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
-// start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(=1024 B: 8 rows x 128 B)>>4 <<32 | 1<<46 | SW128(2)<<61
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 struct TileCoord { int n_tile, img, x0, y0; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int t) {
@@ -271,16 +143,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 for (int kb = 0; kb < kb_per_tap; ++kb, ++kbi) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+                    // warp-uniform descriptor arithmetic outside the elected region (uniform datapath)
+                    const int cvalid = (kb < p.kb1) ? (p.c_in1 - kb * kBlockK) : (p.c_in2 - (kb - p.kb1) * kBlockK);
+                    const int ksteps = cvalid >= kBlockK ? 4 : ((cvalid + 15) >> 4);
+                    const uint32_t sa = smem_a0 + stage * stage_bytes;
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + kATileBytes);
+                    const uint32_t first = kbi ? 1u : 0u;
+                    const bool last = (kbi == num_kb - 1);
                     if (elect_one()) {
-                        const int cvalid = (kb < p.kb1) ? (p.c_in1 - kb * kBlockK) : (p.c_in2 - (kb - p.kb1) * kBlockK);
-                        const int ksteps = cvalid >= kBlockK ? 4 : ((cvalid + 15) >> 4);
-                        const uint32_t sa = smem_a0 + stage * stage_bytes;
-                        const uint64_t adesc = make_sw128_desc(sa);
-                        const uint64_t bdesc = make_sw128_desc(sa + kATileBytes);
-                        for (int k = 0; k < ksteps; ++k)           // +32 B (16 bf16) along K inside the swizzle atom
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kbi | k) != 0);
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k) {              // +32 B (16 bf16) along K inside the swizzle atom
+                            if (k < ksteps) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : first);
+                        }
                         umma_commit(empty_bar(stage));             // smem slot free once these MMAs retire
-                        if (kbi == num_kb - 1) umma_commit(tfull_bar(acc));
+                        if (last) umma_commit(tfull_bar(acc));
                     }
                     __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
@@ -423,6 +300,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+}  // namespace
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     static bool tried = false;
@@ -451,20 +330,6 @@ int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* add
     return 0;
 }
 
-}  // namespace
-}  // namespace yms
-
-using namespace yms;
-
-struct yms_conv_plan {
-    CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_res;
-    ConvKernelParams kp;
-    int grid;
-    size_t smem;
-    double flops, bytes;
-};
-
-namespace {
 
 // activation tensor map: dims (c, X, Y, N); `flat` folds all pixels into X.
 int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, int h, int w, bool flat,
@@ -483,7 +348,11 @@ int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, in
     return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, what);
 }
 
-}  // namespace
+
+
+}  // namespace yms
+
+using namespace yms;
 
 extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** out) {
     if (!q || !out) return fail(YMS_E_ARG, "conv: null argument");
@@ -510,6 +379,13 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 
     yms_conv_plan* pl = new (std::nothrow) yms_conv_plan();
     if (!pl) return fail(YMS_E_ARG, "conv: out of host memory");
+    pl->kind = 0;
+    if (q->ksize == 3 && q->stride == 1 && q->out_dtype == YMS_DTYPE_BF16 && q->c_in2 == 0 && !getenv("YMS_CONV3_LEGACY")) {
+        int rc3 = conv3_plan_init(pl, q);
+        if (rc3) { delete pl; return rc3; }
+        *out = pl;
+        return 0;
+    }
     ConvKernelParams& kp = pl->kp;
     memset(&kp, 0, sizeof(kp));
     const int out_h = q->in_h / q->stride, out_w = q->in_w / q->stride;
@@ -602,6 +478,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 
 extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     if (!pl) return fail(YMS_E_ARG, "conv: null plan");
+    if (pl->kind == 1) return conv3_plan_run(pl, (cudaStream_t)stream);
     conv_gemm_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->tm_x, pl->tm_x2, pl->tm_w, pl->tm_y,
                                                                              pl->tm_res, pl->kp);
     return check_launch("conv_gemm_kernel");

@@ -1,0 +1,66 @@
+// Shared host-side plan structure and tensor-map encoding for the convolution kernels.
+#pragma once
+#include "tc_ptx.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+struct yms_conv_plan;
+
+namespace yms {
+
+constexpr int kBlockK = 64;                    // bf16 channels per k-block = one 128 B swizzle row
+
+struct ConvKernelParams {
+    int tiles_x, tiles_y, batch;               // M tiling (output space)
+    int tw, th;                                // output pixels per tile (tw*th <= 128)
+    int out_w, out_h;
+    int n_tiles, block_n, c_out;
+    int kb1, kb2, c_in1, c_in2;                // 64-channel blocks per tap of source 1 / 2
+    int taps, ksize, stride;
+    int act, out_f32, has_res;
+    int num_stages, total_tiles;
+    int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
+    const float* bias;
+    float* y_f32; long long y_ps;
+};
+
+
+// ---- 3x3 stride-1 halo kernel (conv3x3.cu) ----
+struct Conv3Params {
+    int tiles_x, tiles_y, batch;               // sub-tile grid (8 x th output pixels each)
+    int th;                                    // rows per sub-tile (<= 16)
+    int sub;                                   // sub-tiles (adjacent in x) per work item: 1 or 2
+    int super_x;                               // ceil(tiles_x / sub)
+    int out_w, out_h;
+    int n_tiles, block_n, c_out, c_in, kb;     // kb = 64-channel blocks of c_in
+    int act, has_res;
+    int a_stages, b_stages, resident;          // resident: all weights of the (single) N tile stay in smem
+    int acc_stages;                            // TMEM accumulator stages (2 if sub*block_n <= 256)
+    int total_items;
+    int bias_pad;
+    int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
+    uint32_t halo_bytes;                       // 10 * (th + 2) * 128
+    const float* bias;
+};
+
+int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, const char* what);
+int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, int h, int w, bool flat,
+               int box_x, int box_y, int estride, const char* what);
+
+int conv3_plan_init(::yms_conv_plan* pl, const yms_conv_params* q);   // conv3x3.cu
+int conv3_plan_run(const ::yms_conv_plan* pl, cudaStream_t stream);
+
+}  // namespace yms
+
+struct yms_conv_plan {
+    CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_res;
+    int kind;                   // 0: generic implicit GEMM, 1: 3x3 stride-1 halo kernel
+    yms::ConvKernelParams kp;
+    yms::Conv3Params k3;
+    int grid;
+    size_t smem;
+    double flops, bytes;
+};
+
