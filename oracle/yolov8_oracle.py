@@ -47,8 +47,10 @@ def conv_unit(sd, p, x, stride=1, act=True, residual=None, first=False):
         scale = sd[p + ".bn.weight"] / torch.sqrt(sd[p + ".bn.running_var"] + BN_EPS)
         wf = w * scale.view(-1, 1, 1, 1)
         bf = sd[p + ".bn.bias"] - sd[p + ".bn.running_mean"] * scale
-        if not (first or groups > 1):       # stem and depthwise kernels keep fp32 weights
+        if groups == 1:                     # tensor-core kernels: bf16 operands (the depthwise kernel keeps fp32 weights)
             wf = _bf16(wf)
+        if first:                           # the stem kernel converts the fp32 image to bf16 while gathering
+            x = _bf16(x)
         y = F.conv2d(x, wf, bf, stride, k // 2, 1, groups)
         y = F.silu(y) if act else y
         if residual is not None:

@@ -86,7 +86,7 @@ def test_conv_rejects_cpu_and_bad_shapes(ops):
                      torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV))
 
 
-@pytest.mark.parametrize("cout", [16, 32, 48])
+@pytest.mark.parametrize("cout", [16, 32, 48, 80])
 def test_stem_conv(ops, cout):
     g = torch.Generator().manual_seed(cout)
     x = torch.randn(2, 3, 64, 96, generator=g).to(DEV)
@@ -94,8 +94,12 @@ def test_stem_conv(ops, cout):
     b = (torch.randn(cout, generator=g) * 0.2).to(DEV)
     y = torch.empty(2, 32, 48, cout, device=DEV, dtype=torch.bfloat16)
     ops.stem_conv(x, w, b, y)
-    ref = F.silu(F.conv2d(x, w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    # tensor-core stem: image and weights are rounded to bf16 (fp32 accumulate)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    ref = F.silu(F.conv2d(bf(x), bf(w), b, stride=2, padding=1)).permute(0, 2, 3, 1)
     assert rel_l2(y, ref) < 4e-3
+    ref32 = F.silu(F.conv2d(x, w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert rel_l2(y, ref32) < 1e-2
 
 
 def test_sppf_pool_is_exact(ops):

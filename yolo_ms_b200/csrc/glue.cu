@@ -3,6 +3,8 @@
 // outputs land directly inside the channel slice of the concat buffer that consumes them.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace yms {
 namespace {
 
@@ -211,11 +213,16 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 using namespace yms;
 
+int yms_stem_tc_launch(const float* x, int batch, int in_h, int in_w, int c_out, const float* weight, const float* bias,
+                       void* y, int64_t y_ps, cudaStream_t stream);   // stem_tc.cu (tensor-core path)
+
 extern "C" int yms_stem_conv(const float* x, int batch, int in_h, int in_w, int c_out, const float* weight,
                              const float* bias, void* y, int64_t y_ps, void* stream) {
     if (batch <= 0 || in_h <= 0 || in_w <= 0 || (in_h & 1) || (in_w & 1)) return fail(YMS_E_ARG, "stem: bad image size");
     if (c_out <= 0 || (c_out % 16) != 0 || c_out > 256) return fail(YMS_E_UNSUPPORTED, "stem: c_out must be a multiple of 16 (<= 256)");
     if (!x || !weight || !bias || !y || !aligned16(y) || (y_ps % 8) != 0) return fail(YMS_E_ARG, "stem: bad pointers/strides");
+    if (c_out <= 128 && !getenv("YMS_STEM_LEGACY"))
+        return yms_stem_tc_launch(x, batch, in_h, in_w, c_out, weight, bias, y, y_ps, (cudaStream_t)stream);
     dim3 grid(ceil_div(in_w / 2, 128), in_h / 2, batch);
     size_t smem = (size_t)28 * c_out * sizeof(float);
     stem_conv_kernel<16><<<grid, 128, smem, (cudaStream_t)stream>>>(x, in_h, in_w, c_out, weight, bias,

@@ -411,9 +411,14 @@ class Head(_Compiled):
         for i, f in enumerate(feats):
             b, h, w, _ = f.shape
             raw = P.buf(b, h, w, self.no, dtype=torch.float32)
+            # box[i][0] and cls[i][0] read the same feature map: ONE 3x3 conv with the two weight sets
+            # stacked along c_out (64 + nc) reads it once; the second convs take channel slices.
+            wb, bb = self.box[i][0].folded()
+            wc, bc = self.cls[i][0].folded()
+            first = P.buf(b, h, w, self.no)
+            P.conv(pack_weight(torch.cat([wb, wc], 0)), torch.cat([bb, bc]).contiguous(), f, first, ksize=3, stride=1, act=True)
             for seq, lo, hi in ((self.box[i], 0, self.coordinates), (self.cls[i], self.coordinates, self.no)):
-                t = seq[0].emit(P, f)
-                t = seq[1].emit(P, t)
+                t = seq[1].emit(P, first[..., lo:hi])
                 last = seq[2]
                 wl = pack_weight(last.weight.detach().float())
                 bl = last.bias.detach().float().contiguous()
