@@ -61,10 +61,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
     const int b_tile_bytes = p.block_n * 128;
-    const int stage_bytes = kATileBytes + ((b_tile_bytes + 1023) & ~1023);
+    const int b_tile_pad = (b_tile_bytes + 1023) & ~1023;
+    // streaming: stage = A tile + B tile; resident: stage = A tile only, all B tiles after the ring
+    const int stage_bytes = kATileBytes + (p.resident ? 0 : b_tile_pad);
+    const int kb_total_res = p.taps * (p.kb1 + p.kb2);
+    const int ring_bytes = p.num_stages * stage_bytes + (p.resident ? kb_total_res * b_tile_pad : 0);
     const uint32_t smem_a0 = base;                                   // stage s: A at base + s*stage_bytes, B after A
-    const uint32_t smem_out0 = base + p.num_stages * stage_bytes;     // 2 x 16 KB staging
-    unsigned char* g_out0 = gbase + p.num_stages * stage_bytes;
+    const uint32_t smem_bres = base + p.num_stages * stage_bytes;     // resident weight tiles
+    const uint32_t smem_out0 = base + ring_bytes;                     // 2 x 16 KB staging
+    unsigned char* g_out0 = gbase + ring_bytes;
     float* s_bias = reinterpret_cast<float*>(g_out0 + 2 * kStageOutBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
     const uint32_t bar0 = smem_u32(bars);
@@ -73,7 +78,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 2 + s); };
     auto res_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 4 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+    auto w_bar = [&]() { return bar0 + 8u * (2 * kMaxStages + 6); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 7);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -85,6 +91,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         if (p.has_res) prefetch_tmap(&tm_res);
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); mbar_init(res_bar(s), 1); }
+        mbar_init(w_bar(), 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -98,11 +105,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int num_kb = p.taps * kb_per_tap;
     const int pad = p.ksize >> 1;
     const uint32_t a_bytes = (uint32_t)(p.tw * p.th) * 128u;
-    const uint32_t stage_tx = a_bytes + (uint32_t)b_tile_bytes;
+    const uint32_t stage_tx = a_bytes + (p.resident ? 0u : (uint32_t)b_tile_bytes);
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
+            if (p.resident) {                                   // whole weight set once per persistent CTA
+                mbar_expect_tx(w_bar(), (uint32_t)kb_total_res * (uint32_t)b_tile_bytes);
+                for (int tap = 0; tap < p.taps; ++tap)
+                    for (int kb = 0; kb < kb_per_tap; ++kb)
+                        tma_load_3d(smem_bres + (tap * kb_per_tap + kb) * b_tile_pad, &tm_w, w_bar(),
+                                    kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, 0, tap);
+            }
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
@@ -118,10 +132,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                         mbar_expect_tx(full_bar(stage), stage_tx);
                         if (kb < p.kb1) {
                             tma_load_4d(sa, &tm_x, full_bar(stage), kb * kBlockK, xin, yin, tc.img);
-                            tma_load_3d(sb, &tm_w, full_bar(stage), kb * kBlockK, n0, tap);
+                            if (!p.resident) tma_load_3d(sb, &tm_w, full_bar(stage), kb * kBlockK, n0, tap);
                         } else {
                             tma_load_4d(sa, &tm_x2, full_bar(stage), (kb - p.kb1) * kBlockK, xin, yin, tc.img);
-                            tma_load_3d(sb, &tm_w, full_bar(stage), p.c_in1 + (kb - p.kb1) * kBlockK, n0, tap);
+                            if (!p.resident) tma_load_3d(sb, &tm_w, full_bar(stage), p.c_in1 + (kb - p.kb1) * kBlockK, n0, tap);
                         }
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                     }
@@ -132,6 +146,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         // ================= MMA issuer =================
         // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+        if (p.resident) { mbar_wait(w_bar(), 0u); tc_fence_after(); }
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -148,7 +163,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     const int ksteps = cvalid >= kBlockK ? 4 : ((cvalid + 15) >> 4);
                     const uint32_t sa = smem_a0 + stage * stage_bytes;
                     const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + kATileBytes);
+                    const uint64_t bdesc = make_sw128_desc(p.resident ? smem_bres + (uint32_t)kbi * b_tile_pad : sa + kATileBytes);
                     const uint32_t first = kbi ? 1u : 0u;
                     const bool last = (kbi == num_kb - 1);
                     if (elect_one()) {
@@ -431,13 +446,16 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     kp.y_ps = q->y_pixel_stride;
 
     const int b_bytes = (kp.block_n * 128 + 1023) & ~1023;
-    const int stage_bytes = kATileBytes + b_bytes;
     const int fixed = 2 * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 8) * 8 + 1024 /* alignment slack */;
-    int stages = (kSmemLimit - fixed) / stage_bytes;
+    const int res_bytes = kp.taps * (kp.kb1 + kp.kb2) * b_bytes;
+    // small weight sets stay resident for the whole persistent CTA (no per-tile re-fetch from L2)
+    kp.resident = (kp.n_tiles == 1 && !getenv("YMS_CONV_STREAM") && kSmemLimit - fixed - res_bytes >= 4 * kATileBytes) ? 1 : 0;
+    const int stage_bytes = kATileBytes + (kp.resident ? 0 : b_bytes);
+    int stages = (kSmemLimit - fixed - (kp.resident ? res_bytes : 0)) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { delete pl; return fail(YMS_E_UNSUPPORTED, "conv: tile does not fit in shared memory"); }
     kp.num_stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + fixed;
+    pl->smem = (size_t)stages * stage_bytes + (kp.resident ? res_bytes : 0) + fixed;
     pl->grid = kp.total_tiles < kNumSMs ? kp.total_tiles : kNumSMs;
 
     int rc;

@@ -20,6 +20,7 @@ struct ConvKernelParams {
     int taps, ksize, stride;
     int act, out_f32, has_res;
     int num_stages, total_tiles;
+    int resident;                              // all weight tiles of the (single) N tile stay in smem
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
     const float* bias;
     float* y_f32; long long y_ps;
