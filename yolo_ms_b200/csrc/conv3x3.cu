@@ -30,17 +30,16 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads3 = 64 + kEpiThreads;
+constexpr int kThreads3 = kConvThreads;
 constexpr int kHaloPitch = 10;                         // lines (pixels) per halo row
 constexpr int kHaloStageBytes = 23552;                 // 180 lines = 23040 B, rounded up to 1024
-constexpr int kStageOut = 16384;
 constexpr int kRing = 8;                               // max ring depth (barrier array size)
 constexpr int kSmemLimit3 = 232448;
 
 // barrier slots
 constexpr int kBarAFull = 0, kBarAEmpty = kRing, kBarBFull = 2 * kRing, kBarBEmpty = 3 * kRing;
-constexpr int kBarTFull = 4 * kRing, kBarTEmpty = 4 * kRing + 2, kBarRes = 4 * kRing + 4, kBarW = 4 * kRing + 6;
-constexpr int kNumBars = 4 * kRing + 8;
+constexpr int kBarTFull = 4 * kRing, kBarTEmpty = 4 * kRing + 4, kBarRes = 4 * kRing + 8, kBarW = 4 * kRing + 12;
+constexpr int kNumBars = 4 * kRing + 14;
 
 __device__ __forceinline__ uint64_t make_a_desc(uint32_t addr, int desc_mode) {
     uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) |
@@ -52,11 +51,14 @@ __device__ __forceinline__ uint64_t make_a_desc(uint32_t addr, int desc_mode) {
 struct Item { int n_tile, img, sx, ty; };
 __device__ __forceinline__ Item decode_item(const Conv3Params& p, int t) {
     Item it;
-    it.n_tile = t % p.n_tiles;
-    int m = t / p.n_tiles;
-    it.sx = m % p.super_x; m /= p.super_x;
-    it.ty = m % p.tiles_y;
-    it.img = m / p.tiles_y;
+    uint32_t m = fast_div((uint32_t)t, p.mg_n_tiles);
+    it.n_tile = t - (int)m * p.n_tiles;
+    uint32_t q = fast_div(m, p.mg_super_x);
+    it.sx = (int)(m - q * p.super_x);
+    m = q;
+    q = fast_div(m, p.mg_tiles_y);
+    it.ty = (int)(m - q * p.tiles_y);
+    it.img = (int)q;
     return it;
 }
 
@@ -74,7 +76,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const uint32_t smem_b = base + a_region;
     const uint32_t smem_out0 = smem_b + b_region;
     unsigned char* g_out0 = gbase + a_region + b_region;
-    float* s_bias = reinterpret_cast<float*>(g_out0 + 2 * kStageOut);
+    float* s_bias = reinterpret_cast<float*>(g_out0 + kEpiGroups * kStageOutBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int slot) { return bar0 + 8u * slot; };
@@ -90,7 +92,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             mbar_init(bar(kBarAFull + s), 1); mbar_init(bar(kBarAEmpty + s), 1);
             mbar_init(bar(kBarBFull + s), 1); mbar_init(bar(kBarBEmpty + s), 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarTFull + s), 1); mbar_init(bar(kBarTEmpty + s), kEpiWarps); mbar_init(bar(kBarRes + s), 1); }
+        for (int s = 0; s < kEpiGroups; ++s) { mbar_init(bar(kBarTFull + s), 1); mbar_init(bar(kBarTEmpty + s), 4 * (kEpiGroups / p.acc_stages)); mbar_init(bar(kBarRes + s), 1); }
         mbar_init(bar(kBarW), 1);
         fence_barrier_init();
     }
@@ -101,6 +103,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t out_bytes = (uint32_t)(8 * p.th) * 128u;
+    const int acc_stride = 512 / p.acc_stages;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -149,7 +152,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
             mbar_wait(bar(kBarTEmpty + acc), acc_phase ^ 1u);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
             for (int cb = 0; cb < p.kb; ++cb) {
                 mbar_wait(bar(kBarAFull + as), aph);
                 tc_fence_after();
@@ -213,112 +216,43 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
-        // ================= epilogue (warps 2..9) =================
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int row = quad * 32 + lane;
-        const bool leader = (threadIdx.x == 64);
-        int acc = 0; uint32_t acc_phase = 0;
-        uint32_t chunk_ctr = 0;
-        uint32_t res_phase0 = 0u, res_phase1 = 0u;
-        const int n_chunks = (p.block_n + 63) >> 6;
-        for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
-            const Item it = decode_item(p, t);
-            const int n0 = it.n_tile * p.block_n;
-            const int y0 = it.ty * p.th;
-            mbar_wait(bar(kBarTFull + acc), acc_phase);
-            tc_fence_after();
-            bool released = false;
-            for (int s = 0; s < p.sub; ++s) {
-                const int x0 = (it.sx * p.sub + s) * 8;
-                if (x0 >= p.out_w) continue;                         // sub-tile entirely outside the image
-                const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + s * p.block_n);
-                for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-                    const int buf = chunk_ctr & 1u;
-                    const uint32_t s_out = smem_out0 + buf * kStageOut;
-                    const int cbase = ch * 64;
-                    const int c0 = cbase + half * 32;
-                    const bool active = c0 < p.block_n;
-                    if (leader) tma_store_wait_read<1>();
-                    epi_bar_sync();
-                    if (p.has_res) {
-                        if (leader) {
-                            mbar_expect_tx(bar(kBarRes + buf), out_bytes);
-                            tma_load_4d(s_out, &tm_res, bar(kBarRes + buf), n0 + cbase, x0, y0, it.img);
-                        }
-                        const uint32_t ph = buf ? res_phase1 : res_phase0;
-                        mbar_wait(bar(kBarRes + buf), ph);
-                        if (buf) res_phase1 ^= 1u; else res_phase0 ^= 1u;
-                    }
-                    uint32_t v[32];
-                    if (active) {
-                        tmem_ld32(t_row + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                    }
-                    if (s == p.sub - 1 && ch == n_chunks - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(kBarTEmpty + acc));
-                        released = true;
-                    }
-                    if (active) {
-                        float f[32];
-                        const float4* bq = reinterpret_cast<const float4*>(s_bias + n0 + c0);
-                        if (p.act) {
-                            #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 hb = bq[j];
-                                f[4 * j + 0] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 0]), 0.5f, hb.x));
-                                f[4 * j + 1] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, hb.y));
-                                f[4 * j + 2] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, hb.z));
-                                f[4 * j + 3] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, hb.w));
-                            }
-                        } else {
-                            #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 b4 = bq[j];
-                                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-                            }
-                        }
-                        const uint32_t line = s_out + (uint32_t)row * 128u;
-                        #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t chunk16 = (uint32_t)(half * 4 + q);
-                            const uint32_t addr = line + ((chunk16 ^ (uint32_t)(row & 7)) << 4);
-                            if (p.has_res) {
-                                uint32_t r0, r1, r2, r3;
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-                                f[q * 8 + 0] += bf16_lo(r0); f[q * 8 + 1] += bf16_hi(r0);
-                                f[q * 8 + 2] += bf16_lo(r1); f[q * 8 + 3] += bf16_hi(r1);
-                                f[q * 8 + 4] += bf16_lo(r2); f[q * 8 + 5] += bf16_hi(r2);
-                                f[q * 8 + 6] += bf16_lo(r3); f[q * 8 + 7] += bf16_hi(r3);
-                            }
-                            const uint32_t o0 = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                            const uint32_t o1 = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                            const uint32_t o2 = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                            const uint32_t o3 = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    epi_bar_sync();
-                    if (leader) {
-                        tma_store_4d(&tm_y, s_out, n0 + cbase, x0, y0, it.img);
-                        tma_store_commit();
-                    }
+        // ================= epilogue: up to 4 groups of 4 warps, group e drains accumulator stage e =================
+        const int grp = (warp - 2) >> 2;
+        const int gps = kEpiGroups / p.acc_stages;         // groups sharing one accumulator stage
+        const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        {
+            EpiShared e;
+            e.tm_y = &tm_y; e.tm_res = &tm_res;
+            e.res_bar = bar(kBarRes + grp);
+            e.s_out = smem_out0 + grp * kStageOutBytes;
+            e.s_bias = s_bias;
+            e.block_n = p.block_n; e.c_out = p.c_out; e.act = p.act; e.has_res = p.has_res;
+            e.out_bytes = out_bytes;
+            e.bar_id = 1 + grp;
+            e.leader = ((warp - 2) & 3) == 0 && lane == 0;
+            e.row = (warp & 3) * 32 + lane;
+            const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(stage_id * acc_stride);
+            const int n_chunks = (p.block_n + 63) >> 6;
+            uint32_t res_phase = 0u, acc_phase = 0u;
+            for (int t = blockIdx.x + stage_id * gridDim.x; t < p.total_items; t += p.acc_stages * gridDim.x) {
+                const Item it = decode_item(p, t);
+                mbar_wait(bar(kBarTFull + stage_id), acc_phase);
+                acc_phase ^= 1u;
+                tc_fence_after();
+                int unit = 0;                                        // (sub-tile, chunk) units dealt round-robin to the groups
+                for (int sidx = 0; sidx < p.sub; ++sidx) {
+                    EpiTile tl;
+                    tl.n0 = it.n_tile * p.block_n; tl.x0 = (it.sx * p.sub + sidx) * 8; tl.y0 = it.ty * p.th; tl.img = it.img;
+                    if (tl.x0 >= p.out_w) continue;                  // sub-tile entirely outside the image
+                    for (int ch = 0; ch < n_chunks; ++ch, ++unit)
+                        if (unit % gps == sub_id) epilogue_chunk_bf16(e, res_phase, t_lane + (uint32_t)(sidx * p.block_n), tl, ch);
                 }
-            }
-            if (!released) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarTEmpty + acc));
+                if (lane == 0) mbar_arrive(bar(kBarTEmpty + stage_id));
             }
-            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+            if (e.leader) tma_store_wait_read<0>();
         }
-        if (leader) tma_store_wait_read<0>();
     }
 
     tc_fence_before();
@@ -360,7 +294,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.desc_mode = dm ? atoi(dm) : 0;
 
     const int b_tile = (k.block_n * 128 + 1023) & ~1023;
-    const int fixed = 2 * kStageOut + k.bias_pad * 4 + kNumBars * 8 + 16 + 1024;
+    const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16 + 1024;
     const int resident_bytes = 9 * k.kb * b_tile;
     const char* force_stream = getenv("YMS_CONV3_STREAM");
     k.resident = (k.n_tiles == 1 && kSmemLimit3 - fixed - resident_bytes >= 2 * kHaloStageBytes && !force_stream) ? 1 : 0;
@@ -382,9 +316,10 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     }
     if (k.a_stages > kRing) k.a_stages = kRing;
     if (k.a_stages < 2) return fail(YMS_E_UNSUPPORTED, "conv3x3: tile does not fit in shared memory");
-    k.acc_stages = (k.sub * k.block_n <= 256) ? 2 : 1;
+    k.acc_stages = (k.sub * k.block_n <= 128) ? 4 : ((k.sub * k.block_n <= 256) ? 2 : 1);
     k.super_x = ceil_div(k.tiles_x, k.sub);
     k.total_items = k.super_x * k.tiles_y * k.batch * k.n_tiles;
+    k.mg_n_tiles = fast_div_magic(k.n_tiles); k.mg_super_x = fast_div_magic(k.super_x); k.mg_tiles_y = fast_div_magic(k.tiles_y);
     pl->grid = k.total_items < kNumSMs ? k.total_items : kNumSMs;
     pl->smem = (size_t)k.a_stages * k.sub * kHaloStageBytes + (size_t)(k.resident ? resident_bytes : k.b_stages * b_tile) + fixed;
 

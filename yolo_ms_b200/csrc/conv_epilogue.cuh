@@ -1,0 +1,137 @@
+// Shared epilogue of the tcgen05 convolution kernels.
+//
+// The epilogue of one tile is a latency chain (wait accumulator -> tcgen05.ld -> bias/SiLU ->
+// swizzled smem -> fence -> TMA store); ncu showed the MMA/TMA side idle behind it on the small-N,
+// high-resolution layers.  It is therefore run by up to kEpiGroups independent groups of 4 warps
+// (one warp per TMEM lane quadrant), group e working on accumulator stage e with its own staging
+// buffer, named barrier and TMA-store bulk groups, so that several tiles drain concurrently.
+#pragma once
+#include "tc_ptx.cuh"
+
+namespace yms {
+namespace tc {
+
+constexpr int kEpiGroups = 4;
+constexpr int kEpiGroupThreads = 128;
+constexpr int kConvThreads = 64 + kEpiGroups * kEpiGroupThreads;      // producer warp + MMA warp + 16 epilogue warps
+constexpr int kStageOutBytes = 128 * 128;                             // one 128-row x 64-channel bf16 staging tile
+
+struct EpiTile { int n0, x0, y0, img; };
+
+struct EpiShared {
+    const CUtensorMap* tm_y; const CUtensorMap* tm_res;
+    uint32_t res_bar;          // mbarrier of this group for the residual TMA load
+    uint32_t s_out;            // this group's staging buffer (1024-aligned)
+    const float* s_bias;       // bias (act: 0.5 * bias) in shared memory, indexed by output channel
+    int block_n, c_out, act, has_res;
+    uint32_t out_bytes;        // bytes of one residual / store box
+    int bar_id;                // named barrier of the group
+    bool leader;               // thread that issues the group's TMA traffic
+    int row;                   // accumulator lane == tile row of this thread
+};
+
+// bf16 output of ONE 64-channel chunk through swizzled staging + TMA store (+ residual TMA-loaded
+// into the same buffer).  Callers deal (sub-tile, chunk) units to the groups that share a stage.
+__device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t& res_phase, uint32_t t_row, const EpiTile& tl, int ch) {
+    {
+        const int cbase = ch * 64;
+        if (e.leader) tma_store_wait_read<0>();            // previous store of this group has left the staging buffer
+        group_bar_sync(e.bar_id);
+        if (e.has_res) {
+            if (e.leader) {
+                mbar_expect_tx(e.res_bar, e.out_bytes);
+                tma_load_4d(e.s_out, e.tm_res, e.res_bar, tl.n0 + cbase, tl.x0, tl.y0, tl.img);
+            }
+            mbar_wait(e.res_bar, res_phase);
+            res_phase ^= 1u;
+        }
+        const uint32_t line = e.s_out + (uint32_t)e.row * 128u;
+        #pragma unroll 1
+        for (int q16 = 0; q16 < 4; ++q16) {
+            const int c0 = cbase + q16 * 16;
+            if (c0 >= e.block_n) break;
+            uint32_t v[16];
+            tmem_ld16(t_row + (uint32_t)c0, v);
+            tmem_ld_wait();
+            float f[16];
+            const float4* bq = reinterpret_cast<const float4*>(e.s_bias + tl.n0 + c0);
+            if (e.act) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 hb = bq[j];                 // 0.5 * bias
+                    f[4 * j + 0] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 0]), 0.5f, hb.x));
+                    f[4 * j + 1] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, hb.y));
+                    f[4 * j + 2] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, hb.z));
+                    f[4 * j + 3] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, hb.w));
+                }
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b4 = bq[j];
+                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                }
+            }
+            #pragma unroll
+            for (int q = 0; q < 2; ++q) {                    // 16 columns = 2 x 16 B chunks of the swizzled 128 B line
+                const uint32_t addr = line + (((uint32_t)(q16 * 2 + q) ^ (uint32_t)(e.row & 7)) << 4);
+                if (e.has_res) {
+                    uint32_t r0, r1, r2, r3;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+                    f[q * 8 + 0] += bf16_lo(r0); f[q * 8 + 1] += bf16_hi(r0);
+                    f[q * 8 + 2] += bf16_lo(r1); f[q * 8 + 3] += bf16_hi(r1);
+                    f[q * 8 + 4] += bf16_lo(r2); f[q * 8 + 5] += bf16_hi(r2);
+                    f[q * 8 + 6] += bf16_lo(r3); f[q * 8 + 7] += bf16_hi(r3);
+                }
+                const uint32_t o0 = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                const uint32_t o1 = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                const uint32_t o2 = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                const uint32_t o3 = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+            }
+        }
+        fence_proxy_async_smem();                            // generic-proxy writes -> async proxy (TMA)
+        group_bar_sync(e.bar_id);
+        if (e.leader) {
+            tma_store_4d(e.tm_y, e.s_out, tl.n0 + cbase, tl.x0, tl.y0, tl.img);
+            tma_store_commit();
+        }
+    }
+}
+
+// fp32 output written directly (the head's raw logits): yrow = this thread's output pixel or nullptr.
+// Columns [c_begin, c_end) of the N tile (16-column steps) -- groups sharing a stage split the range.
+__device__ __forceinline__ void epilogue_tile_f32(const EpiShared& e, uint32_t t_row, const EpiTile& tl, float* yrow, int c_begin, int c_end) {
+    #pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const float* bq = e.s_bias + tl.n0 + c0;
+        if (yrow) {
+            #pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const int col = tl.n0 + c0 + j;
+                float f0 = __uint_as_float(v[j]), f1 = __uint_as_float(v[j + 1]), f2 = __uint_as_float(v[j + 2]), f3 = __uint_as_float(v[j + 3]);
+                if (e.act) {
+                    f0 = silu_from_half(fmaf(f0, 0.5f, bq[j])); f1 = silu_from_half(fmaf(f1, 0.5f, bq[j + 1]));
+                    f2 = silu_from_half(fmaf(f2, 0.5f, bq[j + 2])); f3 = silu_from_half(fmaf(f3, 0.5f, bq[j + 3]));
+                } else {
+                    f0 += bq[j]; f1 += bq[j + 1]; f2 += bq[j + 2]; f3 += bq[j + 3];
+                }
+                if (col + 3 < e.c_out) {
+                    *reinterpret_cast<float4*>(yrow + col) = make_float4(f0, f1, f2, f3);
+                } else {
+                    if (col < e.c_out) yrow[col] = f0;
+                    if (col + 1 < e.c_out) yrow[col + 1] = f1;
+                    if (col + 2 < e.c_out) yrow[col + 2] = f2;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace yms

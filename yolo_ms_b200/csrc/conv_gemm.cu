@@ -33,21 +33,22 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;      // 16 KB
-constexpr int kStageOutBytes = kBlockM * 128;           // 16 KB epilogue staging (64 bf16 ch per row)
 using namespace tc;
-constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kThreads = kConvThreads;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;                // TMEM columns between the two accumulator stages
 constexpr int kSmemLimit = 232448;             // 227 KB
 
 struct TileCoord { int n_tile, img, x0, y0; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int t) {
     TileCoord c;
-    c.n_tile = t % p.n_tiles;
-    int m = t / p.n_tiles;
-    int tx = m % p.tiles_x; m /= p.tiles_x;
-    int ty = m % p.tiles_y;
-    c.img = m / p.tiles_y;
+    uint32_t m = fast_div((uint32_t)t, p.mg_n_tiles);
+    c.n_tile = t - (int)m * p.n_tiles;
+    uint32_t q = fast_div(m, p.mg_tiles_x);
+    const int tx = (int)(m - q * p.tiles_x);
+    m = q;
+    q = fast_div(m, p.mg_tiles_y);
+    const int ty = (int)(m - q * p.tiles_y);
+    c.img = (int)q;
     c.x0 = tx * p.tw; c.y0 = ty * p.th;
     return c;
 }
@@ -70,16 +71,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t smem_bres = base + p.num_stages * stage_bytes;     // resident weight tiles
     const uint32_t smem_out0 = base + ring_bytes;                     // 2 x 16 KB staging
     unsigned char* g_out0 = gbase + ring_bytes;
-    float* s_bias = reinterpret_cast<float*>(g_out0 + 2 * kStageOutBytes);
+    float* s_bias = reinterpret_cast<float*>(g_out0 + kEpiGroups * kStageOutBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
-    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 2 + s); };
-    auto res_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 4 + s); };
-    auto w_bar = [&]() { return bar0 + 8u * (2 * kMaxStages + 6); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 7);
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 4 + s); };
+    auto res_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 8 + s); };
+    auto w_bar = [&]() { return bar0 + 8u * (2 * kMaxStages + 12); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 13);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -90,7 +91,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         if (!p.out_f32) prefetch_tmap(&tm_y);
         if (p.has_res) prefetch_tmap(&tm_res);
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); mbar_init(res_bar(s), 1); }
+        for (int s = 0; s < kEpiGroups; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * (kEpiGroups / p.acc_stages)); mbar_init(res_bar(s), 1); }
         mbar_init(w_bar(), 1);
         fence_barrier_init();
     }
@@ -105,6 +106,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int num_kb = p.taps * kb_per_tap;
     const int pad = p.ksize >> 1;
     const uint32_t a_bytes = (uint32_t)(p.tw * p.th) * 128u;
+    const int acc_stride = kTmemCols / p.acc_stages;
     const uint32_t stage_tx = a_bytes + (p.resident ? 0u : (uint32_t)b_tile_bytes);
 
     if (warp == 0) {
@@ -152,7 +154,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
             int kbi = 0;
             for (int tap = 0; tap < p.taps; ++tap) {
                 for (int kb = 0; kb < kb_per_tap; ++kb, ++kbi) {
@@ -178,130 +180,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
-        // ================= epilogue (warps 2..9) =================
-        const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;                  // which 32 columns of every 64-column chunk
-        const int row = quad * 32 + lane;                  // tile row == accumulator lane
-        const bool leader = (threadIdx.x == 64);
-        int acc = 0; uint32_t acc_phase = 0;
-        uint32_t chunk_ctr = 0;
-        uint32_t res_phase0 = 0u, res_phase1 = 0u;
-        const int n_chunks = (p.block_n + 63) >> 6;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(p, t);
-            const int n0 = tc.n_tile * p.block_n;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride);
-            // fp32 path: this thread's output pixel
-            float* yrow = nullptr;
-            if (p.out_f32) {
-                const int lty = row / p.tw, ltx = row - lty * p.tw;
-                if ((row < p.tw * p.th) && (tc.x0 + ltx < p.out_w) && (tc.y0 + lty < p.out_h))
-                    yrow = p.y_f32 + ((size_t)((size_t)tc.img * p.out_h + tc.y0 + lty) * p.out_w + tc.x0 + ltx) * p.y_ps;
+        // ================= epilogue: up to 4 groups of 4 warps, group e drains accumulator stage e =================
+        const int grp = (warp - 2) >> 2;
+        const int gps = kEpiGroups / p.acc_stages;         // groups sharing one accumulator stage
+        const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        {
+            EpiShared e;
+            e.tm_y = &tm_y; e.tm_res = &tm_res;
+            e.res_bar = res_bar(grp);
+            e.s_out = smem_out0 + grp * kStageOutBytes;
+            e.s_bias = s_bias;
+            e.block_n = p.block_n; e.c_out = p.c_out; e.act = p.act; e.has_res = p.has_res;
+            e.out_bytes = a_bytes;
+            e.bar_id = 1 + grp;
+            e.leader = ((warp - 2) & 3) == 0 && lane == 0;
+            e.row = (warp & 3) * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(stage_id * acc_stride);
+            const int n_chunks = (p.block_n + 63) >> 6;
+            uint32_t res_phase = 0u, acc_phase = 0u;
+            for (int t = blockIdx.x + stage_id * gridDim.x; t < p.total_tiles; t += p.acc_stages * gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                EpiTile tl; tl.n0 = tc.n_tile * p.block_n; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
+                mbar_wait(tfull_bar(stage_id), acc_phase);
+                acc_phase ^= 1u;
+                tc_fence_after();
+                if (p.out_f32) {
+                    const int lty = e.row / p.tw, ltx = e.row - lty * p.tw;
+                    float* yrow = nullptr;
+                    if ((e.row < p.tw * p.th) && (tc.x0 + ltx < p.out_w) && (tc.y0 + lty < p.out_h))
+                        yrow = p.y_f32 + ((size_t)((size_t)tc.img * p.out_h + tc.y0 + lty) * p.out_w + tc.x0 + ltx) * p.y_ps;
+                    const int steps = (p.block_n + 15) >> 4, per = (steps + gps - 1) / gps;
+                    const int c_begin = sub_id * per * 16, c_end = min(p.block_n, (sub_id + 1) * per * 16);
+                    epilogue_tile_f32(e, t_row, tl, yrow, c_begin, c_end);
+                } else {
+                    for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
+                }
+                tc_fence_before();                               // all TMEM reads of this stage by this warp are done
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(stage_id));
             }
-            for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-                const int buf = chunk_ctr & 1u;
-                const uint32_t s_out = smem_out0 + buf * kStageOutBytes;
-                const int cbase = ch * 64;                           // column inside the N tile
-                const int c0 = cbase + half * 32;
-                const bool active = c0 < p.block_n;                  // warp-uniform
-                if (!p.out_f32) {
-                    if (leader) tma_store_wait_read<1>();           // staging buffer `buf` no longer being read
-                    epi_bar_sync();
-                    if (p.has_res) {
-                        if (leader) {
-                            mbar_expect_tx(res_bar(buf), a_bytes);
-                            tma_load_4d(s_out, &tm_res, res_bar(buf), n0 + cbase, tc.x0, tc.y0, tc.img);
-                        }
-                        const uint32_t ph = buf ? res_phase1 : res_phase0;
-                        mbar_wait(res_bar(buf), ph);
-                        if (buf) res_phase1 ^= 1u; else res_phase0 ^= 1u;
-                    }
-                }
-                uint32_t v[32];
-                if (active) {
-                    tmem_ld32(t_row + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                }
-                if (ch == n_chunks - 1) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                }
-                if (active) {
-                    float f[32];
-                    const float4* bq = reinterpret_cast<const float4*>(s_bias + n0 + c0);
-                    if (p.act) {
-                        #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 hb = bq[j];                 // 0.5 * bias
-                            f[4 * j + 0] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 0]), 0.5f, hb.x));
-                            f[4 * j + 1] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, hb.y));
-                            f[4 * j + 2] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, hb.z));
-                            f[4 * j + 3] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, hb.w));
-                        }
-                    } else {
-                        #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = bq[j];
-                            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-                        }
-                    }
-                    if (p.out_f32) {
-                        if (yrow) {
-                            #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const int col = n0 + c0 + j;
-                                if (col + 3 < p.c_out) {
-                                    *reinterpret_cast<float4*>(yrow + col) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                                } else {
-                                    for (int q = 0; q < 4; ++q) if (col + q < p.c_out) yrow[col + q] = f[j + q];
-                                }
-                            }
-                        }
-                    } else {
-                        // 32 columns = 64 B = 4 x 16 B chunks of this row's 128 B swizzled line
-                        const uint32_t line = s_out + (uint32_t)row * 128u;
-                        #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t chunk16 = (uint32_t)(half * 4 + q);
-                            const uint32_t addr = line + ((chunk16 ^ (uint32_t)(row & 7)) << 4);
-                            if (p.has_res) {
-                                uint32_t r0, r1, r2, r3;
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-                                f[q * 8 + 0] += bf16_lo(r0); f[q * 8 + 1] += bf16_hi(r0);
-                                f[q * 8 + 2] += bf16_lo(r1); f[q * 8 + 3] += bf16_hi(r1);
-                                f[q * 8 + 4] += bf16_lo(r2); f[q * 8 + 5] += bf16_hi(r2);
-                                f[q * 8 + 6] += bf16_lo(r3); f[q * 8 + 7] += bf16_hi(r3);
-                            }
-                            const uint32_t o0 = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                            const uint32_t o1 = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                            const uint32_t o2 = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                            const uint32_t o3 = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-                        }
-                    }
-                }
-                if (!p.out_f32) {
-                    fence_proxy_async_smem();                        // generic-proxy writes -> async proxy (TMA)
-                    epi_bar_sync();
-                    if (leader) {
-                        tma_store_4d(&tm_y, s_out, n0 + cbase, tc.x0, tc.y0, tc.img);
-                        tma_store_commit();
-                    }
-                }
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (e.leader && !p.out_f32) tma_store_wait_read<0>();
         }
-        if (leader && !p.out_f32) tma_store_wait_read<0>();
     }
 
     tc_fence_before();
@@ -446,7 +368,9 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     kp.y_ps = q->y_pixel_stride;
 
     const int b_bytes = (kp.block_n * 128 + 1023) & ~1023;
-    const int fixed = 2 * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 8) * 8 + 1024 /* alignment slack */;
+    const int fixed = kEpiGroups * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 16) * 8 + 1024 /* alignment slack */;
+    kp.acc_stages = kp.block_n <= 128 ? 4 : 2;
+    kp.mg_n_tiles = fast_div_magic(kp.n_tiles); kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
     const int res_bytes = kp.taps * (kp.kb1 + kp.kb2) * b_bytes;
     // small weight sets stay resident for the whole persistent CTA (no per-tile re-fetch from L2)
     kp.resident = (kp.n_tiles == 1 && !getenv("YMS_CONV_STREAM") && kSmemLimit - fixed - res_bytes >= 4 * kATileBytes) ? 1 : 0;

@@ -1,6 +1,6 @@
 // Shared host-side plan structure and tensor-map encoding for the convolution kernels.
 #pragma once
-#include "tc_ptx.cuh"
+#include "conv_epilogue.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -21,6 +21,8 @@ struct ConvKernelParams {
     int act, out_f32, has_res;
     int num_stages, total_tiles;
     int resident;                              // all weight tiles of the (single) N tile stay in smem
+    int acc_stages;                            // TMEM accumulator stages == active epilogue groups (1, 2 or 4)
+    uint32_t mg_n_tiles, mg_tiles_x, mg_tiles_y;  // fast_div magics
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
     const float* bias;
     float* y_f32; long long y_ps;
@@ -41,9 +43,12 @@ struct Conv3Params {
     int total_items;
     int bias_pad;
     int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
+    uint32_t mg_n_tiles, mg_super_x, mg_tiles_y;  // fast_div magics
     uint32_t halo_bytes;                       // 10 * (th + 2) * 128
     const float* bias;
 };
+
+inline uint32_t fast_div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
 
 int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, const char* what);
