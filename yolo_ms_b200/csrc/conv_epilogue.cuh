@@ -101,35 +101,41 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
     }
 }
 
-// fp32 output written directly (the head's raw logits): yrow = this thread's output pixel or nullptr.
-// Columns [c_begin, c_end) of the N tile (16-column steps) -- groups sharing a stage split the range.
-__device__ __forceinline__ void epilogue_tile_f32(const EpiShared& e, uint32_t t_row, const EpiTile& tl, float* yrow, int c_begin, int c_end) {
+// fp32 output (the head's raw logits) of ONE 32-channel chunk: same staging scheme, the tensor map is
+// FLOAT32 with 32-element (128-byte) rows.
+__device__ __forceinline__ void epilogue_chunk_f32(const EpiShared& e, uint32_t t_row, const EpiTile& tl, int ch) {
+    const int cbase = ch * 32;
+    if (e.leader) tma_store_wait_read<0>();
+    group_bar_sync(e.bar_id);
+    const uint32_t line = e.s_out + (uint32_t)e.row * 128u;
     #pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    for (int q16 = 0; q16 < 2; ++q16) {
+        const int c0 = cbase + q16 * 16;
+        if (c0 >= e.block_n) break;
         uint32_t v[16];
         tmem_ld16(t_row + (uint32_t)c0, v);
         tmem_ld_wait();
-        const float* bq = e.s_bias + tl.n0 + c0;
-        if (yrow) {
-            #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const int col = tl.n0 + c0 + j;
-                float f0 = __uint_as_float(v[j]), f1 = __uint_as_float(v[j + 1]), f2 = __uint_as_float(v[j + 2]), f3 = __uint_as_float(v[j + 3]);
-                if (e.act) {
-                    f0 = silu_from_half(fmaf(f0, 0.5f, bq[j])); f1 = silu_from_half(fmaf(f1, 0.5f, bq[j + 1]));
-                    f2 = silu_from_half(fmaf(f2, 0.5f, bq[j + 2])); f3 = silu_from_half(fmaf(f3, 0.5f, bq[j + 3]));
-                } else {
-                    f0 += bq[j]; f1 += bq[j + 1]; f2 += bq[j + 2]; f3 += bq[j + 3];
-                }
-                if (col + 3 < e.c_out) {
-                    *reinterpret_cast<float4*>(yrow + col) = make_float4(f0, f1, f2, f3);
-                } else {
-                    if (col < e.c_out) yrow[col] = f0;
-                    if (col + 1 < e.c_out) yrow[col + 1] = f1;
-                    if (col + 2 < e.c_out) yrow[col + 2] = f2;
-                }
+        const float4* bq = reinterpret_cast<const float4*>(e.s_bias + tl.n0 + c0);
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 b4 = bq[j];
+            float f0 = __uint_as_float(v[4 * j + 0]), f1 = __uint_as_float(v[4 * j + 1]);
+            float f2 = __uint_as_float(v[4 * j + 2]), f3 = __uint_as_float(v[4 * j + 3]);
+            if (e.act) {
+                f0 = silu_from_half(fmaf(f0, 0.5f, b4.x)); f1 = silu_from_half(fmaf(f1, 0.5f, b4.y));
+                f2 = silu_from_half(fmaf(f2, 0.5f, b4.z)); f3 = silu_from_half(fmaf(f3, 0.5f, b4.w));
+            } else {
+                f0 += b4.x; f1 += b4.y; f2 += b4.z; f3 += b4.w;
             }
+            const uint32_t addr = line + (((uint32_t)(q16 * 4 + j) ^ (uint32_t)(e.row & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(f0), "f"(f1), "f"(f2), "f"(f3) : "memory");
         }
+    }
+    fence_proxy_async_smem();
+    group_bar_sync(e.bar_id);
+    if (e.leader) {
+        tma_store_4d(e.tm_y, e.s_out, tl.n0 + cbase, tl.x0, tl.y0, tl.img);
+        tma_store_commit();
     }
 }
 

@@ -88,7 +88,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
         if (p.kb2) prefetch_tmap(&tm_x2);
-        if (!p.out_f32) prefetch_tmap(&tm_y);
+        prefetch_tmap(&tm_y);
         if (p.has_res) prefetch_tmap(&tm_res);
         for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < kEpiGroups; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * (kEpiGroups / p.acc_stages)); mbar_init(res_bar(s), 1); }
@@ -208,13 +208,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 acc_phase ^= 1u;
                 tc_fence_after();
                 if (p.out_f32) {
-                    const int lty = e.row / p.tw, ltx = e.row - lty * p.tw;
-                    float* yrow = nullptr;
-                    if ((e.row < p.tw * p.th) && (tc.x0 + ltx < p.out_w) && (tc.y0 + lty < p.out_h))
-                        yrow = p.y_f32 + ((size_t)((size_t)tc.img * p.out_h + tc.y0 + lty) * p.out_w + tc.x0 + ltx) * p.y_ps;
-                    const int steps = (p.block_n + 15) >> 4, per = (steps + gps - 1) / gps;
-                    const int c_begin = sub_id * per * 16, c_end = min(p.block_n, (sub_id + 1) * per * 16);
-                    epilogue_tile_f32(e, t_row, tl, yrow, c_begin, c_end);
+                    const int n_chunks32 = (p.block_n + 31) >> 5;
+                    for (int ch = sub_id; ch < n_chunks32; ch += gps) epilogue_chunk_f32(e, t_row, tl, ch);
                 } else {
                     for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
                 }
@@ -222,7 +217,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(stage_id));
             }
-            if (e.leader && !p.out_f32) tma_store_wait_read<0>();
+            if (e.leader) tma_store_wait_read<0>();
         }
     }
 
@@ -270,10 +265,10 @@ int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* add
 
 // activation tensor map: dims (c, X, Y, N); `flat` folds all pixels into X.
 int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, int h, int w, bool flat,
-               int box_x, int box_y, int estride, const char* what) {
+               int box_x, int box_y, int estride, const char* what, bool f32) {
     uint64_t dims[4]; uint64_t strides[3]; uint32_t box[4]; uint32_t es[4] = {1, (uint32_t)estride, (uint32_t)estride, 1};
     dims[0] = (uint64_t)c;
-    strides[0] = (uint64_t)ps * 2;
+    strides[0] = (uint64_t)ps * (f32 ? 4 : 2);
     if (flat) {
         dims[1] = (uint64_t)batch * h * w; dims[2] = 1; dims[3] = 1;
         strides[1] = strides[0] * dims[1]; strides[2] = strides[1];
@@ -281,11 +276,10 @@ int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, in
         dims[1] = (uint64_t)w; dims[2] = (uint64_t)h; dims[3] = (uint64_t)batch;
         strides[1] = strides[0] * (uint64_t)w; strides[2] = strides[1] * (uint64_t)h;
     }
-    box[0] = kBlockK; box[1] = (uint32_t)box_x; box[2] = (uint32_t)box_y; box[3] = 1;
-    return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, what);
+    box[0] = f32 ? 32 : kBlockK;            // 128-byte rows either way
+    box[1] = (uint32_t)box_x; box[2] = (uint32_t)box_y; box[3] = 1;
+    return encode_map(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, what);
 }
-
-
 
 }  // namespace yms
 
@@ -308,7 +302,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     if ((q->x_pixel_stride % 8) || q->x_pixel_stride < q->c_in || q->y_pixel_stride < q->c_out)
         return fail(YMS_E_ARG, "conv: bad pixel stride");
     if (q->out_dtype == YMS_DTYPE_BF16 && (q->y_pixel_stride % 8)) return fail(YMS_E_ARG, "conv: y pixel stride % 8");
-    if (q->out_dtype == YMS_DTYPE_F32 && (q->y_pixel_stride % 4)) return fail(YMS_E_ARG, "conv: y pixel stride % 4");
+    if (q->out_dtype == YMS_DTYPE_F32 && ((q->y_pixel_stride % 4) || (q->c_out % 4))) return fail(YMS_E_ARG, "conv: f32 output needs c_out, pixel stride % 4");
     if (q->c_in2 && (!q->x2 || !al16(q->x2) || (q->x2_pixel_stride % 8) || q->x2_pixel_stride < q->c_in2))
         return fail(YMS_E_ARG, "conv: bad second source");
     if (q->residual && (!al16(q->residual) || (q->res_pixel_stride % 8) || q->res_pixel_stride < q->c_out))
@@ -396,9 +390,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
         uint32_t es[3] = {1, 1, 1};
         if ((rc = encode_map(&pl->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q->weight, dims, strides, box, es, "w"))) { delete pl; return rc; }
     }
-    if (!kp.out_f32) {
-        if ((rc = encode_act(&pl->tm_y, q->y, q->c_out, q->y_pixel_stride, q->batch, out_h, out_w, flat, kp.tw, kp.th, 1, "y"))) { delete pl; return rc; }
-    } else pl->tm_y = pl->tm_x;
+    if ((rc = encode_act(&pl->tm_y, q->y, q->c_out, q->y_pixel_stride, q->batch, out_h, out_w, flat, kp.tw, kp.th, 1, "y", kp.out_f32 != 0))) { delete pl; return rc; }
     if (q->residual) {
         if ((rc = encode_act(&pl->tm_res, q->residual, q->c_out, q->res_pixel_stride, q->batch, out_h, out_w, flat, kp.tw, kp.th, 1, "res"))) { delete pl; return rc; }
     } else pl->tm_res = pl->tm_x;

@@ -53,7 +53,7 @@ inline uint32_t fast_div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x
 int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, const char* what);
 int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, int h, int w, bool flat,
-               int box_x, int box_y, int estride, const char* what);
+               int box_x, int box_y, int estride, const char* what, bool f32 = false);
 
 int conv3_plan_init(::yms_conv_plan* pl, const yms_conv_params* q);   // conv3x3.cu
 int conv3_plan_run(const ::yms_conv_plan* pl, cudaStream_t stream);

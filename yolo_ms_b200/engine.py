@@ -45,6 +45,10 @@ class Program:
         self._keep: list = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.eager_prefix = 0          # leading steps that read caller-owned memory: never captured
+        self.schedule: list = []       # ("op", fn, branch) | ("fork", n, 0) | ("join", 0, 0)
+        self._branch = 0
+        self._n_side = 0
+        self._side: List[torch.cuda.Stream] = []
         self.launches = 0
         self.flops = 0.0
         self.bytes = 0.0
@@ -63,22 +67,64 @@ class Program:
         plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
         self.plans.append(plan)
         self.hold(weight_packed, bias)
-        self.steps.append(plan.run)
-        self.launches += 1
+        self._push(plan.run)
         self.flops += plan.flops
         self.bytes += plan.bytes
         return y
 
     def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0):
-        self.steps.append(fn)
-        self.launches += 1
+        self._push(fn)
         self.bytes += nbytes
         self.flops += flops
 
+    def _push(self, fn):
+        self.steps.append(fn)
+        self.schedule.append(("op", fn, self._branch))
+        self.launches += 1
+
+    # ---- independent branches (e.g. the three head scales): captured as parallel graph branches ----
+    def fork(self, n_branches: int):
+        self.schedule.append(("fork", n_branches, 0))
+        self._n_side = max(self._n_side, n_branches - 1)
+
+    def branch(self, i: int):
+        self._branch = i
+
+    def join(self):
+        self.schedule.append(("join", 0, 0))
+        self._branch = 0
+
     # ---- execution ---------------------------------------------------------------------------
-    def run_eager(self):
-        for s in self.steps:
-            s()
+    def run_eager(self, start: int = 0):
+        """Issue every launch (from op index `start`) on the current stream; branches > 0 go to side
+        streams between fork/join."""
+        main = torch.cuda.current_stream(self.device)
+        while len(self._side) < self._n_side:
+            self._side.append(torch.cuda.Stream(device=self.device))
+        op_idx = 0
+        used = set()
+        for kind, arg, br in self.schedule:
+            if kind == "op":
+                if op_idx >= start:
+                    if br == 0:
+                        arg()
+                    else:
+                        used.add(br)
+                        with torch.cuda.stream(self._side[br - 1]):
+                            arg()
+                op_idx += 1
+            elif kind == "fork":
+                if op_idx >= start:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    for k in range(arg - 1):
+                        self._side[k].wait_event(ev)
+            elif kind == "join":
+                for k in sorted(used):
+                    ev = torch.cuda.Event()
+                    ev.record(self._side[k - 1])
+                    main.wait_event(ev)
+                used.clear()
 
     def capture(self):
         """Warm up once, then capture steps[eager_prefix:] into a CUDA graph."""
@@ -87,10 +133,10 @@ class Program:
         with torch.cuda.stream(side):
             self.run_eager()
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for s in self.steps[self.eager_prefix:]:
-                s()
+            self.run_eager(start=self.eager_prefix)
         self.graph = g
 
     def run(self):

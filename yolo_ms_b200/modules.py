@@ -408,7 +408,9 @@ class Head(_Compiled):
         if self.ch != 16:
             raise RuntimeError("DFL is fixed to 16 bins (the reference builds DFL() with its default ch)")
         raws = []
+        P.fork(len(feats))                                   # the scales are independent: parallel graph branches
         for i, f in enumerate(feats):
+            P.branch(i)
             b, h, w, _ = f.shape
             raw = P.buf(b, h, w, self.no, dtype=torch.float32)
             # box[i][0] and cls[i][0] read the same feature map: ONE 3x3 conv with the two weight sets
@@ -424,6 +426,7 @@ class Head(_Compiled):
                 bl = last.bias.detach().float().contiguous()
                 P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False)
             raws.append(raw)
+        P.join()
         return raws
 
     def _stride_list(self):
