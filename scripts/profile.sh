@@ -1,21 +1,26 @@
 #!/bin/bash
 # ncu evidence for one round (run under gpurun, ONE GPU).  Usage: scripts/profile.sh r01
-# Each ncu pass only after the identical plain command exited 0.  Outputs are kept small
-# (gpurun_out/ is capped at 64 MiB): a launch list and --set full captures of a handful of launches.
+# Every ncu pass runs only after the identical plain command exited 0.  Outputs stay small
+# (gpurun_out/ is capped at 64 MiB): CSV exports only, .ncu-rep files are deleted on the box.
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+MINE='regex:conv_gemm|conv3x3|stem_tc|stem_conv|nms_kernel|head_decode|sppf_pool|upsample2x|select_cand|gather_dets|dwconv'
 mkdir -p $OUT
-rm -f $OUT/*.ncu-rep
+# 1. launch list of one steady-state step (our kernels only): duration + DRAM bytes per launch
 $CMD > $OUT/plain_$TAG.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 204 -c 140 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
-$CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 186 -c 5 -o $OUT/prof_conv_$TAG $CMD > $OUT/ncu_conv_$TAG.log 2>&1
-$CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"nms_kernel|head_decode|stem_conv" -s 9 -c 3 -o $OUT/prof_post_$TAG $CMD > $OUT/ncu_post_$TAG.log 2>&1
-for f in conv post; do
-  ncu -i $OUT/prof_${f}_$TAG.ncu-rep --page raw --csv > $OUT/prof_${f}_${TAG}_raw.csv 2>/dev/null
-  ncu -i $OUT/prof_${f}_$TAG.ncu-rep --page details --csv > $OUT/prof_${f}_${TAG}_details.csv 2>/dev/null
-done
-du -sh $OUT; ls -la $OUT | tail -14
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$MINE" -s 198 -c 66 \
+    --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
+# 2. --set full on a few launches of each hot kernel
+prof() {  # name regex skip count
+  $CMD > /dev/null 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -o $OUT/prof_$1_$TAG $CMD > $OUT/ncu_$1_$TAG.log 2>&1
+  ncu -i $OUT/prof_$1_$TAG.ncu-rep --page raw --csv > $OUT/prof_$1_${TAG}_raw.csv 2>/dev/null
+  ncu -i $OUT/prof_$1_$TAG.ncu-rep --page details --csv > $OUT/prof_$1_${TAG}_details.csv 2>/dev/null
+  rm -f $OUT/prof_$1_$TAG.ncu-rep
+}
+prof gemm conv_gemm_kernel 93 4          # step 4: conv1 (3x3 s2), c2f_2.conv1, c2f_2.conv2, conv3
+prof conv3 conv3x3_kernel 84 4           # step 4: the two 160x160 bottleneck convs + first two 80x80
+prof post 'nms_kernel|head_decode|stem_tc' 9 3
+du -sh $OUT; ls $OUT | grep $TAG
