@@ -104,7 +104,7 @@ def test_stem_conv(ops, cout):
 
 def test_sppf_pool_is_exact(ops):
     g = torch.Generator().manual_seed(1)
-    for (h, w, c) in ((20, 24, 64), (5, 3, 8), (40, 40, 32)):
+    for (h, w, c) in ((20, 24, 64), (5, 3, 8), (40, 40, 32), (50, 50, 16)):
         buf = torch.zeros(2, h, w, 4 * c, device=DEV, dtype=torch.bfloat16)
         buf[..., :c] = torch.randn(2, h, w, c, generator=g).to(DEV).to(torch.bfloat16)
         ops.sppf_pool(buf, c)
@@ -142,7 +142,7 @@ def test_dwconv(ops, k):
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("sizes,nc", [(((20, 24), (10, 12), (5, 6)), 80), (((15, 15), (7, 9), (3, 5)), 3), (((2, 2), (1, 1), (1, 1)), 80)])
 def test_head_decode_matches_oracle(ops, dt, sizes, nc):
-    """fp32 decode; tolerance 1e-4 px * stride on boxes (expf ulps), 1e-6 on scores.  The emitted
+    """fp32 decode; tolerance 5e-3 px on boxes, 5e-6 on scores (ex2/rcp approximations).  The emitted
     candidates must be bit-identical to the reference selection applied to OUR prediction."""
     from oracle import postprocess as P
     from oracle import yolov8_oracle as O
@@ -155,7 +155,7 @@ def test_head_decode_matches_oracle(ops, dt, sizes, nc):
     assert pred.shape == want.shape
     p = pred.cpu()
     assert float((p[..., :4] - want[..., :4]).abs().max()) < 5e-3
-    assert float((p[..., 4:] - want[..., 4:]).abs().max()) < 2e-6
+    assert float((p[..., 4:] - want[..., 4:]).abs().max()) < 5e-6
     sb, ss, sl = ops.select_candidates(pred)
     for i in range(B):
         wb, ws, wl = P.select_candidates(p[i].numpy())

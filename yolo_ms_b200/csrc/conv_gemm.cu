@@ -132,7 +132,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                         const uint32_t sa = smem_a0 + stage * stage_bytes;
                         const uint32_t sb = sa + kATileBytes;
                         mbar_expect_tx(full_bar(stage), stage_tx);
-                        if (kb < p.kb1) {
+                        if (p.s2_dense) {
+                            // dense stride-2 input viewed as (2C, W/2, 2, H/2, N): a tap selects the pixel/row parity
+                            // (channel offset px*C, coordinate py) and a -1/0 shift; every box row is contiguous.
+                            const int px = (kx != 1), py = (ky != 1);
+                            tma_load_5d(sa, &tm_x, full_bar(stage), px * p.c_in1 + kb * kBlockK, tc.x0 - (kx == 0), py,
+                                        tc.y0 - (ky == 0), tc.img);
+                            if (!p.resident) tma_load_3d(sb, &tm_w, full_bar(stage), kb * kBlockK, n0, tap);
+                        } else if (kb < p.kb1) {
                             tma_load_4d(sa, &tm_x, full_bar(stage), kb * kBlockK, xin, yin, tc.img);
                             if (!p.resident) tma_load_3d(sb, &tm_w, full_bar(stage), kb * kBlockK, n0, tap);
                         } else {
@@ -379,6 +386,15 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     int rc;
     const int K_total = q->c_in + q->c_in2;
     const int bx = kp.tw * q->stride, by = kp.th * q->stride;
+    kp.s2_dense = (q->stride == 2 && q->x_pixel_stride == q->c_in && q->c_in2 == 0 && !getenv("YMS_CONV_S2_STRIDED")) ? 1 : 0;
+    if (kp.s2_dense) {
+        const uint64_t C = (uint64_t)q->c_in, W = (uint64_t)q->in_w, H = (uint64_t)q->in_h;
+        uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, (uint64_t)q->batch};
+        uint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+        uint32_t box[5] = {kBlockK, (uint32_t)kp.tw, 1, (uint32_t)kp.th, 1};
+        uint32_t es[5] = {1, 1, 1, 1, 1};
+        if ((rc = encode_map(&pl->tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, q->x, dims, strides, box, es, "x(s2 dense)"))) { delete pl; return rc; }
+    } else
     if ((rc = encode_act(&pl->tm_x, q->x, q->c_in, q->x_pixel_stride, q->batch, q->in_h, q->in_w, flat, bx, by, q->stride, "x"))) { delete pl; return rc; }
     if (q->c_in2) {
         if ((rc = encode_act(&pl->tm_x2, q->x2, q->c_in2, q->x2_pixel_stride, q->batch, q->in_h, q->in_w, flat, bx, by, q->stride, "x2"))) { delete pl; return rc; }

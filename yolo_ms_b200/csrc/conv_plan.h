@@ -21,6 +21,7 @@ struct ConvKernelParams {
     int act, out_f32, has_res;
     int num_stages, total_tiles;
     int resident;                              // all weight tiles of the (single) N tile stay in smem
+    int s2_dense;                              // stride-2 input is a dense NHWC tensor: 5-D parity view, no traversal stride
     int acc_stages;                            // TMEM accumulator stages == active epilogue groups (1, 2 or 4)
     uint32_t mg_n_tiles, mg_tiles_x, mg_tiles_y;  // fast_div magics
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
