@@ -272,12 +272,25 @@ def run_native(args):
         gbs = conv_by / (conv_ms / 1e3) / 1e9
         tfs = conv_fl / (conv_ms / 1e3) / 1e12
         bound = "hbm" if ai < ridge else "tensor"
-        roof = {"kernel": "conv_gemm_kernel", "bound": bound,
+        # DRAM traffic of the same kernels from the committed ncu launch list (profiles/traffic_*.json)
+        traffic, traffic_src = None, None
+        try:
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))[-1]
+            with open(tf) as f:
+                tj = json.load(f)
+            tb = sum(v["dram_bytes"] for k, v in tj.items() if k.startswith("conv"))
+            tl = sum(v["launches"] for k, v in tj.items() if k.startswith("conv"))
+            traffic, traffic_src = round(tb / tl), os.path.basename(tf)
+        except Exception:
+            pass
+        roof = {"kernel": "conv_gemm_kernel + conv3x3_kernel (all tcgen05 conv launches of a step)", "bound": bound,
                 "achieved": round(gbs if bound == "hbm" else tfs, 1),
                 "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops_sustained"],
                 "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
                 "frac": round((gbs / peaks["hbm_gbs"]) if bound == "hbm" else (tfs / peaks["bf16_tflops_sustained"]), 4),
-                "traffic": None, "peak_source": peaks["source"],
+                "traffic": traffic, "traffic_note": f"mean DRAM bytes per launch from {traffic_src} (ncu, same batch/config); algorithmic mean {round(conv_by / n_conv)}",
+                "peak_source": peaks["source"],
                 "launches_per_step": n_conv, "avg_launch_us": round(conv_ms / n_conv * 1e3, 2),
                 "algorithmic_bytes_per_step": conv_by, "algorithmic_flops_per_step": conv_fl,
                 "tflops": round(tfs, 1), "tensor_frac": round(tfs / peaks["bf16_tflops_sustained"], 4),

@@ -102,6 +102,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
     const uint32_t out_bytes = (uint32_t)(8 * p.th) * 128u;
     const int acc_stride = 512 / p.acc_stages;
 
@@ -352,7 +354,8 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
 }
 
 int conv3_plan_run(const yms_conv_plan* pl, cudaStream_t stream) {
-    conv3x3_kernel<<<pl->grid, kThreads3, pl->smem, stream>>>(pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    cudaError_t le = launch_pdl(conv3x3_kernel, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    if (le != cudaSuccess) return fail((int)le, "conv3x3_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv3x3_kernel");
 }
 

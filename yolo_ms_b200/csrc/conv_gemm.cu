@@ -101,6 +101,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
 
     const int kb_per_tap = p.kb1 + p.kb2;
     const int num_kb = p.taps * kb_per_tap;
@@ -429,8 +431,9 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     if (!pl) return fail(YMS_E_ARG, "conv: null plan");
     if (pl->kind == 1) return conv3_plan_run(pl, (cudaStream_t)stream);
-    conv_gemm_kernel<<<pl->grid, kThreads, pl->smem, (cudaStream_t)stream>>>(pl->tm_x, pl->tm_x2, pl->tm_w, pl->tm_y,
-                                                                             pl->tm_res, pl->kp);
+    cudaError_t le = launch_pdl(conv_gemm_kernel, pl->grid, kThreads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
+                                pl->tm_y, pl->tm_res, pl->kp);
+    if (le != cudaSuccess) return fail((int)le, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");
 }
 

@@ -4,6 +4,8 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <utility>
 
 struct yms_conv_plan;
 
@@ -50,6 +52,20 @@ struct Conv3Params {
 };
 
 inline uint32_t fast_div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
+
+// Launch with the programmatic-stream-serialization attribute (kernels call pdl_wait() before touching
+// global data).  YMS_PDL=0 disables it.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static const bool enabled = [] { const char* e = getenv("YMS_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, const char* what);
