@@ -32,7 +32,7 @@ using namespace tc;
 
 constexpr int kThreads3 = kConvThreads;
 constexpr int kHaloPitch = 10;                         // lines (pixels) per halo row
-constexpr int kHaloStageBytes = 23552;                 // 180 lines = 23040 B, rounded up to 1024
+constexpr int kHaloStageBytes = 23552;                 // 180 lines = 23040 B, rounded up to 1024 (max; plans use p.halo_stage)
 constexpr int kRing = 8;                               // max ring depth (barrier array size)
 constexpr int kSmemLimit3 = 232448;
 
@@ -62,15 +62,17 @@ __device__ __forceinline__ Item decode_item(const Conv3Params& p, int t) {
     return it;
 }
 
+template <int kSub>
 __global__ void __launch_bounds__(kThreads3, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
                const __grid_constant__ Conv3Params p) {
-    extern __shared__ unsigned char smem_dyn[];
-    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];      // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t base = smem_u32(smem_dyn);
+    unsigned char* gbase = smem_dyn;
+    if (base & 1023u) __trap();
     const int b_tile_bytes = (p.block_n * 128 + 1023) & ~1023;
-    const int a_region = p.a_stages * p.sub * kHaloStageBytes;
+    const int a_region = ((p.a_stages * p.sub * p.halo_stage) + 1023) & ~1023;
     const int b_region = (p.resident ? 9 * p.kb : p.b_stages) * b_tile_bytes;
     const uint32_t smem_a = base;
     const uint32_t smem_b = base + a_region;
@@ -124,7 +126,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     mbar_wait(bar(kBarAEmpty + as), aph ^ 1u);
                     mbar_expect_tx(bar(kBarAFull + as), (uint32_t)p.sub * p.halo_bytes);
                     for (int s = 0; s < p.sub; ++s)
-                        tma_load_4d(smem_a + (as * p.sub + s) * kHaloStageBytes, &tm_x, bar(kBarAFull + as),
+                        tma_load_4d(smem_a + (as * p.sub + s) * p.halo_stage, &tm_x, bar(kBarAFull + as),
                                     cb * kBlockK, (it.sx * p.sub + s) * 8 - 1, it.ty * p.th - 1, it.img);
                     if (++as == p.a_stages) { as = 0; aph ^= 1u; }
                     if (!p.resident) {
@@ -146,7 +148,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t hi_a = (1ull << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
         const uint64_t hi_b = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-        const uint32_t halo16 = kHaloStageBytes >> 4;
+        const uint32_t halo16 = (uint32_t)p.halo_stage >> 4;
         const uint32_t btile16 = (uint32_t)b_tile_bytes >> 4;
         if (p.resident) { mbar_wait(bar(kBarW), 0u); tc_fence_after(); }
         int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
@@ -160,7 +162,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 tc_fence_after();
                 const int cvalid = p.c_in - cb * kBlockK;
                 const int ksteps = cvalid >= kBlockK ? 4 : ((cvalid + 15) >> 4);
-                const uint32_t a16 = ((smem_a + (uint32_t)(as * p.sub) * kHaloStageBytes) & 0x3FFFFu) >> 4;
+                const uint32_t a16 = ((smem_a + (uint32_t)(as * p.sub) * (uint32_t)p.halo_stage) & 0x3FFFFu) >> 4;
                 const uint32_t first = (cb != 0) ? 1u : 0u;
                 const bool last_cb = (cb == p.kb - 1);
                 if (p.resident) {
@@ -172,9 +174,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                             const uint32_t toff = (uint32_t)((tap / 3) * kHaloPitch + (tap % 3)) * 8u;
                             #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (k < ksteps)
-                                    umma_bf16(d_tmem, hi_a | (uint64_t)(a16 + toff + 2 * k), hi_b | (uint64_t)(b16 + tap * bstride16 + 2 * k),
-                                              idesc, (tap | k) ? 1u : first);
+                                if (k < ksteps) {
+                                    // independent accumulators (sub-tiles) are interleaved: consecutive MMAs do not chain
+                                    #pragma unroll
+                                    for (int sidx = 0; sidx < kSub; ++sidx)
+                                        umma_bf16(d_tmem + (uint32_t)(sidx * p.block_n), hi_a | (uint64_t)(a16 + sidx * halo16 + toff + 2 * k),
+                                                  hi_b | (uint64_t)(b16 + tap * bstride16 + 2 * k), idesc, (tap | k) ? 1u : first);
+                                }
                             }
                         }
                         umma_commit(bar(kBarAEmpty + as));
@@ -195,7 +201,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                                 if (k < ksteps)
                                     umma_bf16(d_tmem, hi_a | (uint64_t)(a16 + toff + 2 * k), hi_b | (uint64_t)(b16 + 2 * k), idesc, k ? 1u : accf);
                             }
-                            if (p.sub == 2) {
+                            if (kSub == 2) {
                                 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     if (k < ksteps)
@@ -296,24 +302,39 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.desc_mode = dm ? atoi(dm) : 0;
 
     const int b_tile = (k.block_n * 128 + 1023) & ~1023;
-    const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16 + 1024;
+    const int halo_stage = (int)k.halo_bytes;
+    k.halo_stage = halo_stage;
+    const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16;
     const int resident_bytes = 9 * k.kb * b_tile;
     const char* force_stream = getenv("YMS_CONV3_STREAM");
-    k.resident = (k.n_tiles == 1 && kSmemLimit3 - fixed - resident_bytes >= 2 * kHaloStageBytes && !force_stream) ? 1 : 0;
+    // largest ring depth (in items of `sub` halos) that fits next to `other` bytes of weights
+    auto max_a_stages = [&](int sub, int other) {
+        int n = 0;
+        while (n < kRing && ((((n + 1) * sub * halo_stage + 1023) & ~1023) + other + fixed <= kSmemLimit3)) ++n;
+        return n;
+    };
+    k.resident = (k.n_tiles == 1 && !force_stream && max_a_stages(1, resident_bytes) >= 2) ? 1 : 0;
     if (k.resident) {
-        k.sub = 1; k.b_stages = 0;
-        k.a_stages = (kSmemLimit3 - fixed - resident_bytes) / kHaloStageBytes;
+        // two sub-tiles per item when they fit: their MMAs use independent accumulators and are
+        // interleaved, which hides part of the ~100-cycle per-instruction tcgen05.mma latency
+        const char* fs = getenv("YMS_CONV3_SUB");
+        const long long sub_tiles = (long long)k.tiles_x * k.tiles_y * k.batch;
+        k.sub = fs ? atoi(fs) : ((k.tiles_x >= 2 && sub_tiles >= 4096) ? 2 : 1);    // pairing only pays with many tiles per CTA
+        k.b_stages = 0;
+        if ((k.sub != 1 && k.sub != 2 && k.sub != 4) || k.sub * k.block_n > 512) k.sub = 1;
+        k.a_stages = max_a_stages(k.sub, resident_bytes);
+        if (k.a_stages < 2) { k.sub = 1; k.a_stages = max_a_stages(1, resident_bytes); }
     } else {
         k.sub = (k.tiles_x >= 2 && 2 * k.block_n <= 512) ? 2 : 1;
         k.b_stages = 4;
         for (;;) {
-            k.a_stages = (kSmemLimit3 - fixed - k.b_stages * b_tile) / (k.sub * kHaloStageBytes);
+            k.a_stages = max_a_stages(k.sub, k.b_stages * b_tile);
             if (k.a_stages >= 2 || k.b_stages == 2) break;
             --k.b_stages;
         }
         if (k.a_stages < 2 && k.sub == 2) {
             k.sub = 1; k.b_stages = 4;
-            k.a_stages = (kSmemLimit3 - fixed - k.b_stages * b_tile) / kHaloStageBytes;
+            k.a_stages = max_a_stages(1, k.b_stages * b_tile);
         }
     }
     if (k.a_stages > kRing) k.a_stages = kRing;
@@ -323,7 +344,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.total_items = k.super_x * k.tiles_y * k.batch * k.n_tiles;
     k.mg_n_tiles = fast_div_magic(k.n_tiles); k.mg_super_x = fast_div_magic(k.super_x); k.mg_tiles_y = fast_div_magic(k.tiles_y);
     pl->grid = k.total_items < kNumSMs ? k.total_items : kNumSMs;
-    pl->smem = (size_t)k.a_stages * k.sub * kHaloStageBytes + (size_t)(k.resident ? resident_bytes : k.b_stages * b_tile) + fixed;
+    pl->smem = (size_t)((k.a_stages * k.sub * halo_stage + 1023) & ~1023) + (size_t)(k.resident ? resident_bytes : k.b_stages * b_tile) + fixed;
 
     int rc;
     if ((rc = encode_act(&pl->tm_x, q->x, q->c_in, q->x_pixel_stride, q->batch, H, W, false, kHaloPitch, k.th + 2, 1, "x(halo)"))) return rc;
@@ -346,7 +367,9 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e != cudaSuccess) return fail((int)e, "conv3x3: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -354,7 +377,10 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
 }
 
 int conv3_plan_run(const yms_conv_plan* pl, cudaStream_t stream) {
-    cudaError_t le = launch_pdl(conv3x3_kernel, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    cudaError_t le;
+    if (pl->k3.sub == 1) le = launch_pdl(conv3x3_kernel<1>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    else if (pl->k3.sub == 2) le = launch_pdl(conv3x3_kernel<2>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    else le = launch_pdl(conv3x3_kernel<4>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     if (le != cudaSuccess) return fail((int)le, "conv3x3_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv3x3_kernel");
 }

@@ -48,6 +48,7 @@ struct Conv3Params {
     int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
     uint32_t mg_n_tiles, mg_super_x, mg_tiles_y;  // fast_div magics
     uint32_t halo_bytes;                       // 10 * (th + 2) * 128
+    int halo_stage;                            // smem stride between halo tiles (== halo_bytes, multiple of 128)
     const float* bias;
 };
 
