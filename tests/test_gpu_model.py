@@ -230,3 +230,34 @@ def test_detect_equals_postprocess_of_forward_and_oracle():
         want, wb, ws, wl = P.postprocess_image(pc[i], 0.3, 0.5, P.greedy_nms_c)
         assert np.array_equal(k.cpu().numpy(), want)
         assert np.array_equal(res[i][0].cpu().numpy(), wb) and np.array_equal(res[i][2].cpu().numpy(), wl)
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json configs at full resolution (small batch so the CPU oracle finishes in seconds)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("version,hw,batch", [("s", (1280, 1280), 2), ("m", (640, 640), 2), ("s", (640, 640), 3)])
+def test_full_resolution_configs(version, hw, batch):
+    """configs[1]/[2]/[4] shapes (S @640, base @640, S @1280 -> 33 600 anchors): raw logits vs the
+    bf16-contract oracle (gate 0.15: deeper/wider nets amplify bf16 rounding flips more; a wiring bug
+    gives ~1), decode consistency, and bit-exact NMS of OUR prediction vs the oracle post-process."""
+    from oracle import postprocess as P
+    from oracle import weights as W
+    from oracle import yolov8_oracle as O
+    m, sd = _model(version, seed=1)
+    x = W.make_images(batch, *hw, seed=7)
+    with torch.no_grad():
+        emu = O.forward_bf16_contract(sd, x[:1], return_parts=True)
+    raws = m.forward_raw(x.to(DEV))
+    for i in range(3):
+        assert rel_l2(raws[i][:1].permute(0, 3, 1, 2), emu["raw"][i]) < 0.15
+    pred = m(x.to(DEV))
+    a = sum((hw[0] // s) * (hw[1] // s) for s in (8, 16, 32))
+    assert pred.shape == (batch, a, 84)
+    want = O.decode([r.permute(0, 3, 1, 2).float().cpu() for r in raws], STRIDES)
+    assert float((pred[..., :4].cpu() - want[..., :4]).abs().max()) < 2e-2
+    assert float((pred[..., 4:].cpu() - want[..., 4:]).abs().max()) < 5e-6
+    boxes, scores, labels, keep, count = m.detect(x.to(DEV), 0.25, 0.45)
+    pc = pred.cpu().numpy()
+    for i in range(batch):
+        k = keep[i, :int(count[i])].cpu().numpy()
+        assert np.array_equal(k, P.postprocess_image(pc[i], 0.25, 0.45, P.greedy_nms_c)[0])
