@@ -84,6 +84,13 @@ int yms_stem_conv(const float* x_nchw, int batch, int in_h, int in_w, int c_out,
                   const float* weight, const float* bias,
                   void* y_nhwc_bf16, int64_t y_pixel_stride, void* stream);
 
+/* Same layer fed by the raw image: x uint8 NHWC [B,H,W,3] (what PIL / cv2 decode), with the reference's
+ * pre-processing ToTensor + Normalize(mean, std) (yolov8/tools/test.py:114-119; resize excluded) fused
+ * into the gather: v -> (v/255 - mean[c]) / std[c].  SURVEY.md section 8(f) rank 1. */
+int yms_stem_conv_u8(const uint8_t* x_nhwc, int batch, int in_h, int in_w, int c_out,
+                     const float* weight, const float* bias, const float* host_mean /* 3 */,
+                     const float* host_std /* 3 */, void* y_nhwc_bf16, int64_t y_pixel_stride, void* stream);
+
 /* Depthwise k x k (k in 3,5,7,9; stride 1; pad k/2) + folded BN + SiLU, NHWC bf16.
  * Conv(c, c, k, 1, k//2, groups=c) of components.py:69-77 as used by the repo-local MS-Block.
  * weight f32 [k*k][c] (tap-major), bias f32 [c]. */

@@ -261,3 +261,20 @@ def test_full_resolution_configs(version, hw, batch):
     for i in range(batch):
         k = keep[i, :int(count[i])].cpu().numpy()
         assert np.array_equal(k, P.postprocess_image(pc[i], 0.25, 0.45, P.greedy_nms_c)[0])
+
+
+def test_uint8_images_match_normalised_float_path():
+    """raw uint8 HWC batches (normalisation fused into the stem) give the same
+    detections pipeline as the reference-style normalised fp32 NCHW batch."""
+    from yolo_ms_b200 import ops
+    m, _ = _model("n", seed=1)
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (2, 160, 192, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    x = ((img.permute(0, 3, 1, 2).float() / 255.0) - mean) / std
+    raw_f = [r.clone() for r in m.forward_raw(x.to(DEV))]
+    raw_u = m.forward_raw(img.to(DEV))
+    for a, b in zip(raw_u, raw_f):
+        assert rel_l2(a, b.float()) < 0.05
+    pred = m(img.to(DEV))
+    assert pred.shape == (2, 20 * 24 + 10 * 12 + 5 * 6, 84)

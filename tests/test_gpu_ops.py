@@ -102,6 +102,22 @@ def test_stem_conv(ops, cout):
     assert rel_l2(y, ref32) < 1e-2
 
 
+def test_stem_conv_u8_fuses_totensor_normalize(ops):
+    """uint8 HWC image -> (v/255 - mean)/std -> stem, vs the fp32 stem on the reference's own
+    ToTensor + Normalize arithmetic (yolov8/tools/test.py:114-119)."""
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (2, 64, 96, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    x = ((img.permute(0, 3, 1, 2).float() / 255.0) - mean) / std                 # ToTensor + Normalize
+    w = (torch.randn(32, 3, 3, 3, generator=g) * 0.3).to(DEV); b = (torch.randn(32, generator=g) * 0.2).to(DEV)
+    y8 = torch.empty(2, 32, 48, 32, device=DEV, dtype=torch.bfloat16); y32 = torch.empty_like(y8)
+    ops.stem_conv_u8(img.to(DEV), w, b, y8)
+    ops.stem_conv(x.to(DEV).contiguous(), w, b, y32)
+    assert rel_l2(y8, y32.float()) < 2e-3
+    ref = F.silu(F.conv2d(x.to(DEV), w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert rel_l2(y8, ref) < 1e-2
+
+
 def test_sppf_pool_is_exact(ops):
     g = torch.Generator().manual_seed(1)
     for (h, w, c) in ((20, 24, 64), (5, 3, 8), (40, 40, 32), (50, 50, 16)):

@@ -253,8 +253,8 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 using namespace yms;
 
-int yms_stem_tc_launch(const float* x, int batch, int in_h, int in_w, int c_out, const float* weight, const float* bias,
-                       void* y, int64_t y_ps, cudaStream_t stream);   // stem_tc.cu (tensor-core path)
+int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* mean, const float* stdv, int batch, int in_h, int in_w,
+                       int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream);   // stem_tc.cu
 
 extern "C" int yms_stem_conv(const float* x, int batch, int in_h, int in_w, int c_out, const float* weight,
                              const float* bias, void* y, int64_t y_ps, void* stream) {
@@ -262,12 +262,21 @@ extern "C" int yms_stem_conv(const float* x, int batch, int in_h, int in_w, int 
     if (c_out <= 0 || (c_out % 16) != 0 || c_out > 256) return fail(YMS_E_UNSUPPORTED, "stem: c_out must be a multiple of 16 (<= 256)");
     if (!x || !weight || !bias || !y || !aligned16(y) || (y_ps % 8) != 0) return fail(YMS_E_ARG, "stem: bad pointers/strides");
     if (c_out <= 128 && !getenv("YMS_STEM_LEGACY"))
-        return yms_stem_tc_launch(x, batch, in_h, in_w, c_out, weight, bias, y, y_ps, (cudaStream_t)stream);
+        return yms_stem_tc_launch(x, nullptr, nullptr, nullptr, batch, in_h, in_w, c_out, weight, bias, y, y_ps, (cudaStream_t)stream);
     dim3 grid(ceil_div(in_w / 2, 128), in_h / 2, batch);
     size_t smem = (size_t)28 * c_out * sizeof(float);
     stem_conv_kernel<16><<<grid, 128, smem, (cudaStream_t)stream>>>(x, in_h, in_w, c_out, weight, bias,
                                                                     reinterpret_cast<__nv_bfloat16*>(y), y_ps);
     return check_launch("stem_conv_kernel");
+}
+
+extern "C" int yms_stem_conv_u8(const uint8_t* x, int batch, int in_h, int in_w, int c_out, const float* weight,
+                                const float* bias, const float* host_mean, const float* host_std, void* y, int64_t y_ps, void* stream) {
+    if (batch <= 0 || in_h <= 0 || in_w <= 0 || (in_h & 1) || (in_w & 1)) return fail(YMS_E_ARG, "stem_u8: bad image size");
+    if (c_out <= 0 || (c_out % 16) != 0 || c_out > 128) return fail(YMS_E_UNSUPPORTED, "stem_u8: c_out must be a multiple of 16 (<= 128)");
+    if (!x || !weight || !bias || !y || !host_mean || !host_std || !aligned16(y) || (y_ps % 8) != 0) return fail(YMS_E_ARG, "stem_u8: bad pointers/strides");
+    for (int c = 0; c < 3; ++c) if (!(host_std[c] > 0.f)) return fail(YMS_E_ARG, "stem_u8: std must be positive");
+    return yms_stem_tc_launch(nullptr, x, host_mean, host_std, batch, in_h, in_w, c_out, weight, bias, y, y_ps, (cudaStream_t)stream);
 }
 
 extern "C" int yms_sppf_pool(void* buf, int64_t ps, int batch, int h, int w, int c, void* stream) {

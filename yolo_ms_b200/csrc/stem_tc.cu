@@ -26,7 +26,10 @@ constexpr int kATile = 128 * 64;          // 8 KB: 128 pixels x 32 bf16
 constexpr int kStageOutS = 16384;
 
 struct StemParams {
-    const float* x; int batch, in_h, in_w, out_h, out_w, c_out;
+    const float* x;            // NCHW fp32 image (kU8 == false)
+    const unsigned char* xu8;  // NHWC uint8 image (kU8 == true): (v * scale[c] + shift[c]) == (v/255 - mean)/std
+    float scale[3], shift[3];
+    int batch, in_h, in_w, out_h, out_w, c_out;
     long long m_total; int total_tiles;
     const float* weight;     // f32 [c_out][27], BN folded
     const float* bias;       // f32 [c_out]
@@ -62,6 +65,34 @@ __device__ __forceinline__ void load_taps(const StemParams& p, long long pix, fl
         }
 }
 
+// uint8 HWC input with the reference's ToTensor + Normalize (yolov8/tools/test.py:114-119) fused in:
+// the 9 bytes of three horizontally adjacent RGB pixels are contiguous.  Padding taps are 0 AFTER
+// normalisation (the reference pads the normalised tensor).
+__device__ __forceinline__ void load_taps_u8(const StemParams& p, long long pix, float (&v)[27]) {
+    #pragma unroll
+    for (int i = 0; i < 27; ++i) v[i] = 0.f;
+    if (pix >= p.m_total) return;
+    const int ox = (int)(pix % p.out_w);
+    const long long t = pix / p.out_w;
+    const int oy = (int)(t % p.out_h);
+    const int b = (int)(t / p.out_h);
+    const int ix0 = 2 * ox - 1, iy0 = 2 * oy - 1;
+    #pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = iy0 + ky;
+        if (iy < 0) continue;
+        const unsigned char* row = p.xu8 + (((long long)b * p.in_h + iy) * p.in_w + ix0) * 3;
+        #pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            if (kx == 0 && ix0 < 0) continue;
+            #pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v[c * 9 + ky * 3 + kx] = fmaf((float)__ldg(row + kx * 3 + c), p.scale[c], p.shift[c]);
+        }
+    }
+}
+
+template <bool kU8>
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ StemParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -111,12 +142,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
         float cur[27], nxt[27];
         int seq = grp;                                              // sequence number of this CTA's tiles
         long long t = (long long)blockIdx.x + (long long)grp * gridDim.x;
-        if (t < p.total_tiles) load_taps(p, t * 128 + r, nxt);
+        if (t < p.total_tiles) { if (kU8) load_taps_u8(p, t * 128 + r, nxt); else load_taps(p, t * 128 + r, nxt); }
         for (; t < p.total_tiles; t += 2LL * gridDim.x, seq += 2) {
             #pragma unroll
             for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
             const long long tn = t + 2LL * gridDim.x;
-            if (tn < p.total_tiles) load_taps(p, tn * 128 + r, nxt);
+            if (tn < p.total_tiles) { if (kU8) load_taps_u8(p, tn * 128 + r, nxt); else load_taps(p, tn * 128 + r, nxt); }
             const int stage = seq % kStages;
             const uint32_t phase = (uint32_t)(seq / kStages) & 1u;
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -233,9 +264,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
 
 using namespace yms;
 
-// declared in glue.cu's dispatcher
-int yms_stem_tc_launch(const float* x, int batch, int in_h, int in_w, int c_out, const float* weight, const float* bias,
-                       void* y, int64_t y_ps, cudaStream_t stream) {
+// declared in glue.cu's dispatcher.  xu8 != nullptr selects the uint8-HWC + normalisation path.
+int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* mean, const float* stdv, int batch, int in_h, int in_w,
+                       int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream) {
     static thread_local struct Cache { const void* y; int64_t ps; int b, h, w, c; CUtensorMap map; bool ok; } cache = {};
     const int out_h = in_h / 2, out_w = in_w / 2;
     if (!(cache.ok && cache.y == y && cache.ps == y_ps && cache.b == batch && cache.h == in_h && cache.w == in_w && cache.c == c_out)) {
@@ -244,18 +275,23 @@ int yms_stem_tc_launch(const float* x, int batch, int in_h, int in_w, int c_out,
         cache.y = y; cache.ps = y_ps; cache.b = batch; cache.h = in_h; cache.w = in_w; cache.c = c_out; cache.ok = true;
     }
     StemParams p;
-    p.x = x; p.batch = batch; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.c_out = c_out;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.xu8 = xu8;
+    if (xu8) for (int c = 0; c < 3; ++c) { p.scale[c] = 1.0f / (255.0f * stdv[c]); p.shift[c] = -mean[c] / stdv[c]; }
+    p.batch = batch; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.c_out = c_out;
     p.m_total = (long long)batch * out_h * out_w;
     p.total_tiles = (int)((p.m_total + 127) / 128);
     p.weight = weight; p.bias = bias;
     const size_t smem = 1024 + kStages * kATile + 8192 + 2 * kStageOutS + 128 * 4 + (2 * kStages + 4) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "stem: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    stem_tc_kernel<<<grid, kStemThreads, smem, stream>>>(cache.map, p);
+    if (xu8) stem_tc_kernel<true><<<grid, kStemThreads, smem, stream>>>(cache.map, p);
+    else stem_tc_kernel<false><<<grid, kStemThreads, smem, stream>>>(cache.map, p);
     return check_launch("stem_tc_kernel");
 }

@@ -313,8 +313,12 @@ class Backbone(_Compiled):
         y0 = P.buf(b, h // 2, w // 2, self.conv0.conv.out_channels)
         P.hold(w0, b0)
         assert not P.steps, "the stem must be the first step of the program"
-        P.add(lambda: ops.stem_conv(image.tensor, w0, b0, y0), nbytes=4.0 * b * cin * h * w + 2.0 * y0.numel(),
-              flops=2.0 * y0.numel() * 27)
+        if image.u8:     # raw uint8 HWC images: ToTensor + Normalize fused into the stem
+            P.add(lambda: ops.stem_conv_u8(image.tensor, w0, b0, y0), nbytes=1.0 * b * cin * h * w + 2.0 * y0.numel(),
+                  flops=2.0 * y0.numel() * 27)
+        else:
+            P.add(lambda: ops.stem_conv(image.tensor, w0, b0, y0), nbytes=4.0 * b * cin * h * w + 2.0 * y0.numel(),
+                  flops=2.0 * y0.numel() * 27)
         P.eager_prefix = 1
         x = self.conv1.emit(P, y0)
         x = self.c2f_2.emit(P, x)
@@ -495,15 +499,26 @@ class YOLOv8(_Compiled):
 # program cache
 # =============================================================================================
 class ImageSlot:
-    """The caller's NCHW fp32 image batch, rebound on every call (no staging copy)."""
+    """The caller's image batch, rebound on every call (no staging copy): NCHW fp32 (the reference's
+    interface) or raw uint8 NHWC [B,H,W,3] (normalisation fused into the stem)."""
 
     def __init__(self, x: torch.Tensor):
-        self.shape = tuple(x.shape)
+        self.u8 = x.dtype == torch.uint8
+        if self.u8:
+            if x.dim() != 4 or x.shape[3] != 3:
+                raise YmsError("uint8 images must be NHWC [B,H,W,3]")
+            self.shape = (x.shape[0], 3, x.shape[1], x.shape[2])     # logical NCHW shape
+        else:
+            self.shape = tuple(x.shape)
         self.tensor = None
         self.bind(x)
 
     def bind(self, x: torch.Tensor):
-        if x.dtype != torch.float32 or not x.is_contiguous():
+        if self.u8:
+            if x.dtype != torch.uint8:
+                raise YmsError("this program was compiled for uint8 images")
+            x = x.contiguous()
+        elif x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         self.tensor = x
 
@@ -514,7 +529,7 @@ def _get_program(module: _Compiled, xs: Tuple[torch.Tensor, ...], build, image_i
     dev = xs[0].device
     if _device_of(module) != dev:
         raise YmsError("module parameters and input live on different devices")
-    key = tuple(tuple(x.shape) for x in xs) + (str(dev),)
+    key = tuple((tuple(x.shape), str(x.dtype)) for x in xs) + (str(dev),)
     cache = module._programs()
     hit = cache.get(key)
     if hit is not None:

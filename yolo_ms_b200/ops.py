@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from ._lib import ConvParams, YmsError, check
 
-__all__ = ["ConvPlan", "stem_conv", "dwconv", "sppf_pool", "upsample2x", "head_decode",
+__all__ = ["ConvPlan", "stem_conv", "stem_conv_u8", "dwconv", "sppf_pool", "upsample2x", "head_decode",
            "select_candidates", "nms_batched", "gather_detections", "YmsError"]
 
 
@@ -99,6 +99,23 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torc
     b, _, h, w = x.shape
     check(_lib.load().yms_stem_conv(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(),
                                     y.data_ptr(), _pixel_stride(y), _stream()), "yms_stem_conv")
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def stem_conv_u8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torch.Tensor,
+                 mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+    """x uint8 NHWC [B,H,W,3]; ToTensor + Normalize(mean, std) fused into the stem (tools/test.py:114-119)."""
+    _need_cuda(x, weight, bias, y)
+    if x.dtype != torch.uint8 or not x.is_contiguous() or x.dim() != 4 or x.shape[3] != 3:
+        raise YmsError("stem_u8: x must be contiguous uint8 [B,H,W,3]")
+    b, h, w, _ = x.shape
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    check(_lib.load().yms_stem_conv_u8(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(), m, s,
+                                       y.data_ptr(), _pixel_stride(y), _stream()), "yms_stem_conv_u8")
 
 
 def dwconv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torch.Tensor, ksize: int) -> None:
