@@ -10,7 +10,7 @@ import os
 import shutil
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyms_b200.so")
+LIB_PATH = os.environ.get("YMS_LIB") or os.path.join(_HERE, "libyms_b200.so")   # YMS_LIB: profiling build (scripts/role_prof.py)
 
 EXPORTS = [
     "yms_abi_version", "yms_last_error", "yms_launch_count",

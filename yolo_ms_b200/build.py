@@ -23,15 +23,19 @@ def _newest_source() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
-        return LIB
+def build(force: bool = False, verbose: bool = False, prof: bool = False) -> str:
+    """prof=True builds libyms_b200_prof.so with -DYMS_PROF (per-role cycle counters in the conv kernels,
+    used by scripts/role_prof.py through YMS_LIB=...); the product library never carries them."""
+    lib = LIB.replace(".so", "_prof.so") if prof else LIB
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _newest_source():
+        return lib
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", "prof" if prof else "rel")
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, *(["-DYMS_PROF"] if prof else []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -44,9 +48,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([NVCC, "-shared", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, prof="--prof" in sys.argv))

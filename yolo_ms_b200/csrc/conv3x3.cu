@@ -68,6 +68,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
                const __grid_constant__ Conv3Params p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];      // SWIZZLE_128B tiles need 1024-byte alignment
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;   // wait-cycle accumulators (dead code unless -DYMS_PROF)
+    (void)pw0; (void)pw1; (void)pw2; (void)pw3;
+    YMS_PROF_ONLY(const long long prof_t_entry = clock64(); long long* prof = p.prof ? p.prof + 16 * blockIdx.x : nullptr;)
     const uint32_t base = smem_u32(smem_dyn);
     unsigned char* gbase = smem_dyn;
     if (base & 1023u) __trap();
@@ -105,25 +108,27 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
+    if (warp == 0 && p.resident && elect_one()) {        // weights are constants of the program: fetched BEFORE the grid dependency
+        mbar_expect_tx(bar(kBarW), (uint32_t)(9 * p.kb) * (uint32_t)(p.block_n * 128));     // resolves (previous layer still draining)
+        for (int tap = 0; tap < 9; ++tap)
+            for (int cb = 0; cb < p.kb; ++cb)
+                tma_load_3d(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, 0, tap);
+    }
+    __syncwarp();
     pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
+    YMS_PROF_ONLY(const long long prof_t_start = clock64();)
     const uint32_t out_bytes = (uint32_t)(8 * p.th) * 128u;
     const int acc_stride = 512 / p.acc_stages;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            if (p.resident) {
-                mbar_expect_tx(bar(kBarW), (uint32_t)(9 * p.kb) * (uint32_t)(p.block_n * 128));
-                for (int tap = 0; tap < 9; ++tap)
-                    for (int cb = 0; cb < p.kb; ++cb)
-                        tma_load_3d(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, 0, tap);
-            }
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
                 const Item it = decode_item(p, t);
                 const int n0 = it.n_tile * p.block_n;
                 for (int cb = 0; cb < p.kb; ++cb) {
-                    mbar_wait(bar(kBarAEmpty + as), aph ^ 1u);
+                    mbar_wait_acc(bar(kBarAEmpty + as), aph ^ 1u, pw0);
                     mbar_expect_tx(bar(kBarAFull + as), (uint32_t)p.sub * p.halo_bytes);
                     for (int s = 0; s < p.sub; ++s)
                         tma_load_4d(smem_a + (as * p.sub + s) * p.halo_stage, &tm_x, bar(kBarAFull + as),
@@ -131,7 +136,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     if (++as == p.a_stages) { as = 0; aph ^= 1u; }
                     if (!p.resident) {
                         for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(bar(kBarBEmpty + bs), bph ^ 1u);
+                            mbar_wait_acc(bar(kBarBEmpty + bs), bph ^ 1u, pw1);
                             mbar_expect_tx(bar(kBarBFull + bs), (uint32_t)(p.block_n * 128));
                             tma_load_3d(smem_b + bs * b_tile_bytes, &tm_w, bar(kBarBFull + bs), cb * kBlockK, n0, tap);
                             if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
@@ -139,43 +144,53 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     }
                 }
             }
+            YMS_PROF_ONLY(if (prof) { prof[4] = clock64() - prof_t_start; prof[5] = pw0; prof[6] = pw1; })
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // The issue loop is the critical path for small N (an MMA lasts only N/2 cycles): all
-        // descriptor arithmetic is warp-uniform (uniform datapath) and hoisted out of the elected
-        // region; taps and k-steps are fully unrolled so the operands are base + immediate.
+        // ONE elected thread runs the whole loop: for small N an MMA is only max(N/2, 32 + N/4) cycles of tensor-pipe
+        // work (the A operand is re-read from shared memory at 128 B/cycle), so the issue path itself -- barrier wait,
+        // fence, descriptor moves, commit -- is what has to be short (scripts/ubench/mma_ring.cu).  Taps and k-steps are
+        // fully unrolled (operands = base + immediate); the try_wait of the next ring slot is issued before the MMAs of
+        // the current one.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t hi_a = (1ull << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
         const uint64_t hi_b = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
         const uint32_t halo16 = (uint32_t)p.halo_stage >> 4;
         const uint32_t btile16 = (uint32_t)b_tile_bytes >> 4;
-        if (p.resident) { mbar_wait(bar(kBarW), 0u); tc_fence_after(); }
-        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
-            mbar_wait(bar(kBarTEmpty + acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-            for (int cb = 0; cb < p.kb; ++cb) {
-                mbar_wait(bar(kBarAFull + as), aph);
-                tc_fence_after();
-                const int cvalid = p.c_in - cb * kBlockK;
-                const int ksteps = cvalid >= kBlockK ? 4 : ((cvalid + 15) >> 4);
-                const uint32_t a16 = ((smem_a + (uint32_t)(as * p.sub) * (uint32_t)p.halo_stage) & 0x3FFFFu) >> 4;
-                const uint32_t first = (cb != 0) ? 1u : 0u;
-                const bool last_cb = (cb == p.kb - 1);
-                if (p.resident) {
-                    const uint32_t b16 = ((smem_b + (uint32_t)cb * b_tile_bytes) & 0x3FFFFu) >> 4;
-                    const uint32_t bstride16 = (uint32_t)p.kb * btile16;
-                    if (elect_one()) {
+        if (elect_one()) {
+            if (p.resident) { mbar_wait_acc(bar(kBarW), 0u, pw2); tc_fence_after(); }
+            YMS_PROF_ONLY(int ntile = 0;)
+            const uint32_t a0_16 = (smem_a & 0x3FFFFu) >> 4, b0_16 = (smem_b & 0x3FFFFu) >> 4;
+            const uint32_t astage16 = (uint32_t)p.sub * halo16;
+            const int tail = ((p.c_in - (p.kb - 1) * kBlockK) + 15) >> 4;
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t a_ready = 0, b_ready = 0;
+            for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+                mbar_wait_acc(bar(kBarTEmpty + acc), acc_phase ^ 1u, pw3);
+                YMS_PROF_ONLY(++ntile;)
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+                for (int cb = 0; cb < p.kb; ++cb) {
+                    if (!a_ready) mbar_wait_acc(bar(kBarAFull + as), aph, pw0);
+                    tc_fence_after();
+                    int nas = as + 1; uint32_t naph = aph;
+                    if (nas == p.a_stages) { nas = 0; naph ^= 1u; }
+                    a_ready = mbar_try_wait(bar(kBarAFull + nas), naph);
+                    const int ksteps = (cb == p.kb - 1) ? tail : 4;
+                    const uint32_t a16 = a0_16 + (uint32_t)as * astage16;
+                    const uint32_t first = (cb != 0) ? 1u : 0u;
+                    const bool last_cb = (cb == p.kb - 1);
+                    if (p.resident) {
+                        const uint32_t b16 = b0_16 + (uint32_t)cb * btile16;
+                        const uint32_t bstride16 = (uint32_t)p.kb * btile16;
                         #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             const uint32_t toff = (uint32_t)((tap / 3) * kHaloPitch + (tap % 3)) * 8u;
                             #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 if (k < ksteps) {
-                                    // independent accumulators (sub-tiles) are interleaved: consecutive MMAs do not chain
+                                    // independent accumulators (sub-tiles) are interleaved
                                     #pragma unroll
                                     for (int sidx = 0; sidx < kSub; ++sidx)
                                         umma_bf16(d_tmem + (uint32_t)(sidx * p.block_n), hi_a | (uint64_t)(a16 + sidx * halo16 + toff + 2 * k),
@@ -185,27 +200,23 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                         }
                         umma_commit(bar(kBarAEmpty + as));
                         if (last_cb) umma_commit(bar(kBarTFull + acc));
-                    }
-                    __syncwarp();
-                } else {
-                    #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(bar(kBarBFull + bs), bph);
-                        tc_fence_after();
-                        const uint32_t b16 = ((smem_b + (uint32_t)bs * b_tile_bytes) & 0x3FFFFu) >> 4;
-                        const uint32_t toff = (uint32_t)((tap / 3) * kHaloPitch + (tap % 3)) * 8u;
-                        const uint32_t accf = tap ? 1u : first;
-                        if (elect_one()) {
+                    } else {
+                        #pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!b_ready) mbar_wait_acc(bar(kBarBFull + bs), bph, pw1);
+                            tc_fence_after();
+                            int nbs = bs + 1; uint32_t nbph = bph;
+                            if (nbs == p.b_stages) { nbs = 0; nbph ^= 1u; }
+                            b_ready = mbar_try_wait(bar(kBarBFull + nbs), nbph);
+                            const uint32_t b16 = b0_16 + (uint32_t)bs * btile16;
+                            const uint32_t toff = (uint32_t)((tap / 3) * kHaloPitch + (tap % 3)) * 8u;
+                            const uint32_t accf = tap ? 1u : first;
                             #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (k < ksteps)
-                                    umma_bf16(d_tmem, hi_a | (uint64_t)(a16 + toff + 2 * k), hi_b | (uint64_t)(b16 + 2 * k), idesc, k ? 1u : accf);
-                            }
-                            if (kSub == 2) {
-                                #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (k < ksteps)
-                                        umma_bf16(d_tmem + (uint32_t)p.block_n, hi_a | (uint64_t)(a16 + halo16 + toff + 2 * k),
+                                if (k < ksteps) {
+                                    #pragma unroll
+                                    for (int sidx = 0; sidx < (kSub >= 2 ? 2 : 1); ++sidx)
+                                        umma_bf16(d_tmem + (uint32_t)(sidx * p.block_n), hi_a | (uint64_t)(a16 + sidx * halo16 + toff + 2 * k),
                                                   hi_b | (uint64_t)(b16 + 2 * k), idesc, k ? 1u : accf);
                                 }
                             }
@@ -214,15 +225,17 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                                 umma_commit(bar(kBarAEmpty + as));
                                 if (last_cb) umma_commit(bar(kBarTFull + acc));
                             }
+                            bs = nbs; bph = nbph;
                         }
-                        __syncwarp();
-                        if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
                     }
+                    as = nas; aph = naph;
                 }
-                if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
-            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+            YMS_PROF_ONLY(if (prof) { prof[0] = clock64() - prof_t_start; prof[1] = pw0; prof[2] = pw1; prof[3] = pw3; prof[10] = pw2;
+                                      prof[11] = ntile; prof[9] = prof_t_start - prof_t_entry; })
         }
+        __syncwarp();
     } else {
         // ================= epilogue: up to 4 groups of 4 warps, group e drains accumulator stage e =================
         const int grp = (warp - 2) >> 2;
@@ -244,7 +257,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             uint32_t res_phase = 0u, acc_phase = 0u;
             for (int t = blockIdx.x + stage_id * gridDim.x; t < p.total_items; t += p.acc_stages * gridDim.x) {
                 const Item it = decode_item(p, t);
-                mbar_wait(bar(kBarTFull + stage_id), acc_phase);
+                mbar_wait_acc(bar(kBarTFull + stage_id), acc_phase, pw0);
                 acc_phase ^= 1u;
                 tc_fence_after();
                 int unit = 0;                                        // (sub-tile, chunk) units dealt round-robin to the groups
@@ -260,6 +273,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 if (lane == 0) mbar_arrive(bar(kBarTEmpty + stage_id));
             }
             if (e.leader) tma_store_wait_read<0>();
+            YMS_PROF_ONLY(if (prof && warp == 2 && lane == 0) { prof[7] = clock64() - prof_t_start; prof[8] = pw0; })
         }
     }
 
@@ -269,6 +283,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    YMS_PROF_ONLY(if (prof && threadIdx.x == 0) prof[12] = clock64() - prof_t_entry;)
 }
 
 }  // namespace
@@ -376,7 +391,10 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     return 0;
 }
 
-int conv3_plan_run(const yms_conv_plan* pl, cudaStream_t stream) {
+int conv3_plan_run(const yms_conv_plan* pl0, cudaStream_t stream) {
+    yms_conv_plan plc = *pl0;                  // by-value launch parameters; the debug hook patches the counter buffer in
+    plc.k3.prof = g_prof_buf;
+    const yms_conv_plan* pl = &plc;
     cudaError_t le;
     if (pl->k3.sub == 1) le = launch_pdl(conv3x3_kernel<1>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else if (pl->k3.sub == 2) le = launch_pdl(conv3x3_kernel<2>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);

@@ -58,6 +58,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                  const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ ConvKernelParams p) {
     extern __shared__ unsigned char smem_dyn[];
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;   // wait-cycle accumulators (dead code unless -DYMS_PROF)
+    (void)pw0; (void)pw1; (void)pw2; (void)pw3;
+    YMS_PROF_ONLY(const long long prof_t_entry = clock64(); long long* prof = p.prof ? p.prof + 16 * blockIdx.x : nullptr;)
     // carve-up (1024-byte aligned for SWIZZLE_128B)
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
@@ -102,8 +105,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
+    if (warp == 0 && p.resident && elect_one()) {        // weights are constants of the program: fetched BEFORE the grid dependency
+        const int kpt = p.kb1 + p.kb2;                   // resolves, i.e. while the previous layer is still draining
+        mbar_expect_tx(w_bar(), (uint32_t)kb_total_res * (uint32_t)b_tile_bytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+            for (int kb = 0; kb < kpt; ++kb)
+                tma_load_3d(smem_bres + (tap * kpt + kb) * b_tile_pad, &tm_w, w_bar(),
+                            kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, 0, tap);
+    }
+    __syncwarp();
     pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
 
+    YMS_PROF_ONLY(const long long prof_t_start = clock64();)
     const int kb_per_tap = p.kb1 + p.kb2;
     const int num_kb = p.taps * kb_per_tap;
     const int pad = p.ksize >> 1;
@@ -114,13 +127,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            if (p.resident) {                                   // whole weight set once per persistent CTA
-                mbar_expect_tx(w_bar(), (uint32_t)kb_total_res * (uint32_t)b_tile_bytes);
-                for (int tap = 0; tap < p.taps; ++tap)
-                    for (int kb = 0; kb < kb_per_tap; ++kb)
-                        tma_load_3d(smem_bres + (tap * kb_per_tap + kb) * b_tile_pad, &tm_w, w_bar(),
-                                    kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, 0, tap);
-            }
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
@@ -130,7 +136,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     const int xin = tc.x0 * p.stride + kx - pad;
                     const int yin = tc.y0 * p.stride + ky - pad;
                     for (int kb = 0; kb < kb_per_tap; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_wait_acc(empty_bar(stage), phase ^ 1u, pw0);
                         const uint32_t sa = smem_a0 + stage * stage_bytes;
                         const uint32_t sb = sa + kATileBytes;
                         mbar_expect_tx(full_bar(stage), stage_tx);
@@ -152,45 +158,57 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                     }
                 }
             }
+            YMS_PROF_ONLY(if (prof) { prof[4] = clock64() - prof_t_start; prof[5] = pw0; })
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // ONE elected thread runs the whole loop (measured with scripts/ubench/mma_ring.cu: the per-k-block cost of the
+        // issue path -- barrier wait, fence, descriptor moves, 4 x tcgen05.mma, commit -- is what bounds the small-N
+        // layers, and it is ~25 % lower without the per-k-block elect/warp-sync); the try_wait of the NEXT stage is
+        // issued before the MMAs of the current one so that its latency overlaps their issue.
         // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-        if (p.resident) { mbar_wait(w_bar(), 0u); tc_fence_after(); }
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
-            int kbi = 0;
-            for (int tap = 0; tap < p.taps; ++tap) {
-                for (int kb = 0; kb < kb_per_tap; ++kb, ++kbi) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    // warp-uniform descriptor arithmetic outside the elected region (uniform datapath)
-                    const int cvalid = (kb < p.kb1) ? (p.c_in1 - kb * kBlockK) : (p.c_in2 - (kb - p.kb1) * kBlockK);
-                    const int ksteps = cvalid >= kBlockK ? 4 : ((cvalid + 15) >> 4);
-                    const uint32_t sa = smem_a0 + stage * stage_bytes;
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(p.resident ? smem_bres + (uint32_t)kbi * b_tile_pad : sa + kATileBytes);
-                    const uint32_t first = kbi ? 1u : 0u;
-                    const bool last = (kbi == num_kb - 1);
-                    if (elect_one()) {
+        if (elect_one()) {
+            if (p.resident) { mbar_wait_acc(w_bar(), 0u, pw2); tc_fence_after(); }
+            YMS_PROF_ONLY(int ntile = 0;)
+            const uint64_t hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);   // make_sw128_desc without the address
+            const uint32_t a0_16 = (smem_a0 & 0x3FFFFu) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+            const uint32_t bres16 = (smem_bres & 0x3FFFFu) >> 4, btile16 = (uint32_t)b_tile_pad >> 4;
+            const int tail1 = ((p.c_in1 - (p.kb1 - 1) * kBlockK) + 15) >> 4;                   // k-steps of the last block of each source
+            const int tail2 = p.kb2 ? (((p.c_in2 - (p.kb2 - 1) * kBlockK) + 15) >> 4) : 4;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t ready = 0;                                      // prefetched try_wait result for (stage, phase)
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                mbar_wait_acc(tempty_bar(acc), acc_phase ^ 1u, pw1);  // epilogue has drained this accumulator
+                YMS_PROF_ONLY(++ntile;)
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+                int kbi = 0;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kb = 0; kb < kb_per_tap; ++kb, ++kbi) {
+                        if (!ready) mbar_wait_acc(full_bar(stage), phase, pw0);
+                        tc_fence_after();
+                        int nstage = stage + 1; uint32_t nphase = phase;
+                        if (nstage == p.num_stages) { nstage = 0; nphase ^= 1u; }
+                        ready = mbar_try_wait(full_bar(nstage), nphase);
+                        const int ksteps = (kb == p.kb1 - 1) ? tail1 : ((kb == kb_per_tap - 1) ? tail2 : 4);
+                        const uint32_t a16 = a0_16 + (uint32_t)stage * stage16;
+                        const uint32_t b16 = p.resident ? bres16 + (uint32_t)kbi * btile16 : a16 + (uint32_t)(kATileBytes >> 4);
+                        umma_bf16(d_tmem, hi | (uint64_t)a16, hi | (uint64_t)b16, idesc, kbi ? 1u : 0u);
                         #pragma unroll
-                        for (int k = 0; k < 4; ++k) {              // +32 B (16 bf16) along K inside the swizzle atom
-                            if (k < ksteps) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : first);
-                        }
+                        for (int k = 1; k < 4; ++k)                 // +32 B (16 bf16) along K inside the swizzle atom
+                            if (k < ksteps) umma_bf16(d_tmem, hi | (uint64_t)(a16 + 2 * k), hi | (uint64_t)(b16 + 2 * k), idesc, 1u);
                         umma_commit(empty_bar(stage));             // smem slot free once these MMAs retire
-                        if (last) umma_commit(tfull_bar(acc));
+                        if (kbi == num_kb - 1) umma_commit(tfull_bar(acc));
+                        stage = nstage; phase = nphase;
                     }
-                    __syncwarp();
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
-            if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+            YMS_PROF_ONLY(if (prof) { prof[0] = clock64() - prof_t_start; prof[1] = pw0; prof[3] = pw1; prof[10] = pw2; prof[11] = ntile;
+                                      prof[9] = prof_t_start - prof_t_entry; })
         }
+        __syncwarp();
     } else {
         // ================= epilogue: up to 4 groups of 4 warps, group e drains accumulator stage e =================
         const int grp = (warp - 2) >> 2;
@@ -213,7 +231,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             for (int t = blockIdx.x + stage_id * gridDim.x; t < p.total_tiles; t += p.acc_stages * gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
                 EpiTile tl; tl.n0 = tc.n_tile * p.block_n; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
-                mbar_wait(tfull_bar(stage_id), acc_phase);
+                mbar_wait_acc(tfull_bar(stage_id), acc_phase, pw0);
                 acc_phase ^= 1u;
                 tc_fence_after();
                 if (p.out_f32) {
@@ -227,6 +245,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 if (lane == 0) mbar_arrive(tempty_bar(stage_id));
             }
             if (e.leader) tma_store_wait_read<0>();
+            YMS_PROF_ONLY(if (prof && warp == 2 && lane == 0) { prof[7] = clock64() - prof_t_start; prof[8] = pw0; })
         }
     }
 
@@ -236,6 +255,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    YMS_PROF_ONLY(if (prof && threadIdx.x == 0) prof[12] = clock64() - prof_t_entry;)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -431,8 +451,10 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     if (!pl) return fail(YMS_E_ARG, "conv: null plan");
     if (pl->kind == 1) return conv3_plan_run(pl, (cudaStream_t)stream);
+    ConvKernelParams kp = pl->kp;
+    kp.prof = g_prof_buf;
     cudaError_t le = launch_pdl(conv_gemm_kernel, pl->grid, kThreads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
-                                pl->tm_y, pl->tm_res, pl->kp);
+                                pl->tm_y, pl->tm_res, kp);
     if (le != cudaSuccess) return fail((int)le, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");
 }

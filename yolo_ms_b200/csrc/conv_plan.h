@@ -29,6 +29,7 @@ struct ConvKernelParams {
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
     const float* bias;
     float* y_f32; long long y_ps;
+    long long* prof;                           // YMS_PROF builds: [grid][16] cycle counters (else unused)
 };
 
 
@@ -50,7 +51,10 @@ struct Conv3Params {
     uint32_t halo_bytes;                       // 10 * (th + 2) * 128
     int halo_stage;                            // smem stride between halo tiles (== halo_bytes, multiple of 128)
     const float* bias;
+    long long* prof;                           // YMS_PROF builds: [grid][16] cycle counters (else unused)
 };
+
+extern long long* g_prof_buf;                  // set by yms_debug_set_prof (capi.cu)
 
 inline uint32_t fast_div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
 

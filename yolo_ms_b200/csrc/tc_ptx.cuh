@@ -42,6 +42,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// Role-level cycle accounting (only in -DYMS_PROF builds, see scripts/role_prof.py): time spent in a wait.
+#ifdef YMS_PROF
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, long long& acc) {
+    const long long t = clock64(); mbar_wait(bar, parity); acc += clock64() - t;
+}
+#define YMS_PROF_ONLY(x) x
+#else
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, long long&) { mbar_wait(bar, parity); }
+#define YMS_PROF_ONLY(x)
+#endif
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

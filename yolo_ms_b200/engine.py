@@ -50,6 +50,8 @@ class Program:
         self._n_side = 0
         self._side: List[torch.cuda.Stream] = []
         self.launches = 0
+        self.names: List[str] = []     # one label per step (profiling / per-layer tables)
+        self.costs: dict = {}          # step index -> (flops, bytes) of non-conv steps
         self.flops = 0.0
         self.bytes = 0.0
 
@@ -67,18 +69,20 @@ class Program:
         plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
         self.plans.append(plan)
         self.hold(weight_packed, bias)
-        self._push(plan.run)
+        self._push(plan.run, plan.desc)
         self.flops += plan.flops
         self.bytes += plan.bytes
         return y
 
-    def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0):
-        self._push(fn)
+    def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0, name: str = "op"):
+        self._push(fn, name)
+        self.costs[len(self.steps) - 1] = (flops, nbytes)
         self.bytes += nbytes
         self.flops += flops
 
-    def _push(self, fn):
+    def _push(self, fn, name="op"):
         self.steps.append(fn)
+        self.names.append(name)
         self.schedule.append(("op", fn, self._branch))
         self.launches += 1
 

@@ -111,7 +111,8 @@ class Conv(_Compiled):
             wk = w.reshape(co, k * k).t().contiguous()          # [k*k, C]
             bb = b.contiguous()
             P.hold(wk, bb)
-            P.add(lambda: ops.dwconv(x, wk, bb, out, k), nbytes=4.0 * bsz * h * wd * co, flops=2.0 * bsz * h * wd * co * k * k)
+            P.add(lambda: ops.dwconv(x, wk, bb, out, k), nbytes=4.0 * bsz * h * wd * co, flops=2.0 * bsz * h * wd * co * k * k,
+                  name=f"dwconv{k}x{k} {co} @{h}x{wd}")
         else:
             raise YmsError("Conv: only groups=1 or depthwise stride-1 convolutions are implemented")
         return out
@@ -230,7 +231,7 @@ class SPPF(_Compiled):
         hc = self.conv1.conv.out_channels
         cat = P.buf(b, hh, ww, 4 * hc)
         self.conv1.emit(P, x, out=cat[..., :hc])
-        P.add(lambda: ops.sppf_pool(cat, hc), nbytes=2.0 * 4 * b * hh * ww * hc)
+        P.add(lambda: ops.sppf_pool(cat, hc), nbytes=2.0 * 4 * b * hh * ww * hc, name=f"sppf_pool {hc} @{hh}x{ww}")
         return self.conv2.emit(P, cat, out=out)
 
     def forward(self, x):
@@ -247,7 +248,8 @@ class Upsample(nn.Module):
         self.scale_factor, self.mode = scale_factor, mode
 
     def emit(self, P, x, out):
-        P.add(lambda: ops.upsample2x(x, out), nbytes=2.0 * 5 * x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3])
+        P.add(lambda: ops.upsample2x(x, out), nbytes=2.0 * 5 * x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3],
+              name=f"upsample2x {x.shape[3]} @{x.shape[1]}x{x.shape[2]}")
         return out
 
     def forward(self, x):
@@ -315,10 +317,10 @@ class Backbone(_Compiled):
         assert not P.steps, "the stem must be the first step of the program"
         if image.u8:     # raw uint8 HWC images: ToTensor + Normalize fused into the stem
             P.add(lambda: ops.stem_conv_u8(image.tensor, w0, b0, y0), nbytes=1.0 * b * cin * h * w + 2.0 * y0.numel(),
-                  flops=2.0 * y0.numel() * 27)
+                  flops=2.0 * y0.numel() * 27, name=f"stem(u8) 3->{y0.shape[3]} @{h}x{w}")
         else:
             P.add(lambda: ops.stem_conv(image.tensor, w0, b0, y0), nbytes=4.0 * b * cin * h * w + 2.0 * y0.numel(),
-                  flops=2.0 * y0.numel() * 27)
+                  flops=2.0 * y0.numel() * 27, name=f"stem 3->{y0.shape[3]} @{h}x{w}")
         P.eager_prefix = 1
         x = self.conv1.emit(P, y0)
         x = self.c2f_2.emit(P, x)

@@ -77,6 +77,8 @@ class ConvPlan:
         fl, by = C.c_double(), C.c_double()
         self._lib.yms_conv_plan_cost(self._h, C.byref(fl), C.byref(by))
         self.flops, self.bytes = fl.value, by.value
+        self.desc = (f"conv{ksize}x{ksize}/s{stride} {c_in}{'+' + str(c_in2) if c_in2 else ''}->{c_out} @{h}x{w}"
+                     f"{' +res' if residual is not None else ''}{' f32' if y.dtype == torch.float32 else ''}")
 
     def run(self) -> None:
         check(self._lib.yms_conv_plan_run(self._h, _stream()), "yms_conv_plan_run")
