@@ -291,13 +291,17 @@ def run_native(args):
         # decode / nms timed alone
         raws = model.forward_raw(x)
         ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        ea.record()
-        pred, (cb, cs, cl) = ops.head_decode(raws, [8.0, 16.0, 32.0], 80, with_candidates=True)
-        eb.record()
-        ops.nms_batched(cb, cs, cl, CONF, IOU, 80)
-        ec.record()
-        torch.cuda.synchronize()
-        dec_ms, nms_ms = ea.elapsed_time(eb), eb.elapsed_time(ec)
+        dec_ms = nms_ms = 0.0
+        for it in range(2 + reps):                      # 2 warm-up rounds (allocator, first-launch attributes), then the mean
+            ea.record()
+            pred, (cb, cs, cl) = ops.head_decode(raws, [8.0, 16.0, 32.0], 80, with_candidates=True)
+            eb.record()
+            ops.nms_batched(cb, cs, cl, CONF, IOU, 80)
+            ec.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                dec_ms += ea.elapsed_time(eb) / reps
+                nms_ms += eb.elapsed_time(ec) / reps
         A = pred.shape[1]
         dec_bytes = B * A * (144 * 4 + 84 * 4 + 24)
         ai = conv_fl / conv_by

@@ -1,0 +1,28 @@
+"""Phase timing of nms_kernel on the bench workload (needs the -DYMS_PROF build)."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("YMS_LIB", os.path.join(ROOT, "yolo_ms_b200", "libyms_b200_prof.so"))
+import torch
+from yolo_ms_b200 import YOLOv8, synth, _lib, ops
+dev = torch.device("cuda", 0)
+lib = _lib.load(); lib.yms_debug_set_prof.argtypes = [C.c_void_p]
+model = YOLOv8(version="s", num_classes=80)
+model.load_state_dict(synth.synthetic_state_dict(model, "s", "c2f", seed=1))
+model = model.to(dev).eval(); model.head.stride = torch.tensor([8.0, 16.0, 32.0])
+x = synth.make_images(32, 640, 640, seed=7).to(dev)
+raws = model.forward_raw(x)
+pred, (cb, cs, cl) = ops.head_decode(raws, [8.0, 16.0, 32.0], 80, with_candidates=True)
+for _ in range(2): ops.nms_batched(cb, cs, cl, 0.25, 0.45, 80)
+buf = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+assert lib.yms_debug_set_prof(buf.data_ptr()) == 1
+keep, cnt = ops.nms_batched(cb, cs, cl, 0.25, 0.45, 80)
+torch.cuda.synchronize(); lib.yms_debug_set_prof(None)
+b = buf.cpu()[:128].double()
+names = ["count", "compact", "sort", "segments+boxes", "tile scan+mask tiles", "sweep", "keep list", "ticket+concat"]
+d = b[:, 1:9] - b[:, 0:8]
+print("kept per image (first 4):", cnt[:4].tolist())
+for i, nm in enumerate(names):
+    col = d[:, i][b[:, i + 1] > 0]
+    if len(col): print(f"{nm:24s} mean {col.mean()/1e3:8.1f} kcyc  max {col.max()/1e3:8.1f} kcyc")
+tot = (b[:, 7] - b[:, 0]); print("total to stamp7: mean %.1f max %.1f kcyc" % (tot.mean()/1e3, tot.max()/1e3))

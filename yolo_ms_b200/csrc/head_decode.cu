@@ -11,6 +11,8 @@
 // shared memory, stages the [32, 4+nc] output tile and streams it out with 16-byte stores.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace yms {
 namespace {
 
@@ -150,6 +152,118 @@ __global__ void __launch_bounds__(kDecodeThreads) head_decode_kernel(DecodeArgs 
     }
 }
 
+// ---- v2: one thread per (anchor, 16-channel group), logits straight from global memory ----------------
+// ncu on the kernel above: 108 M warp instructions for 270 MB (issue-bound at 34 % of HBM): scalar shared
+// memory staging, an integer division per class score and warp-shuffle arg-max dominated.  Here a tile of
+// 32 anchors x (64 + nc) logits is 32 x G chunks of 16 channels (G = 4 DFL sides + nc/16 class groups); thread
+// (anchor, g) loads ITS 16 logits with 16-byte loads (consecutive threads read consecutive 64 B: coalesced),
+// keeps them in registers, and produces either one DFL distance or 16 sigmoid scores + their local arg-max.
+// One thread per anchor then assembles the box and the candidate; the [32, 4+nc] output tile is staged in
+// shared memory and streamed out with 16-byte stores.  ~10x fewer instructions per anchor.
+template <typename T>
+__device__ __forceinline__ void load16(const T* src, float (&v)[16]);
+template <>
+__device__ __forceinline__ void load16<float>(const float* src, float (&v)[16]) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) { const float4 t = __ldg(s4 + q); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+}
+template <>
+__device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* src, float (&v)[16]) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint4 t = __ldg(s4 + q);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { v[8 * q + 2 * j] = bf16_lo(w[j]); v[8 * q + 2 * j + 1] = bf16_hi(w[j]); }
+    }
+}
+
+constexpr int kMaxGroupsV2 = 4 + 16;            // nc <= 256
+
+template <typename T>
+__global__ void __launch_bounds__(kTileAnchors * kMaxGroupsV2) head_decode_v2_kernel(DecodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int no = a.no, nc = a.nc, nout = 4 + nc, ngroups = no >> 4, ncg = ngroups - 4;
+    float* s_out = reinterpret_cast<float*>(smem_raw);                           // [32][nout]
+    float* s_dist = s_out + kTileAnchors * nout;                                 // [32][4]
+    float* s_best = s_dist + kTileAnchors * 4;                                   // [32][ncg]
+    int* s_bidx = reinterpret_cast<int*>(s_best + kTileAnchors * ncg);           // [32][ncg]
+
+    const int img = blockIdx.x / a.tiles_per_image;
+    const int tile = blockIdx.x % a.tiles_per_image;
+    int sc = 0;
+    if (tile >= a.tiles_before[1]) sc = 1;
+    if (tile >= a.tiles_before[2]) sc = 2;
+    const int a0 = (tile - a.tiles_before[sc]) * kTileAnchors;
+    const int cnt = min(kTileAnchors, a.hw[sc] - a0);
+    const T* src = reinterpret_cast<const T*>(a.raw[sc]) + ((size_t)img * a.hw[sc] + a0) * no;
+    const int tid = threadIdx.x;
+    const int an = tid / ngroups, g = tid - an * ngroups;
+
+    if (an < cnt) {
+        float v[16];
+        load16<T>(src + (size_t)tid * 16, v);                                    // chunk tid of the contiguous tile
+        if (g < 4) {                                                             // DFL side g: sum_k k * softmax_k
+            float mx = v[0];
+            #pragma unroll
+            for (int k = 1; k < kRegMax; ++k) mx = fmaxf(mx, v[k]);
+            float sum = 0.f, wsum = 0.f;
+            #pragma unroll
+            for (int k = 0; k < kRegMax; ++k) { const float e = __expf(v[k] - mx); sum += e; wsum = fmaf((float)k, e, wsum); }
+            s_dist[an * 4 + g] = wsum / sum;
+        } else {                                                                 // 16 class scores
+            const int c0 = (g - 4) * 16;
+            float best = -INFINITY; int bi = 0x7fffffff;
+            float4* o4 = reinterpret_cast<float4*>(s_out + an * nout + 4 + c0);
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 r;
+                r.x = sigmoid_f(v[4 * q]); r.y = sigmoid_f(v[4 * q + 1]); r.z = sigmoid_f(v[4 * q + 2]); r.w = sigmoid_f(v[4 * q + 3]);
+                o4[q] = r;
+                const float rr[4] = {r.x, r.y, r.z, r.w};
+                #pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (rr[j] > best || bi == 0x7fffffff) { best = rr[j]; bi = c0 + 4 * q + j; }    // first max wins (torch.max)
+            }
+            s_best[an * ncg + (g - 4)] = best;
+            s_bidx[an * ncg + (g - 4)] = bi;
+        }
+    }
+    __syncthreads();
+
+    const size_t out_anchor = (size_t)img * a.total_anchors + a.anchor_base[sc] + a0;
+    if (tid < cnt) {                                                             // boxes (yolov8_head.py:139-143) + candidate
+        const int gidx = a0 + tid;
+        const float ax = (float)(gidx % a.w[sc]) + 0.5f, ay = (float)(gidx / a.w[sc]) + 0.5f;
+        const float st = a.stride[sc];
+        const float4 d = *reinterpret_cast<const float4*>(s_dist + tid * 4);
+        const float x1 = ax - d.x, y1 = ay - d.y, x2 = ax + d.z, y2 = ay + d.w;
+        float4 box;
+        box.x = ((x1 + x2) / 2.0f) * st;
+        box.y = ((y1 + y2) / 2.0f) * st;
+        box.z = (x2 - x1) * st;
+        box.w = (y2 - y1) * st;
+        *reinterpret_cast<float4*>(s_out + tid * nout) = box;
+        if (a.cand_boxes) {
+            float best = s_best[tid * ncg]; int bi = s_bidx[tid * ncg];
+            for (int q = 1; q < ncg; ++q) {
+                const float ob = s_best[tid * ncg + q];
+                if (ob > best) { best = ob; bi = s_bidx[tid * ncg + q]; }
+            }
+            a.cand_boxes[out_anchor + tid] = to_xyxy(box.x, box.y, box.z, box.w);
+            a.cand_scores[out_anchor + tid] = best;
+            a.cand_labels[out_anchor + tid] = bi;
+        }
+    }
+    __syncthreads();
+    const float4* s4 = reinterpret_cast<const float4*>(s_out);
+    float4* d4 = reinterpret_cast<float4*>(a.pred + out_anchor * nout);
+    const int nvec = (cnt * nout) >> 2;
+    for (int i = tid; i < nvec; i += blockDim.x) d4[i] = s4[i];
+}
+
 // pred [B*A, 4+nc] -> candidates; one warp per anchor, rows are read coalesced.
 __global__ void __launch_bounds__(256) select_candidates_kernel(const float* pred, long long rows, int nc,
                                                                  float4* boxes, float* scores, int32_t* labels) {
@@ -212,6 +326,14 @@ extern "C" int yms_head_decode(const void* raw0, const void* raw1, const void* r
     const long long grid = (long long)batch * tiles;
     if (grid > 0x7fffffffLL) return fail(YMS_E_UNSUPPORTED, "decode: grid too large");
     cudaError_t e;
+    if ((num_classes % 16) == 0 && num_classes <= 256 && !getenv("YMS_DECODE_V1")) {      // v2: one thread per 16-channel chunk
+        const int ngroups = a.no / 16, ncg = ngroups - 4;
+        const size_t smem2 = (size_t)kTileAnchors * ((4 + num_classes) + 4 + 2 * ncg) * 4;
+        const int threads = kTileAnchors * ngroups;
+        if (raw_dtype == YMS_DTYPE_F32) head_decode_v2_kernel<float><<<(unsigned)grid, threads, smem2, (cudaStream_t)stream>>>(a);
+        else head_decode_v2_kernel<__nv_bfloat16><<<(unsigned)grid, threads, smem2, (cudaStream_t)stream>>>(a);
+        return check_launch("head_decode_v2_kernel");
+    }
     if (raw_dtype == YMS_DTYPE_F32) {
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(head_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
             return fail((int)e, "decode: smem attribute");

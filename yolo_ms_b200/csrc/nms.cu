@@ -23,8 +23,17 @@
 //      lists in class order into the final keep list.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace yms {
+extern long long* g_prof_buf;
 namespace {
+
+#ifdef YMS_PROF
+#define NMS_STAMP(i) do { if (a.prof && threadIdx.x == 0) a.prof[16 * blockIdx.x + (i)] = clock64(); } while (0)
+#else
+#define NMS_STAMP(i) do { } while (0)
+#endif
 
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
@@ -62,6 +71,15 @@ __device__ __forceinline__ bool suppresses(const float4& bi, float ai, const flo
     float inter = __fmul_rn(w, h);
     if (!(inter > 0.0f)) return false;          // ovr is 0 or NaN: never > thr (thr >= 0)
     float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    // Division-free decision whenever it is provably the same as the reference's rounded quotient: with
+    // q = inter / uni (real), fl(q) > thr_f is certain for inter >= thr_f*uni*(1 + 2e-6) and impossible for
+    // inter <= thr_f*uni*(1 - 2e-6) (two fp32 products: <= 1.2e-7 relative error; the quotient's rounding: 6e-8;
+    // the magnitude guards keep every value normal).  Only the 4e-6-wide band in between pays for __fdiv_rn.
+    if (inter > 1e-15f && uni > 1e-15f && uni < 1e15f) {
+        const float t = __fmul_rn(thr_f, uni);
+        if (inter >= __fmul_rn(t, 1.000002f)) return true;
+        if (inter <= __fmul_rn(t, 0.999998f)) return false;
+    }
     float ovr = __fdiv_rn(inter, uni);
     // (double)ovr > thr  <=>  ovr > thr_f with thr_f = largest float <= thr (host computes it)
     return ovr > thr_f;
@@ -123,6 +141,85 @@ __device__ __forceinline__ unsigned resolve_chunk(const float4& bj, float aj, bo
     return alive;
 }
 
+// ---- IoU bitmask path (fast path when the masks fit in shared memory) ------------------------------------------
+// A class segment of n sorted boxes is cut into W = ceil(n/32) blocks; tile (k, w >= k) of its strictly-upper-
+// triangular suppression matrix is 32 words: word l = the 32 bits "row 32k+l suppresses column 32w+j".
+//   phase 1 (all 32 warps, tiles of all classes dealt round-robin): every pair test is independent -- no serial
+//            chain through the greedy order;
+//   phase 2 (one warp per class): the greedy order is replayed on the words alone -- per block a 32-step shuffle
+//            sweep over the diagonal tile decides which rows survive, the words of the survivors against later
+//            columns are OR-reduced (__reduce_or_sync) into `removed` (lane w holds word w, so W <= 32).
+// Same pair predicate and same order as the reference => bit-identical keep lists.
+__device__ __forceinline__ int tile_row_offset(int W, int k) { return k * W - ((k * (k - 1)) >> 1); }   // tiles before row k
+
+// Pair predicate for FINITE boxes (the bitmask path is only taken when every box of the CTA is finite): fmaxf/fminf
+// equal std::max/std::min on finite values up to the sign of zero (which cannot make `inter > 0` true), every
+// operation is individually rounded like the reference's, and the decision is branch-free except for the 4e-6-wide
+// band around the threshold that needs the exactly rounded quotient.
+__device__ __forceinline__ bool suppresses_finite(const float4& bi, float ai, const float4& bj, float aj, float thr_f) {
+    const float w = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.0f);
+    const float h = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.0f);
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    const float t = __fmul_rn(thr_f, uni);
+    const bool guard = inter > 1e-15f && uni > 1e-15f && uni < 1e15f;
+    const bool sure_t = guard && inter >= __fmul_rn(t, 1.000002f);
+    const bool sure_f = (guard && inter <= __fmul_rn(t, 0.999998f)) || !(inter > 0.0f);
+    bool hit = sure_t;
+    if (!(sure_t || sure_f)) hit = __fdiv_rn(inter, uni) > thr_f;
+    return hit;
+}
+
+template <bool kDiag>
+__device__ __forceinline__ void nms_mask_tile(const float4* sb, int n, int k, int w, unsigned* out, float thr_f, int lane) {
+    const int r = 32 * k + lane;
+    const float4 bi = (r < n) ? sb[r] : make_float4(0.f, 0.f, 0.f, 0.f);         // empty rows: inter == 0, never suppress
+    const float ai = box_area(bi);
+    const int jn = min(32, n - 32 * w);
+    unsigned word = 0u;
+    #pragma unroll 4
+    for (int jj = 0; jj < jn; ++jj) {                                            // warp-uniform trip count, broadcast reads
+        const float4 bj = sb[32 * w + jj];
+        const bool hit = (!kDiag || lane < jj) && suppresses_finite(bi, ai, bj, box_area(bj), thr_f);
+        word |= hit ? (1u << jj) : 0u;
+    }
+    out[lane] = word;
+}
+
+// returns the kept count; survivor keys compacted in place
+__device__ __forceinline__ int nms_mask_sweep(const unsigned* tiles, unsigned long long* sk, int n, int lane) {
+    const int W = (n + 31) >> 5;
+    unsigned removed = 0u;
+    for (int k = 0; k < W; ++k) {
+        const unsigned* row = tiles + (size_t)tile_row_offset(W, k) * 32;
+        const unsigned diag = row[lane];
+        unsigned rem = __shfl_sync(0xffffffffu, removed, k);
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const unsigned mi = __shfl_sync(0xffffffffu, diag, i);
+            rem |= ((rem >> i) & 1u) ? 0u : mi;                                  // row i survives -> it removes its later neighbours
+        }
+        if (lane == k) removed = rem;
+        const bool alive = (32 * k + lane < n) && !((rem >> lane) & 1u);
+        for (int w = k + 1; w < W; ++w) {
+            const unsigned red = __reduce_or_sync(0xffffffffu, alive ? row[(w - k) * 32 + lane] : 0u);
+            if (lane == w) removed |= red;
+        }
+    }
+    int kept = 0;
+    for (int k = 0; k < W; ++k) {
+        const int r = 32 * k + lane;
+        const unsigned long long key = (r < n) ? sk[r] : kInvalidKey;
+        const unsigned rem = __shfl_sync(0xffffffffu, removed, k);
+        const bool alive = (r < n) && !((rem >> lane) & 1u);
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        __syncwarp();                                                            // the block's keys are in registers before its (lower) slots are rewritten
+        if (alive) sk[kept + __popc(bal & ((1u << lane) - 1u))] = key;
+        kept += __popc(bal);
+    }
+    return kept;
+}
+
 struct NmsArgs {
     const float4* boxes; const float* scores; const int32_t* labels; const int32_t* n_valid;
     int n, num_classes, groups; float conf; float thr_f;
@@ -132,21 +229,21 @@ struct NmsArgs {
     int32_t* ws_count;             // [B*G]
     unsigned int* ws_ticket;       // [B] zeroed by the host before the launch
     int n_pad_full;                // pow2(n)
+    long long* prof;               // -DYMS_PROF builds: [grid][16] phase time stamps
+    int mask_tile_limit;           // bitmask path only below this many 32x32 tiles per CTA (else pipelined greedy chunks)
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);
-    float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)kFastCap * 8);      // fast path only
     const int G = a.groups;
     const int b = blockIdx.x / G, g = blockIdx.x % G;
-    const int c_lo = (int)((long long)g * a.num_classes / G), c_hi = (int)((long long)(g + 1) * a.num_classes / G);
-    const int ncl = c_hi - c_lo;                                                    // classes owned by this CTA
-    int* cls_start = reinterpret_cast<int*>(smem_raw + kKeyRegionBytes);            // [ncl + 1]
-    int* cls_count = cls_start + (ncl + 1);                                         // [ncl + 1] kept counts, then offsets
-    int* chunk_base = cls_count + (ncl + 1);                                        // [ncl + 1]
-    volatile unsigned* state = reinterpret_cast<volatile unsigned*>(chunk_base + (ncl + 1));   // [ncl] (done chunks<<16 | kept)
-    __shared__ int s_count, s_next, s_last;
+    const int nc = a.num_classes;
+    int* cls_start = reinterpret_cast<int*>(smem_raw + kKeyRegionBytes);            // [nc + 1] (a CTA may own up to nc classes)
+    int* cls_count = cls_start + (nc + 1);                                          // [nc + 1] kept counts, then offsets
+    int* chunk_base = cls_count + (nc + 1);                                         // [nc + 1]; first: the image's class histogram
+    volatile unsigned* state = reinterpret_cast<volatile unsigned*>(chunk_base + (nc + 1));   // [nc] (done chunks<<16 | kept)
+    __shared__ int s_count, s_next, s_last, s_clo, s_chi;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n;
@@ -155,30 +252,64 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     const float* scores = a.scores + (size_t)b * n;
     const int32_t* labels = a.labels + (size_t)b * n;
 
+    NMS_STAMP(0);
     if (tid == 0) { s_count = 0; s_next = 0; s_last = 0; }
+    int* hist = chunk_base;
+    for (int c = tid; c <= nc; c += kNmsThreads) hist[c] = 0;
     __syncthreads();
 
-    // ---- A0: count this CTA's candidates --------------------------------------------------
-    {
-        int cnt = 0;
-        for (int i = tid; i < nb; i += kNmsThreads) {
-            const float s = scores[i]; const int lab = labels[i];
-            cnt += (s > a.conf && lab >= c_lo && lab < c_hi) ? 1 : 0;
-        }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && cnt) atomicAdd(&s_count, cnt);
+    // ---- A0: class histogram of the image's candidates; the G CTAs of an image all derive the SAME contiguous class
+    // ranges from it, balanced by the pair-test cost W(W+1)/2 (W = ceil(n_c / 32)) instead of by class count ---------
+    for (int i = tid; i < nb; i += kNmsThreads) {
+        const float sc = scores[i]; const int lab = labels[i];
+        if (sc > a.conf && lab >= 0 && lab < nc) atomicAdd(&hist[lab], 1);
     }
     __syncthreads();
+    if (warp == 0) {
+        long long total = 0;
+        for (int c = lane; c < nc; c += 32) { const int w = (hist[c] + 31) >> 5; total += ((w * (w + 1)) >> 1) + 1; }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        // class c belongs to group floor(cost_before(c) * G / total): monotone => contiguous ranges
+        long long running = 0; int lo = nc, hi = 0, cnt = 0;
+        for (int base = 0; base < nc; base += 32) {
+            const int c = base + lane;
+            const int w = (c < nc) ? ((hist[c] + 31) >> 5) : 0;
+            const long long v = (c < nc) ? (long long)(((w * (w + 1)) >> 1) + 1) : 0;
+            long long incl = v;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (c < nc) {
+                int grp = (int)(((running + incl - v) * G) / total);
+                if (grp > G - 1) grp = G - 1;
+                if (grp == g) { lo = min(lo, c); hi = max(hi, c + 1); cnt += hist[c]; }
+            }
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (lane == 0) { s_clo = (hi > lo) ? lo : 0; s_chi = (hi > lo) ? hi : 0; s_count = cnt; }
+    }
+    __syncthreads();
+    const int c_lo = s_clo, c_hi = s_chi;
+    const int ncl = c_hi - c_lo;                                                    // classes owned by this CTA
     const int m = s_count;
     int n_pad = 32;
     while (n_pad < m) n_pad <<= 1;
     const bool fast = (m <= kFastCap);
     const bool in_smem = (n_pad <= kSortTile);
+    float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)n_pad * 8);        // fast path only: boxes right after the keys
+    unsigned* smask = reinterpret_cast<unsigned*>(sbox + m);                        // bitmask path: tiles after the boxes
+    const int mask_tile_cap = fast ? (int)((kKeyRegionBytes - (size_t)n_pad * 8 - (size_t)m * 16) / 128) : 0;
     unsigned long long* keys = in_smem ? skeys : (a.ws_keys + (size_t)blockIdx.x * a.n_pad_full);
     __syncthreads();
     if (tid == 0) s_count = 0;
     __syncthreads();
 
+    NMS_STAMP(1);
     // ---- A1: compacted keys (any order: the keys are unique and get sorted) ----------------------
     for (int i0 = 0; i0 < nb; i0 += kNmsThreads) {
         const int i = i0 + tid;
@@ -199,6 +330,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     for (int i = m + tid; i < n_pad; i += kNmsThreads) keys[i] = kInvalidKey;
     __syncthreads();
 
+    NMS_STAMP(2);
     // ---- B: sort -----------------------------------------------------------------------
     if (in_smem) {
         for (int k = 2; k <= n_pad; k <<= 1) bitonic_tile_steps(skeys, n_pad, 0, k, k >> 1);
@@ -232,16 +364,72 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         }
     }
 
+    NMS_STAMP(3);
     // ---- C: class segment table (local class index = key >> 52) --------------------------------
     for (int i = tid; i <= m; i += kNmsThreads) {
         int lab_prev = (i == 0) ? -1 : (int)(keys[i - 1] >> 52);
         int lab = (i == m) ? ncl : (int)(keys[i] >> 52);
         for (int c = lab_prev + 1; c <= lab; ++c) cls_start[c] = i;
     }
-    if (fast) for (int i = tid; i < m; i += kNmsThreads) sbox[i] = boxes[(int)(keys[i] & kIdxMask)];
-    __syncthreads();
-
+    int nonfinite = 0;
+    if (fast) for (int i = tid; i < m; i += kNmsThreads) {
+        const float4 bx = boxes[(int)(keys[i] & kIdxMask)];
+        sbox[i] = bx;
+        nonfinite |= !(fabsf(bx.x) <= 3.0e38f && fabsf(bx.y) <= 3.0e38f && fabsf(bx.z) <= 3.0e38f && fabsf(bx.w) <= 3.0e38f);
+    }
+    nonfinite = __syncthreads_or(nonfinite);
+    NMS_STAMP(4);
+    // tile_base (aliases chunk_base) = exclusive scan of the per-class tile counts W(W+1)/2; W > 32 disables the path
+    int use_mask = 0;
     if (fast) {
+        if (warp == 0) {
+            int running = 0, too_big = 0;
+            for (int base = 0; base < ncl; base += 32) {
+                const int c = base + lane;
+                const int wc = (c < ncl) ? ((cls_start[c + 1] - cls_start[c] + 31) >> 5) : 0;
+                too_big |= (wc > 32) ? 1 : 0;
+                const int v = (wc * (wc + 1)) >> 1;
+                int incl = v;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                if (c < ncl) chunk_base[c] = running + incl - v;
+                running += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            too_big = __any_sync(0xffffffffu, too_big);
+            if (lane == 0) { chunk_base[ncl] = running; s_last = (!too_big && !nonfinite && running <= mask_tile_cap && running <= a.mask_tile_limit) ? 1 : 0; }
+        }
+        __syncthreads();
+        use_mask = s_last;
+        __syncthreads();
+        if (tid == 0) s_last = 0;
+    }
+
+    if (use_mask) {
+        // ---- D (bitmask) ------------------------------------------------------------------------------------
+        const int total_tiles = chunk_base[ncl];
+        for (int t = warp; t < total_tiles; t += kNmsWarps) {
+            int lo = 0, hi = ncl - 1;                      // largest c with tile_base[c] <= t
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= t) lo = mid; else hi = mid - 1; }
+            const int c = lo, s0 = cls_start[c], nseg = cls_start[c + 1] - s0, W = (nseg + 31) >> 5;
+            int u = t - chunk_base[c], k = 0, rowlen = W;
+            while (u >= rowlen) { u -= rowlen; --rowlen; ++k; }
+            if (u == 0) nms_mask_tile<true>(sbox + s0, nseg, k, k, smask + (size_t)t * 32, a.thr_f, lane);
+            else nms_mask_tile<false>(sbox + s0, nseg, k, k + u, smask + (size_t)t * 32, a.thr_f, lane);
+        }
+        __syncthreads();
+        NMS_STAMP(5);
+        for (;;) {                                         // big classes first: their sweep is the critical path
+            int v = 0;
+            if (lane == 0) v = atomicAdd(&s_next, 1);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v >= 2 * ncl) break;
+            const int c = (v < ncl) ? v : v - ncl;
+            const int s0 = cls_start[c], nseg = cls_start[c + 1] - s0;
+            if ((nseg > 128) != (v < ncl)) continue;
+            const int kept = nseg ? nms_mask_sweep(smask + (size_t)chunk_base[c] * 32, skeys + s0, nseg, lane) : 0;
+            if (lane == 0) cls_count[c] = kept;
+        }
+    } else if (fast) {
         // ---- D (fast): pipelined chunks -------------------------------------------------------
         if (warp == 0) {                                   // chunk_base = exclusive scan of ceil(n_c / 32)
             int running = 0;
@@ -322,6 +510,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     }
     __syncthreads();
 
+    NMS_STAMP(6);
     // ---- E: per-CTA keep list, then the last CTA of the image concatenates -------------------------
     if (warp == 0) {
         int running = 0;
@@ -348,6 +537,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         if (tid == 0) a.keep_count[b] = my_total;
         return;
     }
+    NMS_STAMP(7);
     if (tid == 0) a.ws_count[blockIdx.x] = my_total;
     __threadfence();
     __syncthreads();
@@ -368,6 +558,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     }
     for (int i = off + tid; i < n; i += kNmsThreads) keep[i] = -1;
     if (tid == 0) a.keep_count[b] = off;
+    NMS_STAMP(8);
 }
 
 __global__ void gather_dets_kernel(const float4* boxes, const float* scores, const int32_t* labels,
@@ -457,12 +648,13 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.ws_stage = reinterpret_cast<int32_t*>(ws + w.stage);
     a.ws_count = reinterpret_cast<int32_t*>(ws + w.count);
     a.ws_ticket = reinterpret_cast<unsigned int*>(ws + w.ticket);
+    a.prof = g_prof_buf;
+    { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 1 << 30; }(); a.mask_tile_limit = lim; }
     if (groups > 1) {
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
         if (e != cudaSuccess) return fail((int)e, "nms: ticket memset failed");
     }
-    const int ncl_max = (num_classes + groups - 1) / groups + 1;
-    const size_t smem = kKeyRegionBytes + (size_t)(ncl_max + 1) * 4 * 4 + 16;
+    const size_t smem = kKeyRegionBytes + (size_t)(num_classes + 2) * 4 * 4 + 16;   // class tables sized for all classes (balanced ranges)
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
