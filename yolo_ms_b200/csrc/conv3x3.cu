@@ -90,15 +90,15 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
-        if (p.has_res) prefetch_tmap(&tm_res);
-        for (int s = 0; s < kRing; ++s) {
-            mbar_init(bar(kBarAFull + s), 1); mbar_init(bar(kBarAEmpty + s), 1);
-            mbar_init(bar(kBarBFull + s), 1); mbar_init(bar(kBarBEmpty + s), 1);
+    if (warp == 0) {                                  // barriers initialised lane-parallel: the prologue is paid by every launch
+        if (lane == 0) {
+            prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
+            if (p.has_res) prefetch_tmap(&tm_res);
         }
-        for (int s = 0; s < kEpiGroups; ++s) { mbar_init(bar(kBarTFull + s), 1); mbar_init(bar(kBarTEmpty + s), 4 * (kEpiGroups / p.acc_stages)); mbar_init(bar(kBarRes + s), 1); }
-        mbar_init(bar(kBarW), 1);
+        for (int i = lane; i < kNumBars; i += 32) {
+            const bool is_tempty = i >= kBarTEmpty && i < kBarTEmpty + 4;
+            mbar_init(bar(i), is_tempty ? 4 * (kEpiGroups / p.acc_stages) : 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);

@@ -88,14 +88,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
-        if (p.kb2) prefetch_tmap(&tm_x2);
-        prefetch_tmap(&tm_y);
-        if (p.has_res) prefetch_tmap(&tm_res);
-        for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kEpiGroups; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * (kEpiGroups / p.acc_stages)); mbar_init(res_bar(s), 1); }
-        mbar_init(w_bar(), 1);
+    if (warp == 0) {                                  // one barrier per lane: the prologue is paid by every launch
+        if (lane == 0) {
+            prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
+            if (p.kb2) prefetch_tmap(&tm_x2);
+            prefetch_tmap(&tm_y);
+            if (p.has_res) prefetch_tmap(&tm_res);
+        }
+        if (lane < 2 * kMaxStages + 13) {
+            const bool is_tempty = lane >= 2 * kMaxStages + 4 && lane < 2 * kMaxStages + 8;
+            mbar_init(bar0 + 8u * lane, is_tempty ? 4 * (kEpiGroups / p.acc_stages) : 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);

@@ -2,13 +2,14 @@
 // + BN + SiLU, yolov8/model/components.py:69-77) on the tensor cores.
 //
 // Input is the caller's NCHW fp32 image, output NHWC bf16.  K = 3*3*3 = 27 is padded to 32:
-//   * 8 producer warps gather the 27 taps of one output pixel per thread straight from the NCHW
+//   * 16 producer warps (4 groups dealing tiles round-robin) gather the 27 taps of one output pixel per thread straight from the NCHW
 //     image (next tile's loads are issued before the current tile is converted, so ~2 x 27 loads per
 //     thread stay in flight), convert to bf16 and write the pixel's 64-byte K row into a
 //     NON-swizzled K-major UMMA tile (8x16B core matrices: LBO = 128 B along K, SBO = 512 B along M);
 //   * one elected thread issues 2 tcgen05.mma (M=128, N=c_out, K=16) per 128-pixel tile against the
 //     weight tile that stays resident in shared memory, accumulating in TMEM (2 stages);
-//   * 8 epilogue warps: tcgen05.ld -> +bias -> SiLU -> bf16 -> swizzled staging -> TMA store.
+//   * 2 independent epilogue groups of 4 warps (conv_epilogue.cuh), group e draining accumulator stage e of every 2nd
+//     tile: tcgen05.ld -> +bias -> SiLU -> bf16 -> swizzled staging -> TMA store.
 // HBM-bound: 12 B in + 2*c_out B out per output pixel.
 #include "conv_plan.h"
 
@@ -19,11 +20,12 @@ namespace {
 
 using namespace tc;
 
-constexpr int kProdWarps = 8;
-constexpr int kStemThreads = kProdWarps * 32 + 32 + kEpiThreads;     // 544
-constexpr int kStages = 4;
+constexpr int kProdWarps = 16;             // 4 gather groups of 4 warps: the gather is latency-bound, bytes in flight = warps x 27 loads
+constexpr int kProdGroups = kProdWarps / 4;
+constexpr int kStemEpiGroups = 2;
+constexpr int kStemThreads = kProdWarps * 32 + 32 + kStemEpiGroups * kEpiGroupThreads;     // 800
+constexpr int kStages = 8;
 constexpr int kATile = 128 * 64;          // 8 KB: 128 pixels x 32 bf16
-constexpr int kStageOutS = 16384;
 
 struct StemParams {
     const float* x;            // NCHW fp32 image (kU8 == false)
@@ -46,10 +48,10 @@ __device__ __forceinline__ void load_taps(const StemParams& p, long long pix, fl
         for (int i = 0; i < 27; ++i) v[i] = 0.f;
         return;
     }
-    const int ox = (int)(pix % p.out_w);
-    const long long t = pix / p.out_w;
-    const int oy = (int)(t % p.out_h);
-    const int b = (int)(t / p.out_h);
+    const uint32_t t = (uint32_t)pix / (uint32_t)p.out_w;            // 32-bit index math (pix < 2^31, checked by the host)
+    const int ox = (int)((uint32_t)pix - t * (uint32_t)p.out_w);
+    const uint32_t b = t / (uint32_t)p.out_h;
+    const int oy = (int)(t - b * (uint32_t)p.out_h);
     const float* xb = p.x + (size_t)b * 3 * p.in_h * p.in_w;
     const int ix0 = 2 * ox - 1, iy0 = 2 * oy - 1;
     #pragma unroll
@@ -65,29 +67,55 @@ __device__ __forceinline__ void load_taps(const StemParams& p, long long pix, fl
         }
 }
 
-// uint8 HWC input with the reference's ToTensor + Normalize (yolov8/tools/test.py:114-119) fused in:
-// the 9 bytes of three horizontally adjacent RGB pixels are contiguous.  Padding taps are 0 AFTER
+// uint8 HWC input with the reference's ToTensor + Normalize (yolov8/tools/test.py:114-119) fused in.  The 9 bytes of
+// three horizontally adjacent RGB pixels are contiguous: they are fetched as the three aligned 32-bit words that cover
+// them (3 loads per image row instead of 9 byte loads) and realigned with funnel shifts.  Padding taps are 0 AFTER
 // normalisation (the reference pads the normalised tensor).
 __device__ __forceinline__ void load_taps_u8(const StemParams& p, long long pix, float (&v)[27]) {
     #pragma unroll
     for (int i = 0; i < 27; ++i) v[i] = 0.f;
     if (pix >= p.m_total) return;
-    const int ox = (int)(pix % p.out_w);
-    const long long t = pix / p.out_w;
-    const int oy = (int)(t % p.out_h);
-    const int b = (int)(t / p.out_h);
-    const int ix0 = 2 * ox - 1, iy0 = 2 * oy - 1;
+    const uint32_t t = (uint32_t)pix / (uint32_t)p.out_w;            // 32-bit index math (pix < 2^31, checked by the host)
+    const int ox = (int)((uint32_t)pix - t * (uint32_t)p.out_w);
+    const uint32_t b = t / (uint32_t)p.out_h;
+    const int oy = (int)(t - b * (uint32_t)p.out_h);
+    const int iy0 = 2 * oy - 1;
+    const bool left = (ox == 0);                                     // tap kx = 0 is padding; the window starts at pixel 0
+    const int px0 = left ? 0 : 2 * ox - 1;
+    const long long total = (long long)p.batch * p.in_h * p.in_w * 3;
     #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = iy0 + ky;
         if (iy < 0) continue;
-        const unsigned char* row = p.xu8 + (((long long)b * p.in_h + iy) * p.in_w + ix0) * 3;
-        #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            if (kx == 0 && ix0 < 0) continue;
+        const long long a = (((long long)b * p.in_h + iy) * p.in_w + px0) * 3;
+        const long long a4 = a & ~3LL;
+        const int sh = (int)(a - a4) * 8;
+        uint32_t lo, mid, hi;
+        if (a4 + 12 <= total) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(p.xu8 + a4);
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+            lo = __funnelshift_r(w0, w1, sh); mid = __funnelshift_r(w1, w2, sh); hi = w2 >> sh;
+        } else {                                                     // the last few bytes of the batch: byte loads
+            uint32_t by[9];
             #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                v[c * 9 + ky * 3 + kx] = fmaf((float)__ldg(row + kx * 3 + c), p.scale[c], p.shift[c]);
+            for (int i = 0; i < 9; ++i) by[i] = (a + i < total) ? (uint32_t)__ldg(p.xu8 + a + i) : 0u;
+            lo = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24);
+            mid = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24);
+            hi = by[8];
+        }
+        // bytes 0..8 of the window = pixels px0, px0+1, px0+2 (RGB each)
+        const uint32_t q[9] = {lo & 0xff, (lo >> 8) & 0xff, (lo >> 16) & 0xff, lo >> 24,
+                               mid & 0xff, (mid >> 8) & 0xff, (mid >> 16) & 0xff, mid >> 24, hi & 0xff};
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (left) {                                              // window = taps kx 1, 2
+                v[c * 9 + ky * 3 + 1] = fmaf((float)q[c], p.scale[c], p.shift[c]);
+                v[c * 9 + ky * 3 + 2] = fmaf((float)q[3 + c], p.scale[c], p.shift[c]);
+            } else {
+                v[c * 9 + ky * 3 + 0] = fmaf((float)q[c], p.scale[c], p.shift[c]);
+                v[c * 9 + ky * 3 + 1] = fmaf((float)q[3 + c], p.scale[c], p.shift[c]);
+                v[c * 9 + ky * 3 + 2] = fmaf((float)q[6 + c], p.scale[c], p.shift[c]);
+            }
         }
     }
 }
@@ -103,14 +131,14 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
     unsigned char* g_b = gbase + kStages * kATile;
     const uint32_t smem_out0 = smem_b + 8192;
     unsigned char* g_out0 = g_b + 8192;
-    float* s_bias = reinterpret_cast<float*>(g_out0 + 2 * kStageOutS);          // 128 floats (0.5 * bias)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 128);
+    float* s_bias = reinterpret_cast<float*>(g_out0 + kStemEpiGroups * kStageOutBytes);   // 192 floats (0.5 * bias, zero padded)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 192);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + kStemEpiGroups + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kStemEpiGroups);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pad = (p.c_out + 15) & ~15;
@@ -118,7 +146,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_y);
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+        for (int s = 0; s < kStemEpiGroups; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         fence_barrier_init();
     }
     if (warp == kProdWarps) tmem_alloc(smem_u32(tmem_slot), 256);
@@ -128,7 +156,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
         const float w = (n < p.c_out && k < 27) ? p.weight[n * 27 + k] : 0.f;
         *reinterpret_cast<__nv_bfloat16*>(g_b + (n >> 3) * 512 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = __float2bfloat16(w);
     }
-    for (int i = threadIdx.x; i < 128; i += kStemThreads) s_bias[i] = (i < p.c_out) ? 0.5f * p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 192; i += kStemThreads) s_bias[i] = (i < p.c_out) ? 0.5f * p.bias[i] : 0.f;
     fence_proxy_async_smem();                                       // weight tile is read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -137,16 +165,16 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
 
     if (warp < kProdWarps) {
         // ================= producers: im2col gather -> bf16 K rows =================
-        const int grp = warp >> 2;                                  // 2 groups of 4 warps, alternate tiles
+        const int grp = warp >> 2;                                  // kProdGroups groups of 4 warps, tiles dealt round-robin
         const int r = (warp & 3) * 32 + lane;                       // row inside the tile
         float cur[27], nxt[27];
         int seq = grp;                                              // sequence number of this CTA's tiles
         long long t = (long long)blockIdx.x + (long long)grp * gridDim.x;
         if (t < p.total_tiles) { if (kU8) load_taps_u8(p, t * 128 + r, nxt); else load_taps(p, t * 128 + r, nxt); }
-        for (; t < p.total_tiles; t += 2LL * gridDim.x, seq += 2) {
+        for (; t < p.total_tiles; t += (long long)kProdGroups * gridDim.x, seq += kProdGroups) {
             #pragma unroll
             for (int i = 0; i < 27; ++i) cur[i] = nxt[i];
-            const long long tn = t + 2LL * gridDim.x;
+            const long long tn = t + (long long)kProdGroups * gridDim.x;
             if (tn < p.total_tiles) { if (kU8) load_taps_u8(p, tn * 128 + r, nxt); else load_taps(p, tn * 128 + r, nxt); }
             const int stage = seq % kStages;
             const uint32_t phase = (uint32_t)(seq / kStages) & 1u;
@@ -188,67 +216,36 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
                 umma_commit(tfull_bar(acc));
             }
             __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == kStemEpiGroups) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         // ================= epilogue =================
         const int ew = warp - kProdWarps - 1;
-        const int quad = warp & 3;
-        const int half = ew >> 2;
-        const int row = quad * 32 + lane;
-        const bool leader = (ew == 0 && lane == 0);
-        int acc = 0; uint32_t acc_phase = 0; uint32_t chunk_ctr = 0;
+        const int grp = ew >> 2;                                    // group e drains accumulator stage e (tiles e, e+4, ...)
+        EpiShared e;
+        e.tm_y = &tm_y; e.tm_res = &tm_y;
+        e.res_bar = 0;
+        e.s_out = smem_out0 + grp * kStageOutBytes;
+        e.s_bias = s_bias;
+        e.block_n = n_pad; e.c_out = p.c_out; e.act = 1; e.has_res = 0;
+        e.out_bytes = 0;
+        e.bar_id = 1 + grp;
+        e.leader = (ew & 3) == 0 && lane == 0;
+        e.row = (warp & 3) * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * 128);
         const int n_chunks = (n_pad + 63) >> 6;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            mbar_wait(tfull_bar(acc), acc_phase);
+        uint32_t res_phase = 0u, acc_phase = 0u;
+        for (long long t = (long long)blockIdx.x + (long long)grp * gridDim.x; t < p.total_tiles; t += (long long)kStemEpiGroups * gridDim.x) {
+            EpiTile tl; tl.n0 = 0; tl.x0 = (int)(t * 128); tl.y0 = 0; tl.img = 0;
+            mbar_wait(tfull_bar(grp), acc_phase);
+            acc_phase ^= 1u;
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128);
-            for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-                const int buf = chunk_ctr & 1u;
-                const uint32_t s_out = smem_out0 + buf * kStageOutS;
-                const int c0 = ch * 64 + half * 32;
-                const bool active = c0 < n_pad;
-                if (leader) tma_store_wait_read<1>();
-                epi_bar_sync();
-                uint32_t v[32];
-                if (active) { tmem_ld32(t_row + (uint32_t)c0, v); tmem_ld_wait(); }
-                if (ch == n_chunks - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
-                }
-                if (active) {
-                    float f[32];
-                    const float4* bq = reinterpret_cast<const float4*>(s_bias + c0);
-                    #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 hb = bq[j];
-                        f[4 * j + 0] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 0]), 0.5f, hb.x));
-                        f[4 * j + 1] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, hb.y));
-                        f[4 * j + 2] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, hb.z));
-                        f[4 * j + 3] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, hb.w));
-                    }
-                    const uint32_t line = s_out + (uint32_t)row * 128u;
-                    #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t addr = line + (((uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7)) << 4);
-                        const uint32_t o0 = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                        const uint32_t o1 = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                        const uint32_t o2 = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                        const uint32_t o3 = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-                    }
-                }
-                fence_proxy_async_smem();
-                epi_bar_sync();
-                if (leader) {
-                    tma_store_4d(&tm_y, s_out, ch * 64, (int)(t * 128), 0, 0);
-                    tma_store_commit();
-                }
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            for (int ch = 0; ch < n_chunks; ++ch) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(grp));
         }
-        if (leader) tma_store_wait_read<0>();
+        if (e.leader) tma_store_wait_read<0>();
     }
 
     tc_fence_before();
@@ -281,8 +278,9 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
     p.batch = batch; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.c_out = c_out;
     p.m_total = (long long)batch * out_h * out_w;
     p.total_tiles = (int)((p.m_total + 127) / 128);
+    if (p.m_total + 128 >= (1LL << 31)) return fail(YMS_E_UNSUPPORTED, "stem: more than 2^31 output pixels");
     p.weight = weight; p.bias = bias;
-    const size_t smem = 1024 + kStages * kATile + 8192 + 2 * kStageOutS + 128 * 4 + (2 * kStages + 4) * 8 + 16;
+    const size_t smem = 1024 + kStages * kATile + 8192 + kStemEpiGroups * kStageOutBytes + 192 * 4 + (2 * kStages + 2 * kStemEpiGroups) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
