@@ -59,7 +59,9 @@ typedef struct yms_conv_params {
     /* second input source (K-concatenation: conv over cat[x, x2], or conv(x + x2) when
        weights are repeated); c_in2 = 0 disables it.  Same spatial size as x.               */
     int32_t c_in2;
-    int32_t reserved0;
+    int32_t variant;                  /* kernel variant for 3x3/s1 layers: 0 = library heuristic, 1 = generic implicit GEMM,
+                                         2 = halo kernel (1 sub-tile per work item), 3 = halo kernel (2 sub-tiles per work item).
+                                         Results agree to fp32 accumulation order; used by the host-side per-layer autotuner. */
     /* tensors */
     const void* x;   int64_t x_pixel_stride;      /* bf16, elements between consecutive pixels   */
     const void* x2;  int64_t x2_pixel_stride;

@@ -31,7 +31,7 @@ class ConvParams(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("c_in", C.c_int32), ("c_out", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
-        ("act", C.c_int32), ("out_dtype", C.c_int32), ("c_in2", C.c_int32), ("reserved0", C.c_int32),
+        ("act", C.c_int32), ("out_dtype", C.c_int32), ("c_in2", C.c_int32), ("variant", C.c_int32),
         ("x", C.c_void_p), ("x_pixel_stride", C.c_int64),
         ("x2", C.c_void_p), ("x2_pixel_stride", C.c_int64),
         ("y", C.c_void_p), ("y_pixel_stride", C.c_int64),

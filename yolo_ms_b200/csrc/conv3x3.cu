@@ -335,12 +335,14 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         const char* fs = getenv("YMS_CONV3_SUB");
         const long long sub_tiles = (long long)k.tiles_x * k.tiles_y * k.batch;
         k.sub = fs ? atoi(fs) : ((k.tiles_x >= 2 && sub_tiles >= 4096) ? 2 : 1);    // pairing only pays with many tiles per CTA
+        if (q->variant == 2) k.sub = 1; else if (q->variant == 3 && k.tiles_x >= 2) k.sub = 2;
         k.b_stages = 0;
         if ((k.sub != 1 && k.sub != 2 && k.sub != 4) || k.sub * k.block_n > 512) k.sub = 1;
         k.a_stages = max_a_stages(k.sub, resident_bytes);
         if (k.a_stages < 2) { k.sub = 1; k.a_stages = max_a_stages(1, resident_bytes); }
     } else {
         k.sub = (k.tiles_x >= 2 && 2 * k.block_n <= 512) ? 2 : 1;
+        if (q->variant == 2) k.sub = 1;
         k.b_stages = 4;
         for (;;) {
             k.a_stages = max_a_stages(k.sub, k.b_stages * b_tile);

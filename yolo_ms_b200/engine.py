@@ -13,6 +13,7 @@ Data layout in HBM
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -21,6 +22,7 @@ from . import ops
 from ._lib import YmsError
 
 BN_EPS_DEFAULT = 1e-3
+AUTOTUNE = os.environ.get("YMS_AUTOTUNE", "1") != "0"     # per-layer kernel-variant selection at program build
 
 
 def fold_conv_bn(weight: torch.Tensor, bn_w, bn_b, bn_mean, bn_var, eps: float):
@@ -52,6 +54,7 @@ class Program:
         self.launches = 0
         self.names: List[str] = []     # one label per step (profiling / per-layer tables)
         self.costs: dict = {}          # step index -> (flops, bytes) of non-conv steps
+        self.tuned: list = []          # (layer, chosen variant) of the autotuned 3x3 layers
         self.flops = 0.0
         self.bytes = 0.0
 
@@ -67,12 +70,43 @@ class Program:
     # ---- ops -------------------------------------------------------------------------------
     def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None):
         plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
+        if AUTOTUNE and ksize == 3 and stride == 1 and x2 is None and y.dtype == torch.bfloat16:
+            plan = self._autotune(plan, dict(x=x, weight=weight_packed, bias=bias, y=y, ksize=ksize, stride=stride, act=act,
+                                             residual=residual, x2=x2))
         self.plans.append(plan)
         self.hold(weight_packed, bias)
         self._push(plan.run, plan.desc)
         self.flops += plan.flops
         self.bytes += plan.bytes
         return y
+
+    def _autotune(self, default_plan, kw):
+        """Measure, don't guess: the 3x3/s1 layers have three tcgen05 implementations whose winner depends on the map
+        size (tile quantisation on 20x20 / 40x40 maps), c_out (resident vs streamed weights) and the tile count per CTA.
+        Each candidate runs on the layer's real buffers at program-build time; the fastest one is kept."""
+        def timed(plan):
+            for _ in range(2):
+                plan.run()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                plan.run()
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b)
+        best, best_t = default_plan, timed(default_plan)
+        for variant in (1, 2, 3):
+            try:
+                cand = ops.ConvPlan(kw["x"], kw["weight"], kw["bias"], kw["y"], ksize=kw["ksize"], stride=kw["stride"], act=kw["act"],
+                                    residual=kw["residual"], x2=kw["x2"], variant=variant)
+            except YmsError:
+                continue
+            t = timed(cand)
+            if t < 0.97 * best_t:
+                best, best_t = cand, t
+        self.tuned.append((default_plan.desc, best.variant))
+        best.desc = default_plan.desc + (f" [v{best.variant}]" if best.variant else "")
+        return best
 
     def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0, name: str = "op"):
         self._push(fn, name)

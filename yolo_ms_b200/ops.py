@@ -45,7 +45,7 @@ class ConvPlan:
     weight: bf16 [k*k, c_out, c_in (+ c_in2)], bias: f32 [c_out].
     """
 
-    def __init__(self, x, weight, bias, y, ksize=1, stride=1, act=True, residual=None, x2=None):
+    def __init__(self, x, weight, bias, y, ksize=1, stride=1, act=True, residual=None, x2=None, variant=0):
         _need_cuda(x, weight, bias, y, residual, x2)
         if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or bias.dtype != torch.float32:
             raise YmsError("conv: x/weight must be bf16 and bias f32")
@@ -63,6 +63,8 @@ class ConvPlan:
         p.ksize, p.stride, p.act = ksize, stride, int(bool(act))
         p.out_dtype = _lib.DTYPE_BF16 if y.dtype == torch.bfloat16 else _lib.DTYPE_F32
         p.c_in2 = c_in2
+        p.variant = int(variant)
+        self.variant = int(variant)
         p.x, p.x_pixel_stride = x.data_ptr(), _pixel_stride(x)
         if x2 is not None:
             p.x2, p.x2_pixel_stride = x2.data_ptr(), _pixel_stride(x2)
