@@ -93,6 +93,16 @@ int yms_stem_conv_u8(const uint8_t* x_nhwc, int batch, int in_h, int in_w, int c
                      const float* weight, const float* bias, const float* host_mean /* 3 */,
                      const float* host_std /* 3 */, void* y_nhwc_bf16, int64_t y_pixel_stride, void* stream);
 
+/* One pass of the resize step of the reference's pre-processing: T.Resize((h, w)) on a PIL image
+ * (yolov8/tools/test.py:114-119,142-145) = Pillow's Image.resize(BILINEAR), src/libImaging/Resample.c: a separable
+ * two-pass (horizontal, then vertical) convolution with 22-bit fixed-point coefficients, each pass rounding to uint8.
+ * src/dst uint8 HWC; bounds int32 [out][2] = (first source index, count), coeffs int32 [out][ksize] (device memory,
+ * computed by the host exactly as precompute_coeffs/normalize_coeffs_8bpc do).  horizontal != 0: x pass (dst_h == src_h),
+ * else y pass (dst_w == src_w).  SURVEY.md section 8(f) rank 1; bit-exact vs Pillow. */
+int yms_resample_u8(const uint8_t* src, int src_h, int src_w, int channels, int64_t src_row_stride_bytes,
+                    uint8_t* dst, int dst_h, int dst_w, int64_t dst_row_stride_bytes,
+                    const int32_t* bounds, const int32_t* coeffs, int ksize, int horizontal, void* stream);
+
 /* Depthwise k x k (k in 3,5,7,9; stride 1; pad k/2) + folded BN + SiLU, NHWC bf16.
  * Conv(c, c, k, 1, k//2, groups=c) of components.py:69-77 as used by the repo-local MS-Block.
  * weight f32 [k*k][c] (tap-major), bias f32 [c]. */

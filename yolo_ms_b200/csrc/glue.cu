@@ -329,3 +329,49 @@ extern "C" int yms_dwconv(const void* x, int64_t xps, int batch, int h, int w, i
     }
     return check_launch("dwconv_kernel");
 }
+
+// ---------------------------------------------------------------------------------------
+// Pillow-exact fixed-point resampling pass (T.Resize of the reference's pre-processing,
+// yolov8/tools/test.py:114-119, runs Image.resize(BILINEAR) = Pillow's src/libImaging/Resample.c).
+// One thread per output byte: acc = 2^21 + sum_k src * coeff (22-bit fixed point), out = clip8(acc >> 22).
+// ---------------------------------------------------------------------------------------
+namespace yms {
+namespace {
+__global__ void __launch_bounds__(256) resample_u8_kernel(const unsigned char* __restrict__ src, long long src_rs, unsigned char* __restrict__ dst,
+                                                          long long dst_rs, int dst_h, int dst_wc, int channels,
+                                                          const int* __restrict__ bounds, const int* __restrict__ coeffs, int ksize, int horizontal) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;         // byte column of the output row (x * channels + c)
+    const int row = blockIdx.y;
+    if (col >= dst_wc || row >= dst_h) return;
+    int acc = 1 << 21;
+    if (horizontal) {
+        const int xo = col / channels, c = col - xo * channels;
+        const int lo = bounds[2 * xo], cnt = bounds[2 * xo + 1];
+        const int* k = coeffs + (size_t)xo * ksize;
+        const unsigned char* s = src + (size_t)row * src_rs + (size_t)lo * channels + c;
+        for (int i = 0; i < cnt; ++i) acc += (int)s[(size_t)i * channels] * __ldg(k + i);
+    } else {
+        const int lo = bounds[2 * row], cnt = bounds[2 * row + 1];
+        const int* k = coeffs + (size_t)row * ksize;
+        const unsigned char* s = src + (size_t)lo * src_rs + col;
+        for (int i = 0; i < cnt; ++i) acc += (int)s[(size_t)i * src_rs] * __ldg(k + i);
+    }
+    acc >>= 22;
+    dst[(size_t)row * dst_rs + col] = (unsigned char)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+}
+}  // namespace
+}  // namespace yms
+
+extern "C" int yms_resample_u8(const uint8_t* src, int src_h, int src_w, int channels, int64_t src_row_stride,
+                               uint8_t* dst, int dst_h, int dst_w, int64_t dst_row_stride,
+                               const int32_t* bounds, const int32_t* coeffs, int ksize, int horizontal, void* stream) {
+    if (!src || !dst || !bounds || !coeffs) return fail(YMS_E_ARG, "resample: null pointer");
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || channels <= 0 || ksize <= 0) return fail(YMS_E_ARG, "resample: bad sizes");
+    if (horizontal ? (dst_h != src_h) : (dst_w != src_w)) return fail(YMS_E_ARG, "resample: a pass changes one axis only");
+    if (src_row_stride < (int64_t)src_w * channels || dst_row_stride < (int64_t)dst_w * channels) return fail(YMS_E_ARG, "resample: bad row stride");
+    if (dst_h > 65535) return fail(YMS_E_UNSUPPORTED, "resample: more than 65535 output rows");
+    dim3 grid(ceil_div(dst_w * channels, 256), dst_h);
+    resample_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_row_stride, dst, dst_row_stride, dst_h, dst_w * channels, channels,
+                                                                bounds, coeffs, ksize, horizontal);
+    return check_launch("resample_u8_kernel");
+}
