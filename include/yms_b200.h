@@ -60,7 +60,9 @@ typedef struct yms_conv_params {
        weights are repeated); c_in2 = 0 disables it.  Same spatial size as x.               */
     int32_t c_in2;
     int32_t variant;                  /* kernel variant for 3x3/s1 layers: 0 = library heuristic, 1 = generic implicit GEMM,
-                                         2 = halo kernel (1 sub-tile per work item), 3 = halo kernel (2 sub-tiles per work item).
+                                         2 = halo kernel (1 sub-tile per work item), 3 = halo kernel (2 sub-tiles per work item);
+                                         4 = stride-2 pair-line kernel for 3x3/s2 with c_in == 32 on a dense input: `weight` is then
+                                         PAIR-PACKED bf16 [6][c_out][64]: tile 2*ky = [w(ky,1) | w(ky,2)], tile 2*ky+1 = [0 | w(ky,0)].
                                          Results agree to fp32 accumulation order; used by the host-side per-layer autotuner. */
     /* tensors */
     const void* x;   int64_t x_pixel_stride;      /* bf16, elements between consecutive pixels   */

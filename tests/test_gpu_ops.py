@@ -83,6 +83,29 @@ def test_conv_gemm_matches_torch_fp32(ops, case, variant):
         assert bool((yfull[..., :8] == 7).all() and (yfull[..., 8 + cout:] == 7).all())
 
 
+@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 64), (1, 40, 24, 48), (1, 320, 320, 64), (2, 36, 52, 128)])
+def test_conv_s2_pair_line_kernel(ops, B, H, W, cout):
+    """variant 4: 3x3/s2 with 32 dense input channels on pair-packed weights vs plain PyTorch fp32 conv (and vs the
+    generic kernel).  Odd tile counts (H/2 not a multiple of the tile height, W/2 not a multiple of 8) included."""
+    g = torch.Generator().manual_seed(B * 1000 + H + W + cout)
+    x = torch.randn(B, H, W, 32, generator=g).to(DEV).to(torch.bfloat16)
+    wt = (torch.randn(cout, 32, 3, 3, generator=g) / (32 * 9) ** 0.5).to(DEV).to(torch.bfloat16)
+    bias = (torch.randn(cout, generator=g) * 0.5).to(DEV)
+    wpk = wt.permute(2, 3, 0, 1).reshape(9, cout, 32).contiguous()
+    tiles = []
+    for ky in range(3):
+        tiles.append(torch.cat([wpk[ky * 3 + 1], wpk[ky * 3 + 2]], -1))
+        tiles.append(torch.cat([torch.zeros_like(wpk[ky * 3]), wpk[ky * 3]], -1))
+    wpair = torch.stack(tiles, 0).contiguous()
+    y4 = torch.full((B, H // 2, W // 2, cout), 7.0, device=DEV, dtype=torch.bfloat16)
+    y0 = torch.empty_like(y4)
+    ops.ConvPlan(x, wpair, bias, y4, ksize=3, stride=2, act=True, variant=4).run()
+    ops.ConvPlan(x, wpk, bias, y0, ksize=3, stride=2, act=True).run()
+    ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert rel_l2(y4, ref) < 4e-3
+    assert rel_l2(y4, y0.float()) < 3e-3
+
+
 def test_conv_rejects_cpu_and_bad_shapes(ops):
     x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16)
     with pytest.raises(ops.YmsError):

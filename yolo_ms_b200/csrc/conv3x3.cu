@@ -20,6 +20,15 @@
 //     memory for the whole persistent CTA; larger ones stream through their own mbarrier ring and
 //     are shared by two adjacent sub-tiles (two accumulators) to halve their L2 traffic.
 // Warp roles / epilogue are the same as conv_gemm.cu.
+//
+// Stride-2 "pair-line" mode (s2pair; backbone.conv1 of the s model: 3x3/s2, c_in = 32, dense NHWC input).  The generic
+// kernel needs 9 shifted 128-row TMA boxes per output tile there and is bound by the TMA row rate (~4 cycles per 128 B
+// row, half of each row being zero fill).  A dense stride-2 input viewed as (2C = 64 channels, W/2 pixel pairs, 2 row
+// parities, H/2, N) has 128-byte lines that hold BOTH pixels of a pair, so:
+//   * per tile only the two parity planes are loaded: 2 boxes of 9 pairs x (th+1) rows (4x fewer rows);
+//   * taps (ky,1),(ky,2) are ONE K = 64 block of the pair line at output x (weights [w(ky,1) | w(ky,2)]), tap (ky,0) is
+//     the upper 32 channels of the pair line at x-1 (k-steps 2,3 against [0 | w(ky,0)]): 6 weight tiles ("pair-packed",
+//     yms_conv_params.variant == 4) and 18 MMAs per tile, all on shifted descriptors of the two planes (row pitch 9).
 #include "conv_plan.h"
 
 #include <stdlib.h>
@@ -75,8 +84,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     unsigned char* gbase = smem_dyn;
     if (base & 1023u) __trap();
     const int b_tile_bytes = (p.block_n * 128 + 1023) & ~1023;
-    const int a_region = ((p.a_stages * p.sub * p.halo_stage) + 1023) & ~1023;
-    const int b_region = (p.resident ? 9 * p.kb : p.b_stages) * b_tile_bytes;
+    const int a_region = ((p.a_stages * p.planes * p.halo_stage) + 1023) & ~1023;
+    const int b_region = (p.resident ? p.wtiles * p.kb : p.b_stages) * b_tile_bytes;
     const uint32_t smem_a = base;
     const uint32_t smem_b = base + a_region;
     const uint32_t smem_out0 = smem_b + b_region;
@@ -109,8 +118,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
     if (warp == 0 && p.resident && elect_one()) {        // weights are constants of the program: fetched BEFORE the grid dependency
-        mbar_expect_tx(bar(kBarW), (uint32_t)(9 * p.kb) * (uint32_t)(p.block_n * 128));     // resolves (previous layer still draining)
-        for (int tap = 0; tap < 9; ++tap)
+        mbar_expect_tx(bar(kBarW), (uint32_t)(p.wtiles * p.kb) * (uint32_t)(p.block_n * 128));     // resolves (previous layer still draining)
+        for (int tap = 0; tap < p.wtiles; ++tap)
             for (int cb = 0; cb < p.kb; ++cb)
                 tma_load_3d(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, 0, tap);
     }
@@ -129,7 +138,12 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 const int n0 = it.n_tile * p.block_n;
                 for (int cb = 0; cb < p.kb; ++cb) {
                     mbar_wait_acc(bar(kBarAEmpty + as), aph ^ 1u, pw0);
-                    mbar_expect_tx(bar(kBarAFull + as), (uint32_t)p.sub * p.halo_bytes);
+                    mbar_expect_tx(bar(kBarAFull + as), (uint32_t)p.planes * p.halo_bytes);
+                    if (p.s2pair) {                                  // the two row-parity planes: 9 pairs x (th+1) rows each
+                        for (int py = 0; py < 2; ++py)
+                            tma_load_5d(smem_a + (as * 2 + py) * p.halo_stage, &tm_x, bar(kBarAFull + as),
+                                        0, it.sx * 8 - 1, py, it.ty * p.th - 1, it.img);
+                    } else
                     for (int s = 0; s < p.sub; ++s)
                         tma_load_4d(smem_a + (as * p.sub + s) * p.halo_stage, &tm_x, bar(kBarAFull + as),
                                     cb * kBlockK, (it.sx * p.sub + s) * 8 - 1, it.ty * p.th - 1, it.img);
@@ -162,7 +176,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             if (p.resident) { mbar_wait_acc(bar(kBarW), 0u, pw2); tc_fence_after(); }
             YMS_PROF_ONLY(int ntile = 0;)
             const uint32_t a0_16 = (smem_a & 0x3FFFFu) >> 4, b0_16 = (smem_b & 0x3FFFFu) >> 4;
-            const uint32_t astage16 = (uint32_t)p.sub * halo16;
+            const uint32_t astage16 = (uint32_t)p.planes * halo16;
             const int tail = ((p.c_in - (p.kb - 1) * kBlockK) + 15) >> 4;
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -181,7 +195,22 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     const uint32_t a16 = a0_16 + (uint32_t)as * astage16;
                     const uint32_t first = (cb != 0) ? 1u : 0u;
                     const bool last_cb = (cb == p.kb - 1);
-                    if (p.resident) {
+                    if (p.s2pair) {
+                        const uint64_t hi_a9 = (1ull << 16) | ((uint64_t)((9 * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+                        #pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const uint32_t row16 = a16 + (ky == 1 ? 0u : halo16) + (uint32_t)((ky == 0 ? 0 : 1) * 9) * 8u;
+                            const uint32_t bw = b0_16 + (uint32_t)(2 * ky) * btile16;
+                            #pragma unroll
+                            for (int k = 0; k < 4; ++k)               // pair x: taps (ky,1) | (ky,2), K = 64
+                                umma_bf16(d_tmem, hi_a9 | (uint64_t)(row16 + 8u + 2 * k), hi_b | (uint64_t)(bw + 2 * k), idesc, (ky | k) ? 1u : 0u);
+                            #pragma unroll
+                            for (int k = 2; k < 4; ++k)               // pair x-1, upper 32 channels: tap (ky,0)
+                                umma_bf16(d_tmem, hi_a9 | (uint64_t)(row16 + 2 * k), hi_b | (uint64_t)(bw + btile16 + 2 * k), idesc, 1u);
+                        }
+                        umma_commit(bar(kBarAEmpty + as));
+                        umma_commit(bar(kBarTFull + acc));
+                    } else if (p.resident) {
                         const uint32_t b16 = b0_16 + (uint32_t)cb * btile16;
                         const uint32_t bstride16 = (uint32_t)p.kb * btile16;
                         #pragma unroll
@@ -357,6 +386,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     if (k.a_stages > kRing) k.a_stages = kRing;
     if (k.a_stages < 2) return fail(YMS_E_UNSUPPORTED, "conv3x3: tile does not fit in shared memory");
     k.acc_stages = (k.sub * k.block_n <= 128) ? 4 : ((k.sub * k.block_n <= 256) ? 2 : 1);
+    k.planes = k.sub; k.wtiles = 9; k.pitch = kHaloPitch; k.s2pair = 0;
     k.super_x = ceil_div(k.tiles_x, k.sub);
     k.total_items = k.super_x * k.tiles_y * k.batch * k.n_tiles;
     k.mg_n_tiles = fast_div_magic(k.n_tiles); k.mg_super_x = fast_div_magic(k.super_x); k.mg_tiles_y = fast_div_magic(k.tiles_y);
@@ -390,6 +420,71 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         if (e != cudaSuccess) return fail((int)e, "conv3x3: smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
+    return 0;
+}
+
+// Stride-2 pair-line mode (see the header comment).  q->weight is PAIR-PACKED: bf16 [6][c_out][64], tile 2*ky =
+// [w(ky,1) | w(ky,2)], tile 2*ky+1 = [0 | w(ky,0)] (32 input channels each).
+int conv3_s2pair_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
+    if (!(q->ksize == 3 && q->stride == 2 && q->c_in == 32 && q->c_in2 == 0 && q->x_pixel_stride == 32 && q->out_dtype == YMS_DTYPE_BF16 &&
+          q->c_out <= 256 && !q->residual))
+        return fail(YMS_E_UNSUPPORTED, "conv (variant 4): needs 3x3/s2, c_in == 32, dense input, bf16 output, c_out <= 256, no residual");
+    Conv3Params& k = pl->k3;
+    memset(&k, 0, sizeof(k));
+    pl->kind = 1;
+    const int H = q->in_h / 2, W = q->in_w / 2;                 // output size
+    k.out_w = W; k.out_h = H; k.batch = q->batch;
+    k.c_in = 64; k.c_out = q->c_out; k.kb = 1;
+    k.n_tiles = 1; k.block_n = ((q->c_out + 15) / 16) * 16;
+    k.act = q->act ? 1 : 0; k.has_res = 0;
+    k.bias_pad = k.block_n + 64;
+    k.bias = q->bias;
+    k.s2pair = 1; k.planes = 2; k.wtiles = 6; k.pitch = 9; k.sub = 1; k.resident = 1; k.b_stages = 0;
+    const int b_tile = (k.block_n * 128 + 1023) & ~1023;
+    const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16;
+    k.th = 0;
+    for (int th_max = 16; th_max >= 4 && !k.th; th_max -= 2) {   // tallest tile that still leaves a 3-deep ring
+        const int ny = ceil_div(H, th_max), th = ceil_div(H, ny);
+        const int stage = 2 * 9 * (th + 1) * 128;
+        if (((3 * stage + 1023) & ~1023) + 6 * b_tile + fixed <= kSmemLimit3) k.th = th;
+    }
+    if (!k.th) return fail(YMS_E_UNSUPPORTED, "conv (variant 4): does not fit in shared memory");
+    k.halo_bytes = (uint32_t)(9 * (k.th + 1) * 128);
+    k.halo_stage = (int)k.halo_bytes;
+    k.a_stages = 0;
+    while (k.a_stages < kRing && ((((k.a_stages + 1) * 2 * k.halo_stage + 1023) & ~1023) + 6 * b_tile + fixed <= kSmemLimit3)) ++k.a_stages;
+    k.tiles_x = ceil_div(W, 8); k.tiles_y = ceil_div(H, k.th);
+    k.acc_stages = (k.block_n <= 128) ? 4 : 2;
+    k.super_x = k.tiles_x;
+    k.total_items = k.super_x * k.tiles_y * k.batch;
+    k.mg_n_tiles = fast_div_magic(1); k.mg_super_x = fast_div_magic(k.super_x); k.mg_tiles_y = fast_div_magic(k.tiles_y);
+    pl->grid = k.total_items < kNumSMs ? k.total_items : kNumSMs;
+    pl->smem = (size_t)((k.a_stages * 2 * k.halo_stage + 1023) & ~1023) + (size_t)6 * b_tile + fixed;
+
+    int rc;
+    {   // dense stride-2 input as (2C = 64 channels, W/2 pairs, 2 row parities, H/2, N)
+        const uint64_t Wi = (uint64_t)q->in_w, Hi = (uint64_t)q->in_h;
+        uint64_t dims[5] = {64, Wi / 2, 2, Hi / 2, (uint64_t)q->batch};
+        uint64_t strides[4] = {64 * 2, Wi * 32 * 2, 2 * Wi * 32 * 2, Hi * Wi * 32 * 2};
+        uint32_t box[5] = {64, 9, 1, (uint32_t)(k.th + 1), 1};
+        uint32_t es[5] = {1, 1, 1, 1, 1};
+        if ((rc = encode_map(&pl->tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, q->x, dims, strides, box, es, "x(s2 pair planes)"))) return rc;
+    }
+    {
+        uint64_t dims[3] = {64, (uint64_t)q->c_out, 6};
+        uint64_t strides[2] = {64 * 2, 64 * 2 * (uint64_t)q->c_out};
+        uint32_t box[3] = {kBlockK, (uint32_t)k.block_n, 1};
+        uint32_t es[3] = {1, 1, 1};
+        if ((rc = encode_map(&pl->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q->weight, dims, strides, box, es, "w(pair-packed)"))) return rc;
+    }
+    if ((rc = encode_act(&pl->tm_y, q->y, q->c_out, q->y_pixel_stride, q->batch, H, W, false, 8, k.th, 1, "y"))) return rc;
+    pl->tm_res = pl->tm_y;
+    pl->tm_x2 = pl->tm_x;
+    const double m = (double)q->batch * H * W;
+    pl->flops = 2.0 * m * q->c_out * 32.0 * 9.0;
+    pl->bytes = 2.0 * (double)q->batch * q->in_h * q->in_w * 32.0 + 2.0 * m * q->c_out + 2.0 * 9.0 * q->c_out * 32.0;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+    if (e != cudaSuccess) return fail((int)e, "conv3x3: smem attribute: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -343,7 +343,13 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     yms_conv_plan* pl = new (std::nothrow) yms_conv_plan();
     if (!pl) return fail(YMS_E_ARG, "conv: out of host memory");
     pl->kind = 0;
-    if (q->variant < 0 || q->variant > 3) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..3"); }
+    if (q->variant < 0 || q->variant > 4) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..4"); }
+    if (q->variant == 4) {                                       // stride-2 pair-line kernel, pair-packed weights (conv3x3.cu)
+        int rc4 = conv3_s2pair_plan_init(pl, q);
+        if (rc4) { delete pl; return rc4; }
+        *out = pl;
+        return 0;
+    }
     if (q->ksize == 3 && q->stride == 1 && q->out_dtype == YMS_DTYPE_BF16 && q->c_in2 == 0 && q->variant != 1 && !getenv("YMS_CONV3_LEGACY")) {
         int rc3 = conv3_plan_init(pl, q);
         if (rc3) { delete pl; return rc3; }

@@ -47,6 +47,10 @@ struct Conv3Params {
     int total_items;
     int bias_pad;
     int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
+    int s2pair;                                // stride-2 pair-line mode (c_in == 32, dense input): see conv3x3.cu
+    int planes;                                // TMA boxes per A stage (== sub, or 2 parity planes in s2pair mode)
+    int wtiles;                                // resident weight tiles per 64-channel block (9 taps, or 6 pair-packed tiles)
+    int pitch;                                 // lines per halo row (10, or 9 pixel pairs in s2pair mode)
     uint32_t mg_n_tiles, mg_super_x, mg_tiles_y;  // fast_div magics
     uint32_t halo_bytes;                       // 10 * (th + 2) * 128
     int halo_stage;                            // smem stride between halo tiles (== halo_bytes, multiple of 128)
@@ -78,6 +82,7 @@ int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, in
                int box_x, int box_y, int estride, const char* what, bool f32 = false);
 
 int conv3_plan_init(::yms_conv_plan* pl, const yms_conv_params* q);   // conv3x3.cu
+int conv3_s2pair_plan_init(::yms_conv_plan* pl, const yms_conv_params* q);
 int conv3_plan_run(const ::yms_conv_plan* pl, cudaStream_t stream);
 
 }  // namespace yms

@@ -70,6 +70,9 @@ class Program:
     # ---- ops -------------------------------------------------------------------------------
     def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None):
         plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
+        if (AUTOTUNE and ksize == 3 and stride == 2 and x2 is None and residual is None and y.dtype == torch.bfloat16
+                and x.shape[-1] == 32 and x.stride(-2) == 32 and y.shape[-1] <= 256):
+            plan = self._autotune_s2pair(plan, weight_packed, dict(x=x, bias=bias, y=y, act=act))
         if AUTOTUNE and ksize == 3 and stride == 1 and x2 is None and y.dtype == torch.bfloat16:
             plan = self._autotune(plan, dict(x=x, weight=weight_packed, bias=bias, y=y, ksize=ksize, stride=stride, act=act,
                                              residual=residual, x2=x2))
@@ -79,6 +82,39 @@ class Program:
         self.flops += plan.flops
         self.bytes += plan.bytes
         return y
+
+    @staticmethod
+    def _time_plan(plan, reps=5):
+        for _ in range(2):
+            plan.run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            plan.run()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b)
+
+    def _autotune_s2pair(self, default_plan, weight_packed, kw):
+        """3x3/s2 with 32 dense input channels (backbone.conv1 of the s model): the pair-line kernel (variant 4) reads
+        each input pixel pair once instead of nine shifted tiles.  Its weights are pair-packed [6][c_out][64]:
+        tile 2*ky = [w(ky,1) | w(ky,2)], tile 2*ky+1 = [0 | w(ky,0)]."""
+        w = weight_packed                                         # [9, c_out, 32], tap = ky*3 + kx
+        tiles = []
+        for ky in range(3):
+            tiles.append(torch.cat([w[ky * 3 + 1], w[ky * 3 + 2]], dim=-1))
+            tiles.append(torch.cat([torch.zeros_like(w[ky * 3]), w[ky * 3]], dim=-1))
+        wp = torch.stack(tiles, 0).contiguous()
+        try:
+            cand = ops.ConvPlan(kw["x"], wp, kw["bias"], kw["y"], ksize=3, stride=2, act=kw["act"], variant=4)
+        except YmsError:
+            return default_plan
+        if self._time_plan(cand) < 0.97 * self._time_plan(default_plan):
+            self.hold(wp)
+            cand.desc = default_plan.desc + " [v4]"
+            self.tuned.append((default_plan.desc, 4))
+            return cand
+        return default_plan
 
     def _autotune(self, default_plan, kw):
         """Measure, don't guess: the 3x3/s1 layers have three tcgen05 implementations whose winner depends on the map

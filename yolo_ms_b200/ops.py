@@ -54,7 +54,8 @@ class ConvPlan:
         b, h, w, c_in = x.shape
         c_out = y.shape[-1]
         c_in2 = 0 if x2 is None else x2.shape[-1]
-        if tuple(weight.shape) != (ksize * ksize, c_out, c_in + c_in2) or not weight.is_contiguous():
+        want = (6, c_out, 64) if variant == 4 else (ksize * ksize, c_out, c_in + c_in2)     # variant 4: pair-packed (include/yms_b200.h)
+        if tuple(weight.shape) != want or not weight.is_contiguous():
             raise YmsError(f"conv: weight must be contiguous [{ksize * ksize},{c_out},{c_in + c_in2}], got {tuple(weight.shape)}")
         if tuple(y.shape[:3]) != (b, h // stride, w // stride):
             raise YmsError("conv: output spatial shape mismatch")
