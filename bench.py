@@ -177,6 +177,15 @@ def run_native(args):
     prog = list(model._programs().values())[0][0]
     launches_per_step = prog.launches + 2           # + head_decode + nms
 
+    if args.profile_step:        # ncu --profile-from-start off: exactly one steady-state step inside the capture range
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        out = step(x)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_step": True, "launches_per_step": launches_per_step}), flush=True)
+        return
+
     # ------------------------------------------------------------------ device-resident throughput
     sampler = ClockSampler(local)
     if rank == 0:
@@ -373,6 +382,7 @@ def main():
     ap.add_argument("--hw", type=int, default=640)
     ap.add_argument("--cpu-images", type=int, default=8, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run one step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,26 +1,25 @@
 #!/bin/bash
 # ncu evidence for one round (run under gpurun, ONE GPU).  Usage: scripts/profile.sh r01
-# Every ncu pass runs only after the identical plain command exited 0.  Outputs stay small
-# (gpurun_out/ is capped at 64 MiB): CSV exports only, .ncu-rep files are deleted on the box.
+# Every ncu pass runs only after the identical plain command exited 0.  The capture range is exactly ONE steady-state
+# step of bench.py (cudaProfilerStart/Stop, --profile-from-start off).  Outputs stay small (gpurun_out/ is capped at
+# 64 MiB): CSV exports only, .ncu-rep files are deleted on the box.
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-MINE='regex:conv_gemm|conv3x3|stem_tc|stem_conv|nms_kernel|head_decode|sppf_pool|upsample2x|select_cand|gather_dets|dwconv'
+CMD="python bench.py --profile-step --warmup 3"
 mkdir -p $OUT
-# 1. launch list of one steady-state step (our kernels only): duration + DRAM bytes per launch
+# 1. launch list of one steady-state step: duration + DRAM bytes per launch
 $CMD > $OUT/plain_$TAG.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$MINE" -s 198 -c 66 \
+ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
-# 2. --set full on a few launches of each hot kernel
+# 2. --set full on a few launches of each hot kernel (same capture range)
 prof() {  # name regex skip count
   $CMD > /dev/null 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -o $OUT/prof_$1_$TAG $CMD > $OUT/ncu_$1_$TAG.log 2>&1
+  ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -o $OUT/prof_$1_$TAG $CMD > $OUT/ncu_$1_$TAG.log 2>&1
   ncu -i $OUT/prof_$1_$TAG.ncu-rep --page raw --csv > $OUT/prof_$1_${TAG}_raw.csv 2>/dev/null
-  ncu -i $OUT/prof_$1_$TAG.ncu-rep --page details --csv > $OUT/prof_$1_${TAG}_details.csv 2>/dev/null
   rm -f $OUT/prof_$1_$TAG.ncu-rep
 }
-prof gemm conv_gemm_kernel 93 4          # step 4: conv1 (3x3 s2), c2f_2.conv1, c2f_2.conv2, conv3
-prof conv3 conv3x3_kernel 84 4           # step 4: the two 160x160 bottleneck convs + first two 80x80
-prof post 'nms_kernel|head_decode|stem_tc' 9 3
+prof gemm conv_gemm_kernel 0 6           # c2f_2.conv1 (1x1 64->64 @160), c2f_2.conv2, conv3 (3x3/s2), c2f_4.conv1, c2f_4.conv2, conv5
+prof conv3 conv3x3_kernel 0 5            # conv1 (pair-line s2), the two 160x160 bottleneck convs, first two 80x80
+prof post 'nms_kernel|head_decode|stem_tc' 0 3
 du -sh $OUT; ls $OUT | grep $TAG
