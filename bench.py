@@ -100,10 +100,14 @@ def cpu_reference_run(version, hw, images_per_step, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = W.calibrated_state_dict(version, seed=1)
-    x = W.make_images(images_per_step, hw, hw, seed=7)
+    g8 = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (images_per_step, hw, hw, 3), generator=g8, dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
 
     def step():
         with torch.no_grad():
+            x = (u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std       # ToTensor + Normalize (tools/test.py:114-119)
             pred = O.forward(sd, x)
         p = pred.numpy()
         return sum(PP.postprocess_image(p[i], CONF, IOU, PP.greedy_nms_c)[0].size for i in range(p.shape[0]))
@@ -115,7 +119,7 @@ def cpu_reference_run(version, hw, images_per_step, steps, warmup):
         step()
     dt = time.perf_counter() - t0
     return {"value": images_per_step * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": cores,
-            "sample": f"{steps} steps x {images_per_step} images ({version}, {hw}x{hw}, fp32, torch CPU ops + C greedy NMS) after {warmup} warm-up"}
+            "sample": f"{steps} steps x {images_per_step} uint8 images ({version}, {hw}x{hw}): ToTensor+Normalize, fp32 forward (torch CPU ops), C greedy NMS; {warmup} warm-up"}
 
 
 def run_reference(args):
@@ -133,7 +137,7 @@ def run_reference(args):
         "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ================================================================================================
@@ -183,7 +187,7 @@ def run_native(args):
         out = step(x)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        print(json.dumps({"profiled_step": True, "launches_per_step": launches_per_step}), flush=True)
+        emit({"profiled_step": True, "launches_per_step": launches_per_step})
         return
 
     # ------------------------------------------------------------------ device-resident throughput
@@ -240,9 +244,10 @@ def run_native(args):
     e2e_loop(args.steps)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
-    e2e = {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": UNIT,
-           "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(B * MAX_DET * 6 * 4 + B * 4),
-           "ms_per_step": round(e2e_ms, 3), "pipelined": "H2D of step i+1 overlaps compute of step i (2 buffers)"}
+    e2e_f32 = {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(B * MAX_DET * 6 * 4 + B * 4),
+               "ms_per_step": round(e2e_ms, 3), "pipelined": "H2D of step i+1 overlaps compute of step i (2 buffers)",
+               "input": "the reference's forward interface: normalised fp32 [B,3,H,W] host tensors (PCIe-bound: 157 MB per step)"}
 
     # ------------------------------------------------------------------ same, raw uint8 HWC host images
     # (ToTensor + Normalize fused into the stem; 4x less PCIe traffic than the fp32 interface)
@@ -273,9 +278,11 @@ def run_native(args):
     e2e_u8_loop(args.steps)
     barrier()
     u8_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
-    e2e_u8 = {"value": round(world * B / (u8_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(u8_host.numel()),
-              "d2h_bytes_per_step": int(B * MAX_DET * 6 * 4 + B * 4), "ms_per_step": round(u8_ms, 3),
-              "input": "uint8 HWC images, ToTensor+Normalize fused into the stem kernel (extension of the reference interface)"}
+    e2e = {"value": round(world * B / (u8_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(u8_host.numel()),
+           "d2h_bytes_per_step": int(B * MAX_DET * 6 * 4 + B * 4), "ms_per_step": round(u8_ms, 3),
+           "pipelined": "H2D of step i+1 overlaps compute of step i (2 buffers)",
+           "input": "uint8 RGB HWC host images [B,640,640,3] (what tools/test.py holds after decode + resize); ToTensor+Normalize run "
+                    "inside the stem kernel; public call: YOLOv8.detect(uint8 batch) + gather_detections"}
 
     # ------------------------------------------------------------------ per-kernel roofline (rank 0)
     roof, cpu_base, breakdown = None, None, None
@@ -360,17 +367,35 @@ def run_native(args):
                        "parallelism": f"dp{world} (batch sharded by image, no collective)",
                        "l2": "per-step working set (~2.4 GB activations + 157 MB input) >> 126 MB L2, no explicit flush",
                        "kept_detections_rank0": int(sum(kept))},
-            "clocks": clocks, "e2e": e2e, "e2e_uint8": e2e_u8, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "e2e": e2e, "e2e_fp32_interface": e2e_f32, "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_note": f"{launches_per_step} kernels per step ({prog.launches - 1} inside the CUDA graph, stem + decode + NMS launched "
                                  f"through the C ABI: {api_launches} ABI launches counted in the timed region)",
             "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu_base,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

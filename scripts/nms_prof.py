@@ -25,4 +25,5 @@ print("kept per image (first 4):", cnt[:4].tolist())
 for i, nm in enumerate(names):
     col = d[:, i][b[:, i + 1] > 0]
     if len(col): print(f"{nm:24s} mean {col.mean()/1e3:8.1f} kcyc  max {col.max()/1e3:8.1f} kcyc")
+t = (b[:, 11] - b[:, 10]); print("tile loop (thread 0 view): mean %.1f max %.1f kcyc; tiles/CTA mean %.0f max %.0f; m mean %.0f max %.0f; ncl mean %.1f" % (t.mean()/1e3, t.max()/1e3, b[:,12].mean(), b[:,12].max(), b[:,13].mean(), b[:,13].max(), b[:,14].mean()))
 tot = (b[:, 7] - b[:, 0]); print("total to stamp7: mean %.1f max %.1f kcyc" % (tot.mean()/1e3, tot.max()/1e3))

@@ -170,17 +170,31 @@ __device__ __forceinline__ bool suppresses_finite(const float4& bi, float ai, co
     return hit;
 }
 
+// Tile of the suppression matrix with a two-stage conservative pre-filter.  For proper boxes (w, h >= 0; checked per
+// CTA) IoU > t implies  x-overlap > t * max(w_i, w_j)  AND  y-overlap > t * max(h_i, h_j)  (inter = ix*iy <= ix*h_i and
+// union >= w_i*h_i, symmetrically for j and for y).  Both tests use t * 0.999, far more slack than fp32 rounding needs,
+// so they never reject a pair the exact predicate accepts; they are warp-voted, so that the ~40-instruction exact
+// predicate only runs for the few column boxes that at least one of the 32 row boxes can possibly suppress.
 template <bool kDiag>
 __device__ __forceinline__ void nms_mask_tile(const float4* sb, int n, int k, int w, unsigned* out, float thr_f, int lane) {
     const int r = 32 * k + lane;
-    const float4 bi = (r < n) ? sb[r] : make_float4(0.f, 0.f, 0.f, 0.f);         // empty rows: inter == 0, never suppress
+    const bool rv = r < n;
+    const float4 bi = rv ? sb[r] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float ai = box_area(bi);
+    const float wi = __fsub_rn(bi.z, bi.x), hi = __fsub_rn(bi.w, bi.y);
+    const float tq = thr_f * 0.999f;
     const int jn = min(32, n - 32 * w);
     unsigned word = 0u;
     #pragma unroll 4
     for (int jj = 0; jj < jn; ++jj) {                                            // warp-uniform trip count, broadcast reads
         const float4 bj = sb[32 * w + jj];
-        const bool hit = (!kDiag || lane < jj) && suppresses_finite(bi, ai, bj, box_area(bj), thr_f);
+        const float ix = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+        bool cand = rv && (!kDiag || lane < jj) && ix > tq * fmaxf(wi, __fsub_rn(bj.z, bj.x));
+        if (!__any_sync(0xffffffffu, cand)) continue;
+        const float iy = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+        cand = cand && iy > tq * fmaxf(hi, __fsub_rn(bj.w, bj.y));
+        if (!__any_sync(0xffffffffu, cand)) continue;
+        const bool hit = cand && suppresses_finite(bi, ai, bj, box_area(bj), thr_f);
         word |= hit ? (1u << jj) : 0u;
     }
     out[lane] = word;
@@ -376,6 +390,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         const float4 bx = boxes[(int)(keys[i] & kIdxMask)];
         sbox[i] = bx;
         nonfinite |= !(fabsf(bx.x) <= 3.0e38f && fabsf(bx.y) <= 3.0e38f && fabsf(bx.z) <= 3.0e38f && fabsf(bx.w) <= 3.0e38f);
+        nonfinite |= !(bx.z >= bx.x && bx.w >= bx.y);                 // inverted boxes: the bitmask path's pre-filter assumes w, h >= 0
     }
     nonfinite = __syncthreads_or(nonfinite);
     NMS_STAMP(4);
@@ -407,6 +422,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     if (use_mask) {
         // ---- D (bitmask) ------------------------------------------------------------------------------------
         const int total_tiles = chunk_base[ncl];
+        NMS_STAMP(10);
+#ifdef YMS_PROF
+        if (a.prof && threadIdx.x == 0) { a.prof[16 * blockIdx.x + 12] = total_tiles; a.prof[16 * blockIdx.x + 13] = m; a.prof[16 * blockIdx.x + 14] = ncl; }
+#endif
         for (int t = warp; t < total_tiles; t += kNmsWarps) {
             int lo = 0, hi = ncl - 1;                      // largest c with tile_base[c] <= t
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= t) lo = mid; else hi = mid - 1; }
@@ -416,6 +435,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
             if (u == 0) nms_mask_tile<true>(sbox + s0, nseg, k, k, smask + (size_t)t * 32, a.thr_f, lane);
             else nms_mask_tile<false>(sbox + s0, nseg, k, k + u, smask + (size_t)t * 32, a.thr_f, lane);
         }
+        NMS_STAMP(11);
         __syncthreads();
         NMS_STAMP(5);
         for (;;) {                                         // big classes first: their sweep is the critical path
