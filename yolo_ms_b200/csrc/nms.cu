@@ -200,32 +200,37 @@ __device__ __forceinline__ void nms_mask_tile(const float4* sb, int n, int k, in
     out[lane] = word;
 }
 
-// returns the kept count; survivor keys compacted in place
-__device__ __forceinline__ int nms_mask_sweep(const unsigned* tiles, unsigned long long* sk, int n, int lane) {
+// Greedy replay of row blocks [kb, ke) of one class on the mask words alone (one warp).  `tiles` holds, row block after row
+// block, the W-k tiles (k, k..W-1) of the round; remw[w] (shared memory, owned by this warp) accumulates the removed bits.
+__device__ __forceinline__ void nms_mask_sweep_rows(const unsigned* tiles, unsigned* remw, int n, int kb, int ke, int lane) {
     const int W = (n + 31) >> 5;
-    unsigned removed = 0u;
-    for (int k = 0; k < W; ++k) {
-        const unsigned* row = tiles + (size_t)tile_row_offset(W, k) * 32;
-        const unsigned diag = row[lane];
-        unsigned rem = __shfl_sync(0xffffffffu, removed, k);
+    for (int k = kb; k < ke; ++k) {
+        const unsigned diag = tiles[lane];
+        unsigned rem = remw[k];
         #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const unsigned mi = __shfl_sync(0xffffffffu, diag, i);
             rem |= ((rem >> i) & 1u) ? 0u : mi;                                  // row i survives -> it removes its later neighbours
         }
-        if (lane == k) removed = rem;
         const bool alive = (32 * k + lane < n) && !((rem >> lane) & 1u);
+        if (lane == 0) remw[k] = rem;
         for (int w = k + 1; w < W; ++w) {
-            const unsigned red = __reduce_or_sync(0xffffffffu, alive ? row[(w - k) * 32 + lane] : 0u);
-            if (lane == w) removed |= red;
+            const unsigned red = __reduce_or_sync(0xffffffffu, alive ? tiles[(w - k) * 32 + lane] : 0u);
+            if (lane == 0 && red) remw[w] |= red;
         }
+        __syncwarp();
+        tiles += (size_t)(W - k) * 32;
     }
+}
+
+// survivor keys compacted in place (score order preserved); returns the kept count
+__device__ __forceinline__ int nms_mask_compact(unsigned long long* sk, const unsigned* remw, int n, int lane) {
+    const int W = (n + 31) >> 5;
     int kept = 0;
     for (int k = 0; k < W; ++k) {
         const int r = 32 * k + lane;
         const unsigned long long key = (r < n) ? sk[r] : kInvalidKey;
-        const unsigned rem = __shfl_sync(0xffffffffu, removed, k);
-        const bool alive = (r < n) && !((rem >> lane) & 1u);
+        const bool alive = (r < n) && !((remw[k] >> lane) & 1u);
         const unsigned bal = __ballot_sync(0xffffffffu, alive);
         __syncwarp();                                                            // the block's keys are in registers before its (lower) slots are rewritten
         if (alive) sk[kept + __popc(bal & ((1u << lane) - 1u))] = key;
@@ -244,7 +249,7 @@ struct NmsArgs {
     unsigned int* ws_ticket;       // [B] zeroed by the host before the launch
     int n_pad_full;                // pow2(n)
     long long* prof;               // -DYMS_PROF builds: [grid][16] phase time stamps
-    int mask_tile_limit;           // bitmask path only below this many 32x32 tiles per CTA (else pipelined greedy chunks)
+    int mask_tile_limit;           // bitmask path only when the largest class of the CTA has at most this many 32-box blocks
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
@@ -256,7 +261,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     int* cls_start = reinterpret_cast<int*>(smem_raw + kKeyRegionBytes);            // [nc + 1] (a CTA may own up to nc classes)
     int* cls_count = cls_start + (nc + 1);                                          // [nc + 1] kept counts, then offsets
     int* chunk_base = cls_count + (nc + 1);                                         // [nc + 1]; first: the image's class histogram
-    volatile unsigned* state = reinterpret_cast<volatile unsigned*>(chunk_base + (nc + 1));   // [nc] (done chunks<<16 | kept)
+    volatile unsigned* state = reinterpret_cast<volatile unsigned*>(chunk_base + (nc + 1));   // [nc + 1] (done chunks<<16 | kept) / next row block
+    unsigned* remw_all = const_cast<unsigned*>(reinterpret_cast<volatile unsigned*>(state + (nc + 1)));   // [kFastCap/32 + nc + 2] removed words
     __shared__ int s_count, s_next, s_last, s_clo, s_chi;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -280,16 +286,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     }
     __syncthreads();
     if (warp == 0) {
-        long long total = 0;
-        for (int c = lane; c < nc; c += 32) { const int w = (hist[c] + 31) >> 5; total += ((w * (w + 1)) >> 1) + 1; }
+        // cost of a class = its share of the image's pair-test tiles + its share of the image's candidates (both matter:
+        // tiles bound the suppression work, the count must stay inside the shared-memory fast path of every CTA)
+        long long t_tot = 0, n_tot = 0;
+        for (int c = lane; c < nc; c += 32) { const int w = (hist[c] + 31) >> 5; t_tot += (w * (w + 1)) >> 1; n_tot += hist[c]; }
         #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        for (int o = 16; o > 0; o >>= 1) { t_tot += __shfl_xor_sync(0xffffffffu, t_tot, o); n_tot += __shfl_xor_sync(0xffffffffu, n_tot, o); }
+        t_tot = max(t_tot, 1LL); n_tot = max(n_tot, 1LL);
+        const long long total = 2 * t_tot * n_tot + nc;
         // class c belongs to group floor(cost_before(c) * G / total): monotone => contiguous ranges
         long long running = 0; int lo = nc, hi = 0, cnt = 0;
         for (int base = 0; base < nc; base += 32) {
             const int c = base + lane;
             const int w = (c < nc) ? ((hist[c] + 31) >> 5) : 0;
-            const long long v = (c < nc) ? (long long)(((w * (w + 1)) >> 1) + 1) : 0;
+            const long long v = (c < nc) ? (long long)((w * (w + 1)) >> 1) * n_tot + (long long)hist[c] * t_tot + 1 : 0;
             long long incl = v;
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -394,59 +404,83 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     }
     nonfinite = __syncthreads_or(nonfinite);
     NMS_STAMP(4);
-    // tile_base (aliases chunk_base) = exclusive scan of the per-class tile counts W(W+1)/2; W > 32 disables the path
+    // ---- bitmask path: decision.  Needs every box finite and proper and room for at least two full tile rows of the
+    // largest class after the keys and boxes (the masks are built in rounds of as many row blocks as fit) ---------------
     int use_mask = 0;
     if (fast) {
-        if (warp == 0) {
-            int running = 0, too_big = 0;
-            for (int base = 0; base < ncl; base += 32) {
-                const int c = base + lane;
-                const int wc = (c < ncl) ? ((cls_start[c + 1] - cls_start[c] + 31) >> 5) : 0;
-                too_big |= (wc > 32) ? 1 : 0;
-                const int v = (wc * (wc + 1)) >> 1;
-                int incl = v;
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                if (c < ncl) chunk_base[c] = running + incl - v;
-                running += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            too_big = __any_sync(0xffffffffu, too_big);
-            if (lane == 0) { chunk_base[ncl] = running; s_last = (!too_big && !nonfinite && running <= mask_tile_cap && running <= a.mask_tile_limit) ? 1 : 0; }
-        }
+        int wmax = 0;
+        for (int c = tid; c < ncl; c += kNmsThreads) wmax = max(wmax, (cls_start[c + 1] - cls_start[c] + 31) >> 5);
+        wmax = __reduce_max_sync(0xffffffffu, wmax);
+        if (lane == 0 && wmax) atomicMax(&s_last, wmax);
+        for (int c = tid; c <= ncl; c += kNmsThreads) state[c] = 0u;                  // next row block of every class
+        for (int i = tid; i < (m >> 5) + ncl + 2; i += kNmsThreads) remw_all[i] = 0u;
         __syncthreads();
-        use_mask = s_last;
+        wmax = s_last;
+        use_mask = (!nonfinite && mask_tile_cap >= 2 * wmax && mask_tile_cap >= 64 && wmax <= a.mask_tile_limit) ? 1 : 0;
         __syncthreads();
         if (tid == 0) s_last = 0;
     }
 
     if (use_mask) {
-        // ---- D (bitmask) ------------------------------------------------------------------------------------
-        const int total_tiles = chunk_base[ncl];
+        // ---- D (bitmask), in rounds: plan -> tiles (all warps) -> greedy replay (one warp per class) ------------------
         NMS_STAMP(10);
-#ifdef YMS_PROF
-        if (a.prof && threadIdx.x == 0) { a.prof[16 * blockIdx.x + 12] = total_tiles; a.prof[16 * blockIdx.x + 13] = m; a.prof[16 * blockIdx.x + 14] = ncl; }
-#endif
-        for (int t = warp; t < total_tiles; t += kNmsWarps) {
-            int lo = 0, hi = ncl - 1;                      // largest c with tile_base[c] <= t
-            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= t) lo = mid; else hi = mid - 1; }
-            const int c = lo, s0 = cls_start[c], nseg = cls_start[c + 1] - s0, W = (nseg + 31) >> 5;
-            int u = t - chunk_base[c], k = 0, rowlen = W;
-            while (u >= rowlen) { u -= rowlen; --rowlen; ++k; }
-            if (u == 0) nms_mask_tile<true>(sbox + s0, nseg, k, k, smask + (size_t)t * 32, a.thr_f, lane);
-            else nms_mask_tile<false>(sbox + s0, nseg, k, k + u, smask + (size_t)t * 32, a.thr_f, lane);
+        for (;;) {
+            if (tid == 0) {                                // plan: per class as many further row blocks as the tile budget allows
+                int budget = mask_tile_cap, total = 0, done = 1;
+                for (int c = 0; c < ncl; ++c) {
+                    const int W = (cls_start[c + 1] - cls_start[c] + 31) >> 5;
+                    int ke = (int)state[c];
+                    chunk_base[c] = total;
+                    while (ke < W && W - ke <= budget) { budget -= W - ke; total += W - ke; ++ke; }
+                    cls_count[c] = ke;
+                    if (ke < W) done = 0;
+                }
+                chunk_base[ncl] = total;
+                s_last = done; s_next = 0;
+            }
+            __syncthreads();
+            const int total_tiles = chunk_base[ncl];
+            for (int t = warp; t < total_tiles; t += kNmsWarps) {
+                int lo = 0, hi = ncl - 1;                  // largest c with tile_base[c] <= t (classes without tiles share the next base)
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= t) lo = mid; else hi = mid - 1; }
+                const int c = lo, s0 = cls_start[c], nseg = cls_start[c + 1] - s0, W = (nseg + 31) >> 5;
+                int u = t - chunk_base[c], k = (int)state[c], rowlen = W - k;
+                while (u >= rowlen) { u -= rowlen; --rowlen; ++k; }
+                unsigned* out = smask + (size_t)t * 32;
+                const unsigned valid = (nseg - 32 * k >= 32) ? 0xffffffffu : ((1u << (nseg - 32 * k)) - 1u);
+                if ((remw_all[(s0 >> 5) + c + k] & valid) == valid) { out[lane] = 0u; continue; }   // every row already removed in an earlier round
+                if (u == 0) nms_mask_tile<true>(sbox + s0, nseg, k, k, out, a.thr_f, lane);
+                else nms_mask_tile<false>(sbox + s0, nseg, k, k + u, out, a.thr_f, lane);
+            }
+            __syncthreads();
+            for (;;) {                                     // big classes first: their replay is the critical path of the round
+                int v = 0;
+                if (lane == 0) v = atomicAdd(&s_next, 1);
+                v = __shfl_sync(0xffffffffu, v, 0);
+                if (v >= 2 * ncl) break;
+                const int c = (v < ncl) ? v : v - ncl;
+                if ((cls_start[c + 1] - cls_start[c] > 128) != (v < ncl)) continue;
+                const int kb = (int)state[c], ke = cls_count[c];
+                if (ke > kb) {
+                    const int s0 = cls_start[c], nseg = cls_start[c + 1] - s0;
+                    nms_mask_sweep_rows(smask + (size_t)chunk_base[c] * 32, remw_all + (s0 >> 5) + c, nseg, kb, ke, lane);
+                    if (lane == 0) state[c] = (unsigned)ke;
+                }
+            }
+            __syncthreads();
+            if (s_last) break;
         }
         NMS_STAMP(11);
-        __syncthreads();
         NMS_STAMP(5);
-        for (;;) {                                         // big classes first: their sweep is the critical path
-            int v = 0;
-            if (lane == 0) v = atomicAdd(&s_next, 1);
-            v = __shfl_sync(0xffffffffu, v, 0);
-            if (v >= 2 * ncl) break;
-            const int c = (v < ncl) ? v : v - ncl;
+        if (tid == 0) s_next = 0;
+        __syncthreads();
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&s_next, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= ncl) break;
             const int s0 = cls_start[c], nseg = cls_start[c + 1] - s0;
-            if ((nseg > 128) != (v < ncl)) continue;
-            const int kept = nseg ? nms_mask_sweep(smask + (size_t)chunk_base[c] * 32, skeys + s0, nseg, lane) : 0;
+            const int kept = nseg ? nms_mask_compact(skeys + s0, remw_all + (s0 >> 5) + c, nseg, lane) : 0;
             if (lane == 0) cls_count[c] = kept;
         }
     } else if (fast) {
@@ -602,9 +636,11 @@ __global__ void gather_dets_kernel(const float4* boxes, const float* scores, con
 
 int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
-int pick_groups(int batch, int num_classes) {
+int pick_groups(int batch, int num_classes, int n) {
     static const int forced = [] { const char* e = getenv("YMS_NMS_GROUPS"); return e ? atoi(e) : 0; }();
     int g = forced > 0 ? forced : kNumSMs / batch;
+    const int by_size = (n + 4095) / 4096;          // keep the expected candidates per CTA well inside the shared-memory fast path
+    if (forced <= 0 && g < by_size) g = by_size;
     if (g < 1) g = 1;
     if (g > kMaxGroups) g = kMaxGroups;
     if (g > num_classes) g = num_classes;
@@ -632,7 +668,7 @@ using namespace yms;
 
 extern "C" size_t yms_nms_workspace_bytes(int batch, int n) {
     if (batch <= 0 || n <= 0) return 0;
-    return ws_layout(batch, n, pick_groups(batch, kMaxGroups)).total;   // group count before the num_classes clamp (upper bound)
+    return ws_layout(batch, n, pick_groups(batch, kMaxGroups, n)).total;   // group count before the num_classes clamp (upper bound)
 }
 
 extern "C" int yms_nms_batched(const float* boxes, const float* scores, const int32_t* labels,
@@ -651,7 +687,7 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
         return e == cudaSuccess ? 0 : fail((int)e, "nms: memset failed");
     }
     if (((uintptr_t)boxes & 15) != 0) return fail(YMS_E_ARG, "nms: boxes must be 16-byte aligned");
-    const int groups = pick_groups(batch, num_classes);
+    const int groups = pick_groups(batch, num_classes, n);
     const WsLayout w = ws_layout(batch, n, groups);
     if (w.total > 0 && (!workspace || workspace_bytes < w.total || ((uintptr_t)workspace & 15)))
         return fail(YMS_E_WORKSPACE, "nms: workspace %zu < %zu (or misaligned)", workspace_bytes, w.total);
@@ -670,18 +706,18 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.ws_count = reinterpret_cast<int32_t*>(ws + w.count);
     a.ws_ticket = reinterpret_cast<unsigned int*>(ws + w.ticket);
     a.prof = g_prof_buf;
-    { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 1 << 30; }(); a.mask_tile_limit = lim; }
+    { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 8; }(); a.mask_tile_limit = lim; }
     if (groups > 1) {
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
         if (e != cudaSuccess) return fail((int)e, "nms: ticket memset failed");
     }
-    const size_t smem = kKeyRegionBytes + (size_t)(num_classes + 2) * 4 * 4 + 16;   // class tables sized for all classes (balanced ranges)
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(kKeyRegionBytes + (size_t)(kMaxClasses + 2) * 16 + 16));
+    const size_t smem = kKeyRegionBytes + (size_t)(num_classes + 2) * 4 * 4 + (size_t)(kFastCap / 32 + num_classes + 4) * 4 + 16;   // class tables + removed words
+    if (smem > 232448) return fail(YMS_E_UNSUPPORTED, "nms: %d classes need %zu bytes of shared memory (limit 232448)", num_classes, smem);
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "nms: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+        attr_bytes = smem;
     }
     nms_kernel<<<batch * groups, kNmsThreads, smem, st>>>(a);
     return check_launch("nms_kernel");
