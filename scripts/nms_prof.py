@@ -19,11 +19,11 @@ assert lib.yms_debug_set_prof(buf.data_ptr()) == 1
 keep, cnt = ops.nms_batched(cb, cs, cl, 0.25, 0.45, 80)
 torch.cuda.synchronize(); lib.yms_debug_set_prof(None)
 b = buf.cpu()[:128].double()
-names = ["count", "compact", "sort", "segments+boxes", "tile scan+mask tiles", "sweep", "keep list", "ticket+concat"]
+names = ["histogram+ranges", "compact", "sort", "segments+boxes", "suppression (stamp 4->6)", "-", "keep list", "ticket+concat"]
 d = b[:, 1:9] - b[:, 0:8]
+d[:, 4] = b[:, 6] - b[:, 4]
 print("kept per image (first 4):", cnt[:4].tolist())
 for i, nm in enumerate(names):
     col = d[:, i][b[:, i + 1] > 0]
-    if len(col): print(f"{nm:24s} mean {col.mean()/1e3:8.1f} kcyc  max {col.max()/1e3:8.1f} kcyc")
-t = (b[:, 11] - b[:, 10]); print("tile loop (thread 0 view): mean %.1f max %.1f kcyc; tiles/CTA mean %.0f max %.0f; m mean %.0f max %.0f; ncl mean %.1f" % (t.mean()/1e3, t.max()/1e3, b[:,12].mean(), b[:,12].max(), b[:,13].mean(), b[:,13].max(), b[:,14].mean()))
+    if nm != "-" and len(col): print(f"{nm:24s} mean {col.mean()/1e3:8.1f} kcyc  max {col.max()/1e3:8.1f} kcyc")
 tot = (b[:, 7] - b[:, 0]); print("total to stamp7: mean %.1f max %.1f kcyc" % (tot.mean()/1e3, tot.max()/1e3))

@@ -23,6 +23,8 @@
 //      lists in class order into the final keep list.
 #include "common.cuh"
 
+#include <type_traits>
+
 #include <stdlib.h>
 
 namespace yms {
@@ -239,6 +241,55 @@ __device__ __forceinline__ int nms_mask_compact(unsigned long long* sk, const un
     return kept;
 }
 
+// ---- pipelined greedy path, shared-memory flavour ------------------------------------------------------------------
+template <bool kFinite>
+__device__ __forceinline__ bool pair_hit(const float4& bi, float ai, const float4& bj, float aj, float thr_f) {
+    return kFinite ? suppresses_finite(bi, ai, bj, aj, thr_f) : suppresses(bi, ai, bj, aj, thr_f);
+}
+
+// Apply the kept boxes kb[from, to) of the class (compact, score order, in shared memory) to the lane's box.  The kept
+// boxes are broadcast reads (no shuffles) and four of them are tested per iteration: the tests are independent, which
+// gives the single warp that owns a chunk the instruction-level parallelism its dependent predicate chain lacks.
+template <bool kFinite>
+__device__ __forceinline__ bool apply_kept_smem(const float4* kb, int from, int to, const float4& bj, float aj, bool removed, float thr_f) {
+    int g = from;
+    for (; g + 4 <= to; g += 4) {
+        if (__all_sync(0xffffffffu, removed)) return true;
+        const float4 b0 = kb[g], b1 = kb[g + 1], b2 = kb[g + 2], b3 = kb[g + 3];
+        const bool h0 = pair_hit<kFinite>(b0, box_area(b0), bj, aj, thr_f);
+        const bool h1 = pair_hit<kFinite>(b1, box_area(b1), bj, aj, thr_f);
+        const bool h2 = pair_hit<kFinite>(b2, box_area(b2), bj, aj, thr_f);
+        const bool h3 = pair_hit<kFinite>(b3, box_area(b3), bj, aj, thr_f);
+        removed = removed || h0 || h1 || h2 || h3;
+    }
+    for (; g < to; ++g) {
+        const float4 b0 = kb[g];
+        removed = removed || pair_hit<kFinite>(b0, box_area(b0), bj, aj, thr_f);
+    }
+    return removed;
+}
+
+// Resolve one chunk (32 boxes in score order, box of lane l = chunk[l]): the 32 x 32 pair tests are independent (each lane
+// tests its box against the broadcast box jj), the greedy order is then replayed on the mask words.  Returns the survivors.
+template <bool kFinite>
+__device__ __forceinline__ unsigned resolve_chunk_smem(const float4* chunk, int cnt, const float4& bj, float aj, bool& removed, float thr_f, int lane) {
+    unsigned word = 0u;
+    #pragma unroll 4
+    for (int jj = 1; jj < cnt; ++jj) {
+        const float4 bc = chunk[jj];
+        const bool hit = (lane < jj) && pair_hit<kFinite>(bj, aj, bc, box_area(bc), thr_f);
+        word |= hit ? (1u << jj) : 0u;
+    }
+    unsigned rem = __ballot_sync(0xffffffffu, removed);
+    #pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const unsigned mi = __shfl_sync(0xffffffffu, word, i);
+        rem |= ((rem >> i) & 1u) ? 0u : mi;
+    }
+    removed = (rem >> lane) & 1u;
+    return ~rem;
+}
+
 struct NmsArgs {
     const float4* boxes; const float* scores; const int32_t* labels; const int32_t* n_valid;
     int n, num_classes, groups; float conf; float thr_f;
@@ -250,6 +301,8 @@ struct NmsArgs {
     int n_pad_full;                // pow2(n)
     long long* prof;               // -DYMS_PROF builds: [grid][16] phase time stamps
     int mask_tile_limit;           // bitmask path only when the largest class of the CTA has at most this many 32-box blocks
+    int dbg;                       // YMS_NMS_DBG switches: 1 = broadcast/4-way apply of kept boxes (default), 2 = mask-based chunk
+                                   // resolve (measured slower: the phase is issue-bound and it executes more instructions)
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
@@ -501,39 +554,46 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         for (int c = tid; c < ncl; c += kNmsThreads) state[c] = 0u;
         __syncthreads();
         const int total_chunks = chunk_base[ncl];
-        for (int ci = warp; ci < total_chunks; ci += kNmsWarps) {
-            int lo = 0, hi = ncl - 1;                      // largest c with chunk_base[c] <= ci
-            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= ci) lo = mid; else hi = mid - 1; }
-            const int c = lo, j = ci - chunk_base[c];
-            const int s0 = cls_start[c], s1 = cls_start[c + 1];
-            const int pos = s0 + 32 * j + lane;
-            const bool have = pos < s1;
-            const unsigned long long key = have ? skeys[pos] : kInvalidKey;
-            const float4 bj = have ? sbox[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float aj = box_area(bj);
-            bool removed = !have;
-            int applied = 0, kept = 0;
-            for (;;) {
-                unsigned st = 0;
-                if (lane == 0) st = state[c];
-                st = __shfl_sync(0xffffffffu, st, 0);
+        auto run_chunks = [&](auto finite_tag) {
+            constexpr bool kFinite = decltype(finite_tag)::value;
+            for (int ci = warp; ci < total_chunks; ci += kNmsWarps) {
+                int lo = 0, hi = ncl - 1;                      // largest c with chunk_base[c] <= ci
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= ci) lo = mid; else hi = mid - 1; }
+                const int c = lo, j = ci - chunk_base[c];
+                const int s0 = cls_start[c], s1 = cls_start[c + 1];
+                const int pos = s0 + 32 * j + lane;
+                const bool have = pos < s1;
+                const unsigned long long key = have ? skeys[pos] : kInvalidKey;
+                const float4 bj = have ? sbox[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float aj = box_area(bj);
+                bool removed = !have;
+                int applied = 0, kept = 0;
+                for (;;) {
+                    unsigned st = 0;
+                    if (lane == 0) st = state[c];
+                    st = __shfl_sync(0xffffffffu, st, 0);
+                    __threadfence_block();
+                    kept = (int)(st & 0xffffu);
+                    if (a.dbg & 1) removed = apply_kept_smem<kFinite>(sbox + s0, applied, kept, bj, aj, removed, a.thr_f);
+                    else removed = apply_kept([&](int q) { return sbox[s0 + q]; }, applied, kept, bj, aj, removed, a.thr_f, lane);
+                    applied = kept;
+                    if ((int)(st >> 16) == j) break;           // every earlier chunk of this class is final
+                    if (applied == kept) __nanosleep(32);
+                }
+                const unsigned surv = (a.dbg & 2) ? resolve_chunk_smem<kFinite>(sbox + s0 + 32 * j, min(32, s1 - s0 - 32 * j), bj, aj, removed, a.thr_f, lane)
+                                                  : resolve_chunk(bj, aj, removed, a.thr_f, lane);
+                __syncwarp();                                  // every lane has read its chunk box before the in-place compaction
+                if (!removed) {
+                    const int dst = s0 + kept + __popc(surv & ((1u << lane) - 1u));   // in place: dst < s0 + 32*(j+1)
+                    skeys[dst] = key;
+                    sbox[dst] = bj;
+                }
                 __threadfence_block();
-                kept = (int)(st & 0xffffu);
-                removed = apply_kept([&](int q) { return sbox[s0 + q]; }, applied, kept, bj, aj, removed, a.thr_f, lane);
-                applied = kept;
-                if ((int)(st >> 16) == j) break;           // every earlier chunk of this class is final
-                if (applied == kept) __nanosleep(64);
+                __syncwarp();
+                if (lane == 0) state[c] = ((unsigned)(j + 1) << 16) | (unsigned)(kept + __popc(surv));
             }
-            const unsigned surv = resolve_chunk(bj, aj, removed, a.thr_f, lane);
-            if (!removed) {
-                const int dst = s0 + kept + __popc(surv & ((1u << lane) - 1u));   // in place: dst < s0 + 32*(j+1)
-                skeys[dst] = key;
-                sbox[dst] = bj;
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) state[c] = ((unsigned)(j + 1) << 16) | (unsigned)(kept + __popc(surv));
-        }
+        };
+        if (nonfinite) run_chunks(std::false_type{}); else run_chunks(std::true_type{});
         __syncthreads();
         for (int c = tid; c < ncl; c += kNmsThreads) cls_count[c] = (int)(state[c] & 0xffffu);
     } else {
@@ -706,6 +766,7 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.ws_count = reinterpret_cast<int32_t*>(ws + w.count);
     a.ws_ticket = reinterpret_cast<unsigned int*>(ws + w.ticket);
     a.prof = g_prof_buf;
+    { static const int dbg = [] { const char* e = getenv("YMS_NMS_DBG"); return e ? atoi(e) : 1; }(); a.dbg = dbg; }
     { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 8; }(); a.mask_tile_limit = lim; }
     if (groups > 1) {
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
