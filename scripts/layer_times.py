@@ -32,15 +32,27 @@ prog = next(iter(model._programs().values()))[0]
 reps = 10
 n = len(prog.steps)
 per = [0.0] * n
-evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
-for _ in range(3):
-    for st in prog.steps: st()
-for _ in range(reps):
-    for (a, b), st in zip(evs, prog.steps):
-        a.record(); st(); b.record()
+# device time per launch: every step is captured alone in a CUDA graph, `reps` times back to back (no host launch gaps;
+# the eager event pairs used before included the host's launch latency for every kernel shorter than it)
+for st in prog.steps:
+    st()
+torch.cuda.synchronize()
+for i, st in enumerate(prog.steps):
+    if i < prog.eager_prefix and False:
+        continue
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        st()
     torch.cuda.synchronize()
-    for i, (a, b) in enumerate(evs):
-        per[i] += a.elapsed_time(b) * 1e3 / reps
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            st()
+    g.replay()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); g.replay(); b.record()
+    torch.cuda.synchronize()
+    per[i] = a.elapsed_time(b) * 1e3 / reps
 rows = []
 for i, (t, st, nm) in enumerate(zip(per, prog.steps, prog.names)):
     pl = getattr(st, "__self__", None)
@@ -51,7 +63,7 @@ for i, (t, st, nm) in enumerate(zip(per, prog.steps, prog.names)):
     ideal = max(by / peaks["hbm"], fl / peaks["tc"]) * 1e6
     rows.append((i, nm, t, by / 1e6, fl / 1e9, by / t / 1e3 if t else 0, fl / t / 1e6 if t else 0, ideal, t - ideal))
 tot = sum(r[2] for r in rows); tid = sum(r[7] for r in rows)
-lines = [f"# per-launch times: version {version}, batch {B}, {HW}x{HW}, block {block} (eager, CUDA events, mean of {reps})",
+lines = [f"# per-launch times: version {version}, batch {B}, {HW}x{HW}, block {block} (device time: each launch replayed {reps}x back to back in a CUDA graph)",
          f"total {tot:.1f} us, roofline ideal {tid:.1f} us (HBM {peaks['hbm']/1e9:.0f} GB/s, tensor {peaks['tc']/1e12:.0f} TF/s)", "",
          "| # | step | us | MB | GFLOP | GB/s | TF/s | ideal us | gap us |", "|---|---|---|---|---|---|---|---|---|"]
 for r in rows:
