@@ -23,3 +23,9 @@ prof gemm conv_gemm_kernel 0 6           # c2f_2.conv1 (1x1 64->64 @160), c2f_2.
 prof conv3 conv3x3_kernel 0 5            # conv1 (pair-line s2), the two 160x160 bottleneck convs, first two 80x80
 prof post 'nms_kernel|head_decode|stem_tc' 0 3
 du -sh $OUT; ls $OUT | grep $TAG
+# 3. MS-Block variant: the depthwise kernels (launch list + --set full of four of them)
+CMDMS="python bench.py --block ms --profile-step --warmup 3"
+$CMDMS > /dev/null 2>&1 && \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:dwconv" -s 0 -c 4 -o $OUT/prof_dw_$TAG $CMDMS > $OUT/ncu_dw_$TAG.log 2>&1
+ncu -i $OUT/prof_dw_$TAG.ncu-rep --page raw --csv > $OUT/prof_dw_${TAG}_raw.csv 2>/dev/null
+rm -f $OUT/prof_dw_$TAG.ncu-rep
