@@ -109,6 +109,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             mbar_init(bar(i), is_tempty ? 4 * (kEpiGroups / p.acc_stages) : 1);
         }
         fence_barrier_init();
+        __syncwarp();
+        // weights are constants of the program: fetched before the CTA-wide sync (overlapping the TMEM allocation and the
+        // bias staging) and BEFORE the grid dependency resolves, i.e. while the previous layer is still draining
+        if (p.resident && elect_one()) {
+            mbar_expect_tx(bar(kBarW), (uint32_t)(p.wtiles * p.kb) * (uint32_t)(p.block_n * 128));
+            for (int tap = 0; tap < p.wtiles; ++tap)
+                for (int cb = 0; cb < p.kb; ++cb)
+                    tma_load_3d(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, 0, tap);
+        }
+        __syncwarp();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     for (int i = threadIdx.x; i < p.bias_pad; i += kThreads3) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
@@ -117,13 +127,6 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (warp == 0 && p.resident && elect_one()) {        // weights are constants of the program: fetched BEFORE the grid dependency
-        mbar_expect_tx(bar(kBarW), (uint32_t)(p.wtiles * p.kb) * (uint32_t)(p.block_n * 128));     // resolves (previous layer still draining)
-        for (int tap = 0; tap < p.wtiles; ++tap)
-            for (int cb = 0; cb < p.kb; ++cb)
-                tma_load_3d(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, 0, tap);
-    }
-    __syncwarp();
     pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
     YMS_PROF_ONLY(const long long prof_t_start = clock64();)
     const uint32_t out_bytes = (uint32_t)(8 * p.th) * 128u;

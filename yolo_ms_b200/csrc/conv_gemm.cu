@@ -100,6 +100,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             mbar_init(bar0 + 8u * lane, is_tempty ? 4 * (kEpiGroups / p.acc_stages) : 1);
         }
         fence_barrier_init();
+        __syncwarp();
+        // weights are constants of the program: fetched before the CTA-wide sync (overlapping the TMEM allocation and the
+        // bias staging) and BEFORE the grid dependency resolves, i.e. while the previous layer is still draining
+        if (p.resident && elect_one()) {
+            const int kpt = p.kb1 + p.kb2;
+            mbar_expect_tx(w_bar(), (uint32_t)kb_total_res * (uint32_t)b_tile_bytes);
+            for (int tap = 0; tap < p.taps; ++tap)
+                for (int kb = 0; kb < kpt; ++kb)
+                    tma_load_3d(smem_bres + (tap * kpt + kb) * b_tile_pad, &tm_w, w_bar(),
+                                kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, 0, tap);
+        }
+        __syncwarp();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     for (int i = threadIdx.x; i < p.bias_pad; i += kThreads) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
@@ -108,15 +120,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (warp == 0 && p.resident && elect_one()) {        // weights are constants of the program: fetched BEFORE the grid dependency
-        const int kpt = p.kb1 + p.kb2;                   // resolves, i.e. while the previous layer is still draining
-        mbar_expect_tx(w_bar(), (uint32_t)kb_total_res * (uint32_t)b_tile_bytes);
-        for (int tap = 0; tap < p.taps; ++tap)
-            for (int kb = 0; kb < kpt; ++kb)
-                tma_load_3d(smem_bres + (tap * kpt + kb) * b_tile_pad, &tm_w, w_bar(),
-                            kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, 0, tap);
-    }
-    __syncwarp();
     pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
 
     YMS_PROF_ONLY(const long long prof_t_start = clock64();)
