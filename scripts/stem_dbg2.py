@@ -1,0 +1,14 @@
+import torch, sys
+sys.path.insert(0, '.')
+from yolo_ms_b200 import ops
+dev='cuda'
+which, B, HW, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+x=torch.randn(B,3,HW,HW,device=dev); xu=torch.randint(0,256,(B,HW,HW,3),dtype=torch.uint8,device=dev)
+w=torch.randn(32,3,3,3,device=dev)*0.2; b=torch.randn(32,device=dev)*0.1
+y=torch.empty(B,HW//2,HW//2,32,device=dev,dtype=torch.bfloat16)
+for i in range(n):
+    if which=='f32': ops.stem_conv(x,w,b,y)
+    else: ops.stem_conv_u8(xu,w,b,y)
+    if len(sys.argv) < 6: torch.cuda.synchronize()
+torch.cuda.synchronize()
+print(which,B,HW,n,'ok')

@@ -132,6 +132,23 @@ def test_stem_conv(ops, cout):
     assert rel_l2(y, ref32) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 256, 32), (1, 96, 320, 48), (2, 32, 640, 32), (1, 64, 260, 16)])
+def test_stem_tma_variant_fp32_and_u8(ops, B, H, W, cout, monkeypatch):
+    """Image widths >= 256 take the TMA-fed stem (raw rows through a TMA ring, row-aligned tiles, partial last tile when
+    W/2 is not a multiple of 128): vs plain PyTorch and vs the gather kernel (YMS_STEM_GATHER), fp32 and uint8 inputs."""
+    g = torch.Generator().manual_seed(W + cout)
+    img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    x = (((img.permute(0, 3, 1, 2).float() / 255.0) - mean) / std).contiguous()
+    w = (torch.randn(cout, 3, 3, 3, generator=g) * 0.3).to(DEV); b = (torch.randn(cout, generator=g) * 0.2).to(DEV)
+    ref = F.silu(F.conv2d(x.to(DEV), w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    yf = torch.empty(B, H // 2, W // 2, cout, device=DEV, dtype=torch.bfloat16); yu = torch.empty_like(yf)
+    ops.stem_conv(x.to(DEV), w, b, yf)
+    ops.stem_conv_u8(img.to(DEV), w, b, yu)
+    assert rel_l2(yf, ref) < 1e-2 and rel_l2(yu, ref) < 1e-2
+    assert rel_l2(yu, yf.float()) < 2e-3
+
+
 def test_stem_conv_u8_fuses_totensor_normalize(ops):
     """uint8 HWC image -> (v/255 - mean)/std -> stem, vs the fp32 stem on the reference's own
     ToTensor + Normalize arithmetic (yolov8/tools/test.py:114-119)."""

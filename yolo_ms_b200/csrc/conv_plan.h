@@ -76,6 +76,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+PFN_cuTensorMapEncodeTiled_v12000 get_encode();
 int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, const char* what);
 int encode_act(CUtensorMap* m, const void* ptr, int c, int64_t ps, int batch, int h, int w, bool flat,

@@ -14,6 +14,7 @@
 #include "conv_plan.h"
 
 #include <string.h>
+#include <stdlib.h>
 
 namespace yms {
 namespace {
@@ -256,6 +257,239 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-fed variant (default when the image width is a multiple of 4).  The gather kernel above is bound by the latency of
+// its per-thread loads (27 scalar loads per output pixel, one tile in flight per warp).  Here the raw image rows of a
+// tile travel through their own TMA ring: a tile is 128 consecutive output pixels of ONE output row, i.e. input rows
+// 2*oy-1 .. 2*oy+1 and input columns 2*x0-1 .. 2*x0+256, fetched as two boxes (one per 64-pixel half, each starting at a
+// 16-byte aligned column 4 elements / bytes before the first tap so that TMA alignment rules hold); padding is the TMA
+// zero fill (fp32 input) or an explicit post-normalisation zero (uint8 input).  12 converter warps (3 tiles in flight) read
+// their 27 taps from shared memory, convert to bf16 and build the K-major UMMA tile exactly like the gather producers; the
+// MMA and epilogue roles are unchanged.  No registers are tied up by loads in flight and the ring is 8 tiles deep.
+constexpr int kRawStages = 8;
+constexpr int kConvWarps = 12;
+constexpr int kConvGroups = kConvWarps / 4;
+constexpr int kTmaEpiGroups = 4;
+constexpr int kStemTmaThreads = 32 + kConvWarps * 32 + 32 + kTmaEpiGroups * kEpiGroupThreads;     // 576
+constexpr int kRawBoxF32 = 4992;            // 3 ch x 3 rows x 136 floats = 4896 B, padded to 128 B
+constexpr int kU8BoxW = 128;                // 32-bit words per box row (98 are needed; 128 keeps every row a multiple of 128 B)
+constexpr int kRawBoxU8 = 3 * kU8BoxW * 4;  // 3 rows x 512 B
+
+struct StemTmaParams {
+    float scale[3], shift[3];
+    int batch, in_h, in_w, out_h, out_w, c_out, nxb, nyp, total_tiles;     // nxb: 128-pixel tiles per output row; nyp = out_h
+    const float* weight; const float* bias;
+};
+
+template <bool kU8>
+__global__ void __launch_bounds__(kStemTmaThreads, 1)
+stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ StemTmaParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    constexpr int kRawBox = kU8 ? kRawBoxU8 : kRawBoxF32;
+    constexpr int kRawStage = 2 * kRawBox;
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t smem_a = base;                                   // kStages x 8 KB im2col tiles
+    const uint32_t smem_b = base + kStages * kATile;                // weights
+    unsigned char* g_b = gbase + kStages * kATile;
+    const uint32_t smem_out0 = smem_b + 8192;
+    unsigned char* g_out0 = g_b + 8192;
+    const uint32_t smem_raw = smem_out0 + kTmaEpiGroups * kStageOutBytes;
+    unsigned char* g_raw = g_out0 + kTmaEpiGroups * kStageOutBytes;
+    float* s_bias = reinterpret_cast<float*>(g_raw + kRawStages * kRawStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 192);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + kTmaEpiGroups + s); };
+    auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 * kTmaEpiGroups + s); };
+    auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 * kTmaEpiGroups + kRawStages + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kTmaEpiGroups + 2 * kRawStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_pad = (p.c_out + 15) & ~15;
+    constexpr int kMmaWarp = 1 + kConvWarps;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_in); prefetch_tmap(&tm_y);
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kTmaEpiGroups; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kRawStages; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int i = threadIdx.x; i < n_pad * 32; i += kStemTmaThreads) {
+        const int n = i >> 5, k = i & 31;
+        const float w = (n < p.c_out && k < 27) ? p.weight[n * 27 + k] : 0.f;
+        *reinterpret_cast<__nv_bfloat16*>(g_b + (n >> 3) * 512 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = __float2bfloat16(w);
+    }
+    for (int i = threadIdx.x; i < 192; i += kStemTmaThreads) s_bias[i] = (i < p.c_out) ? 0.5f * p.bias[i] : 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // a tile = 128 consecutive output pixels of one output row; half h = pixels [64h, 64h+64) = one TMA box of raw rows
+    auto tile_coord = [&](long long t, int& b, int& oy, int& x0) {
+        const uint32_t q = (uint32_t)t / (uint32_t)p.nxb;
+        x0 = (int)((uint32_t)t - q * (uint32_t)p.nxb) * 128;
+        b = (int)(q / (uint32_t)p.out_h);
+        oy = (int)(q - (uint32_t)b * (uint32_t)p.out_h);
+    };
+
+    if (warp == 0) {
+        // ================= raw-row TMA producer =================
+        if (elect_one()) {
+            int seq = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
+                const int stage = seq % kRawStages;
+                const uint32_t phase = (uint32_t)(seq / kRawStages) & 1u;
+                int b, oy, x0; tile_coord(t, b, oy, x0);
+                mbar_wait(rempty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(rfull_bar(stage), kU8 ? 2u * (uint32_t)kRawBoxU8 : 2u * 4896u);
+                const uint32_t dst = smem_raw + stage * kRawStage;
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    // box origin 16 B before the first tap (TMA needs a 16-byte aligned origin): 4 floats / 16 bytes
+                    if (kU8) tma_load_4d(dst + h * kRawBox, &tm_in, rfull_bar(stage), (6 * x0 - 16) / 4 + 96 * h, 2 * oy - 1, 0, b);
+                    else tma_load_4d(dst + h * kRawBox, &tm_in, rfull_bar(stage), 2 * x0 - 4 + 128 * h, 2 * oy - 1, 0, b);
+                }
+            }
+        }
+    } else if (warp < kMmaWarp) {
+        // ================= converters: raw rows (smem) -> bf16 im2col K rows =================
+        const int cw = warp - 1;
+        const int grp = cw >> 2;                                    // kConvGroups groups of 4 warps, tiles dealt round-robin
+        const int r = (cw & 3) * 32 + lane;                         // row of the MMA tile = output pixel x0 + r
+        const int half = r >> 6, rl = r & 63;
+        int seq = grp;
+        for (long long t = (long long)blockIdx.x + (long long)grp * gridDim.x; t < p.total_tiles; t += (long long)kConvGroups * gridDim.x, seq += kConvGroups) {
+            const int rstage = seq % kRawStages;
+            const uint32_t rphase = (uint32_t)(seq / kRawStages) & 1u;
+            int b, oy, x0; tile_coord(t, b, oy, x0);
+            mbar_wait(rfull_bar(rstage), rphase);
+            const unsigned char* raw = g_raw + rstage * kRawStage + half * kRawBox;
+            float v[27];
+            if (kU8) {
+                const int off = 6 * rl + 13, off4 = off & ~3, sh = (off & 3) * 8;    // window starts 16 bytes before byte 3*(2*xh - 1) + 3
+                const bool left = (x0 + r == 0);
+                #pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + ky * (kU8BoxW * 4) + off4);
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh), mid = __funnelshift_r(w1, w2, sh), hi = w2 >> sh;
+                    const uint32_t q[9] = {lo & 0xff, (lo >> 8) & 0xff, (lo >> 16) & 0xff, lo >> 24,
+                                           mid & 0xff, (mid >> 8) & 0xff, (mid >> 16) & 0xff, mid >> 24, hi & 0xff};
+                    const bool rowpad = (ky == 0 && oy == 0);        // the reference pads the NORMALISED tensor with zeros
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        #pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float val = fmaf((float)q[3 * kx + c], p.scale[c], p.shift[c]);
+                            v[c * 9 + ky * 3 + kx] = (rowpad || (kx == 0 && left)) ? 0.f : val;
+                        }
+                }
+            } else {
+                const float* rf = reinterpret_cast<const float*>(raw) + 2 * rl + 3;
+                #pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    #pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                        #pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = rf[(c * 3 + ky) * 136 + kx];
+            }
+            // pack first: the bf16 words depend on every tap, so the shared-memory reads of the raw tile have COMPLETED
+            // (not merely been issued) before the slot is handed back to the TMA producer
+            uint32_t wpk[16];
+            #pragma unroll
+            for (int kc = 0; kc < 4; ++kc)
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k0 = kc * 8 + q * 2;
+                    const float a = (k0 < 27) ? v[k0 < 27 ? k0 : 0] : 0.f;
+                    const float c = (k0 + 1 < 27) ? v[k0 + 1 < 27 ? k0 + 1 : 0] : 0.f;
+                    wpk[kc * 4 + q] = pack_bf16x2(a, c);
+                }
+            asm volatile("" :: "r"(wpk[0]), "r"(wpk[1]), "r"(wpk[2]), "r"(wpk[3]), "r"(wpk[4]), "r"(wpk[5]), "r"(wpk[6]), "r"(wpk[7]),
+                         "r"(wpk[8]), "r"(wpk[9]), "r"(wpk[10]), "r"(wpk[11]), "r"(wpk[12]), "r"(wpk[13]), "r"(wpk[14]), "r"(wpk[15]) : "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rempty_bar(rstage));         // this warp has consumed its part of the raw tile
+            const int stage = seq % kStages;
+            const uint32_t phase = (uint32_t)(seq / kStages) & 1u;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t dst = smem_a + stage * kATile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 16u;
+            #pragma unroll
+            for (int kc = 0; kc < 4; ++kc)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + kc * 128u), "r"(wpk[kc * 4]), "r"(wpk[kc * 4 + 1]),
+                             "r"(wpk[kc * 4 + 2]), "r"(wpk[kc * 4 + 3]) : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+        }
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t bdesc = make_nosw_desc(smem_b);
+        int seq = 0, acc = 0; uint32_t acc_phase = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
+            const int stage = seq % kStages;
+            const uint32_t phase = (uint32_t)(seq / kStages) & 1u;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t adesc = make_nosw_desc(smem_a + stage * kATile);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+            if (elect_one()) {
+                umma_bf16(d_tmem, adesc, bdesc, idesc, 0u);
+                umma_bf16(d_tmem, adesc + 16ull, bdesc + 16ull, idesc, 1u);     // +256 B: next 16 K elements
+                umma_commit(empty_bar(stage));
+                umma_commit(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (++acc == kTmaEpiGroups) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        // ================= epilogue =================
+        const int ew = warp - kMmaWarp - 1;
+        const int grp = ew >> 2;
+        EpiShared e;
+        e.tm_y = &tm_y; e.tm_res = &tm_y;
+        e.res_bar = 0;
+        e.s_out = smem_out0 + grp * kStageOutBytes;
+        e.s_bias = s_bias;
+        e.block_n = n_pad; e.c_out = p.c_out; e.act = 1; e.has_res = 0;
+        e.out_bytes = 0;
+        e.bar_id = 1 + grp;
+        e.leader = (ew & 3) == 0 && lane == 0;
+        e.row = (warp & 3) * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * 128);
+        const int n_chunks = (n_pad + 63) >> 6;
+        uint32_t res_phase = 0u, acc_phase = 0u;
+        for (long long t = (long long)blockIdx.x + (long long)grp * gridDim.x; t < p.total_tiles; t += (long long)kTmaEpiGroups * gridDim.x) {
+            int b, oy, x0; tile_coord(t, b, oy, x0);
+            EpiTile tl; tl.n0 = 0; tl.x0 = x0; tl.y0 = oy; tl.img = b;
+            mbar_wait(tfull_bar(grp), acc_phase);
+            acc_phase ^= 1u;
+            tc_fence_after();
+            for (int ch = 0; ch < n_chunks; ++ch) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(grp));
+        }
+        if (e.leader) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 }  // namespace yms
 
@@ -264,8 +498,58 @@ using namespace yms;
 // declared in glue.cu's dispatcher.  xu8 != nullptr selects the uint8-HWC + normalisation path.
 int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* mean, const float* stdv, int batch, int in_h, int in_w,
                        int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream) {
-    static thread_local struct Cache { const void* y; int64_t ps; int b, h, w, c; CUtensorMap map; bool ok; } cache = {};
     const int out_h = in_h / 2, out_w = in_w / 2;
+    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && !getenv("YMS_STEM_GATHER")) {
+        // ---- TMA-fed variant: raw rows through a TMA ring, row-aligned tiles ----
+        static thread_local struct Cache2 { const void* in; const void* y; int64_t ps; int b, h, w, c, u8; CUtensorMap min, my; bool ok; } c2 = {};
+        const void* in = xu8 ? (const void*)xu8 : (const void*)x;
+        if (!(c2.ok && c2.in == in && c2.y == y && c2.ps == y_ps && c2.b == batch && c2.h == in_h && c2.w == in_w && c2.c == c_out && c2.u8 == (xu8 ? 1 : 0))) {
+            int rc = encode_act(&c2.my, y, c_out, y_ps, batch, out_h, out_w, /*flat=*/false, out_w < 128 ? out_w : 128, 1, 1, "stem y");
+            if (rc) return rc;
+            auto fn = get_encode();
+            if (!fn) return fail(YMS_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+            CUresult r;
+            if (xu8) {      // uint8 NHWC rows as 32-bit words: (W*3/4, H, 1, B), box (128, 3, 1, 1)
+                uint64_t dims[4] = {(uint64_t)in_w * 3 / 4, (uint64_t)in_h, 1, (uint64_t)batch};
+                uint64_t strides[3] = {(uint64_t)in_w * 3, (uint64_t)in_w * 3 * in_h, (uint64_t)in_w * 3 * in_h};
+                uint32_t box[4] = {(uint32_t)kU8BoxW, 3, 1, 1}, es[4] = {1, 1, 1, 1};
+                r = fn(&c2.min, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            } else {        // fp32 NCHW: (W, H, 3, B), box (136, 3, 3, 1)
+                uint64_t dims[4] = {(uint64_t)in_w, (uint64_t)in_h, 3, (uint64_t)batch};
+                uint64_t strides[3] = {(uint64_t)in_w * 4, (uint64_t)in_w * 4 * in_h, (uint64_t)in_w * 4 * in_h * 3};
+                uint32_t box[4] = {136, 3, 3, 1}, es[4] = {1, 1, 1, 1};
+                r = fn(&c2.min, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+            if (r != CUDA_SUCCESS) return fail(YMS_E_DRIVER, "cuTensorMapEncodeTiled(stem input) failed: %d", (int)r);
+            c2.in = in; c2.y = y; c2.ps = y_ps; c2.b = batch; c2.h = in_h; c2.w = in_w; c2.c = c_out; c2.u8 = xu8 ? 1 : 0; c2.ok = true;
+        }
+        StemTmaParams q;
+        memset(&q, 0, sizeof(q));
+        if (xu8) for (int c = 0; c < 3; ++c) { q.scale[c] = 1.0f / (255.0f * stdv[c]); q.shift[c] = -mean[c] / stdv[c]; }
+        q.batch = batch; q.in_h = in_h; q.in_w = in_w; q.out_h = out_h; q.out_w = out_w; q.c_out = c_out;
+        q.nxb = (out_w + 127) / 128; q.nyp = out_h;
+        const long long tiles = (long long)q.nxb * out_h * batch;
+        if (tiles >= (1LL << 31)) return fail(YMS_E_UNSUPPORTED, "stem: too many tiles");
+        q.total_tiles = (int)tiles;
+        q.weight = weight; q.bias = bias;
+        const size_t raw = (size_t)kRawStages * 2 * (xu8 ? kRawBoxU8 : kRawBoxF32);
+        const size_t smem2 = 1024 + kStages * kATile + 8192 + kTmaEpiGroups * kStageOutBytes + raw + 192 * 4 +
+                             (2 * kStages + 2 * kTmaEpiGroups + 2 * kRawStages) * 8 + 16;
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaError_t e = cudaFuncSetAttribute(stem_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return fail((int)e, "stem: smem attribute: %s", cudaGetErrorString(e));
+            attr2 = true;
+        }
+        const int grid2 = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
+        if (xu8) stem_tma_kernel<true><<<grid2, kStemTmaThreads, smem2, stream>>>(c2.min, c2.my, q);
+        else stem_tma_kernel<false><<<grid2, kStemTmaThreads, smem2, stream>>>(c2.min, c2.my, q);
+        return check_launch("stem_tma_kernel");
+    }
+    static thread_local struct Cache { const void* y; int64_t ps; int b, h, w, c; CUtensorMap map; bool ok; } cache = {};
     if (!(cache.ok && cache.y == y && cache.ps == y_ps && cache.b == batch && cache.h == in_h && cache.w == in_w && cache.c == c_out)) {
         int rc = encode_act(&cache.map, y, c_out, y_ps, batch, out_h, out_w, /*flat=*/true, 128, 1, 1, "stem y");
         if (rc) return rc;

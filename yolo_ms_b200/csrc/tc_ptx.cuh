@@ -39,7 +39,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (clock64() - t0 > 4000000000LL) {
+#ifdef YMS_PROF
+            printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
+            __trap();
+        }
     }
 }
 // Role-level cycle accounting (only in -DYMS_PROF builds, see scripts/role_prof.py): time spent in a wait.
