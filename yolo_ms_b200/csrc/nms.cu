@@ -538,15 +538,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         }
     } else if (fast) {
         // ---- D (fast): pipelined chunks -------------------------------------------------------
-        if (warp == 0) {                                   // chunk_base = exclusive scan of ceil(n_c / 32)
+        // Chunks are enumerated class by class in DESCENDING class size (perm, kept in cls_count until the end): the chain of
+        // a class's chunks is sequential, so the longest chains must start first and overlap with everything else.
+        int* perm = cls_count;
+        for (int c = tid; c < ncl; c += kNmsThreads) {
+            const int nme = cls_start[c + 1] - cls_start[c];
+            int rank = 0;
+            for (int o = 0; o < ncl; ++o) {
+                const int no = cls_start[o + 1] - cls_start[o];
+                rank += (no > nme || (no == nme && o < c)) ? 1 : 0;
+            }
+            perm[rank] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {                                   // chunk_base[i] = exclusive scan of ceil(n / 32) over perm order
             int running = 0;
             for (int base = 0; base < ncl; base += 32) {
-                const int c = base + lane;
-                const int v = (c < ncl) ? ((cls_start[c + 1] - cls_start[c] + 31) >> 5) : 0;
+                const int i = base + lane;
+                const int c = (i < ncl) ? perm[i] : 0;
+                const int v = (i < ncl) ? ((cls_start[c + 1] - cls_start[c] + 31) >> 5) : 0;
                 int incl = v;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                if (c < ncl) chunk_base[c] = running + incl - v;
+                if (i < ncl) chunk_base[i] = running + incl - v;
                 running += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (lane == 0) chunk_base[ncl] = running;
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
             for (int ci = warp; ci < total_chunks; ci += kNmsWarps) {
                 int lo = 0, hi = ncl - 1;                      // largest c with chunk_base[c] <= ci
                 while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= ci) lo = mid; else hi = mid - 1; }
-                const int c = lo, j = ci - chunk_base[c];
+                const int c = perm[lo], j = ci - chunk_base[lo];
                 const int s0 = cls_start[c], s1 = cls_start[c + 1];
                 const int pos = s0 + 32 * j + lane;
                 const bool have = pos < s1;

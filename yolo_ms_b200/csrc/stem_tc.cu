@@ -499,7 +499,7 @@ using namespace yms;
 int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* mean, const float* stdv, int batch, int in_h, int in_w,
                        int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream) {
     const int out_h = in_h / 2, out_w = in_w / 2;
-    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && !getenv("YMS_STEM_GATHER")) {
+    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && getenv("YMS_STEM_TMA")) {     // opt-in: an intermittent launch failure at 1280x1280 / batch 16 is not understood yet
         // ---- TMA-fed variant: raw rows through a TMA ring, row-aligned tiles ----
         static thread_local struct Cache2 { const void* in; const void* y; int64_t ps; int b, h, w, c, u8; CUtensorMap min, my; bool ok; } c2 = {};
         const void* in = xu8 ? (const void*)xu8 : (const void*)x;
