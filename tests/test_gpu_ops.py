@@ -134,10 +134,8 @@ def test_stem_conv(ops, cout):
 
 @pytest.mark.parametrize("B,H,W,cout", [(2, 64, 256, 32), (1, 96, 320, 48), (2, 32, 640, 32), (1, 64, 260, 16)])
 def test_stem_tma_variant_fp32_and_u8(ops, B, H, W, cout, monkeypatch):
-    """The opt-in TMA-fed stem (YMS_STEM_TMA=1; raw rows through a TMA ring, row-aligned tiles, partial last tile when W/2
-    is not a multiple of 128) and the default gather kernel on the same wide images: vs plain PyTorch, fp32 and uint8."""
-    if os.environ.get("YMS_TEST_EXPERIMENTAL") == "1":      # the TMA variant is opt-in (DESIGN.md 4.3); default: gather kernel
-        monkeypatch.setenv("YMS_STEM_TMA", "1")
+    """Image widths >= 256 take the TMA-fed stem (raw rows through a TMA ring, row-aligned tiles, partial last tile when
+    W/2 is not a multiple of 128): vs plain PyTorch, fp32 and uint8 inputs, and vs the gather kernel (YMS_STEM_GATHER)."""
     g = torch.Generator().manual_seed(W + cout)
     img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
     mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
@@ -149,6 +147,25 @@ def test_stem_tma_variant_fp32_and_u8(ops, B, H, W, cout, monkeypatch):
     ops.stem_conv_u8(img.to(DEV), w, b, yu)
     assert rel_l2(yf, ref) < 1e-2 and rel_l2(yu, ref) < 1e-2
     assert rel_l2(yu, yf.float()) < 2e-3
+    monkeypatch.setenv("YMS_STEM_GATHER", "1")          # same arithmetic, different data path: bit-identical outputs
+    yg = torch.empty_like(yf); ygu = torch.empty_like(yf)
+    ops.stem_conv(x.to(DEV), w, b, yg)
+    ops.stem_conv_u8(img.to(DEV), w, b, ygu)
+    assert torch.equal(yg, yf) and torch.equal(ygu, yu)
+
+
+def test_stem_tma_many_back_to_back_launches(ops):
+    """Regression for the ring-slot ownership bug of the first TMA-fed stem (3 converter groups on 8-deep rings: a group could
+    pass the parity wait of a slot two uses ahead): 60 back-to-back launches on a 1280-wide fp32 batch must complete and agree."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(6, 3, 1280, 1280, generator=g).to(DEV)
+    w = (torch.randn(32, 3, 3, 3, generator=g) * 0.3).to(DEV); b = (torch.randn(32, generator=g) * 0.2).to(DEV)
+    y0 = torch.empty(6, 640, 640, 32, device=DEV, dtype=torch.bfloat16); y = torch.empty_like(y0)
+    ops.stem_conv(x, w, b, y0)
+    for _ in range(60):
+        ops.stem_conv(x, w, b, y)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y0)
 
 
 def test_stem_conv_u8_fuses_totensor_normalize(ops):

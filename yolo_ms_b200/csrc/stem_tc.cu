@@ -24,6 +24,8 @@ using namespace tc;
 constexpr int kProdWarps = 16;             // 4 gather groups of 4 warps: the gather is latency-bound, bytes in flight = warps x 27 loads
 constexpr int kProdGroups = kProdWarps / 4;
 constexpr int kStemEpiGroups = 2;
+constexpr int kStagesGather = 8;
+static_assert(kStagesGather % kProdGroups == 0, "every ring slot must have a single producer group (see the TMA-fed kernel)");
 constexpr int kStemThreads = kProdWarps * 32 + 32 + kStemEpiGroups * kEpiGroupThreads;     // 800
 constexpr int kStages = 8;
 constexpr int kATile = 128 * 64;          // 8 KB: 128 pixels x 32 bf16
@@ -266,11 +268,19 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
 // 16-byte aligned column 4 elements / bytes before the first tap so that TMA alignment rules hold); padding is the TMA
 // zero fill (fp32 input) or an explicit post-normalisation zero (uint8 input).  12 converter warps (3 tiles in flight) read
 // their 27 taps from shared memory, convert to bf16 and build the K-major UMMA tile exactly like the gather producers; the
-// MMA and epilogue roles are unchanged.  No registers are tied up by loads in flight and the ring is 8 tiles deep.
-constexpr int kRawStages = 8;
+// MMA and epilogue roles are unchanged.  No registers are tied up by loads in flight and the rings are 6 tiles deep.
+// Ring depths are MULTIPLES of the number of converter groups: every ring slot then has a single owner group, whose
+// consecutive uses are ordered by its own program order.  With 3 groups on 8-deep rings (first version) a group could
+// reach the parity wait of use k+2 of a slot before use k (owned by another group) had completed -- the wait then passed on
+// the stale phase, the slot was consumed and released twice and the CTA dead-locked a few tiles later (seen only with fp32
+// images >= 1280 wide, where one late TMA box was enough skew).  Found with the host-mapped wait-for-graph records of the
+// profiling build (tc_ptx.cuh::mbar_wait).
+constexpr int kRawStages = 6;
+constexpr int kTmaStages = 6;                // A-tile ring of the TMA-fed kernel
 constexpr int kConvWarps = 12;
 constexpr int kConvGroups = kConvWarps / 4;
 constexpr int kTmaEpiGroups = 4;
+static_assert(kRawStages % kConvGroups == 0 && kTmaStages % kConvGroups == 0, "ring depths must be multiples of the converter group count");
 constexpr int kStemTmaThreads = 32 + kConvWarps * 32 + 32 + kTmaEpiGroups * kEpiGroupThreads;     // 576
 constexpr int kRawBoxF32 = 4992;            // 3 ch x 3 rows x 136 floats = 4896 B, padded to 128 B
 constexpr int kU8BoxW = 128;                // 32-bit words per box row (98 are needed; 128 keeps every row a multiple of 128 B)
@@ -290,9 +300,9 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     constexpr int kRawStage = 2 * kRawBox;
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
-    const uint32_t smem_a = base;                                   // kStages x 8 KB im2col tiles
-    const uint32_t smem_b = base + kStages * kATile;                // weights
-    unsigned char* g_b = gbase + kStages * kATile;
+    const uint32_t smem_a = base;                                   // kTmaStages x 8 KB im2col tiles
+    const uint32_t smem_b = base + kTmaStages * kATile;                // weights
+    unsigned char* g_b = gbase + kTmaStages * kATile;
     const uint32_t smem_out0 = smem_b + 8192;
     unsigned char* g_out0 = g_b + 8192;
     const uint32_t smem_raw = smem_out0 + kTmaEpiGroups * kStageOutBytes;
@@ -301,12 +311,12 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 192);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + kTmaEpiGroups + s); };
-    auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 * kTmaEpiGroups + s); };
-    auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 * kTmaEpiGroups + kRawStages + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kTmaEpiGroups + 2 * kRawStages);
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kTmaStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kTmaStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kTmaStages + kTmaEpiGroups + s); };
+    auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * kTmaStages + 2 * kTmaEpiGroups + s); };
+    auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * kTmaStages + 2 * kTmaEpiGroups + kRawStages + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTmaStages + 2 * kTmaEpiGroups + 2 * kRawStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pad = (p.c_out + 15) & ~15;
@@ -314,7 +324,7 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_in); prefetch_tmap(&tm_y);
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kTmaStages; ++s) { mbar_init(full_bar(s), 4); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < kTmaEpiGroups; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         for (int s = 0; s < kRawStages; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4); }
         fence_barrier_init();
@@ -417,8 +427,8 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                          "r"(wpk[8]), "r"(wpk[9]), "r"(wpk[10]), "r"(wpk[11]), "r"(wpk[12]), "r"(wpk[13]), "r"(wpk[14]), "r"(wpk[15]) : "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(rempty_bar(rstage));         // this warp has consumed its part of the raw tile
-            const int stage = seq % kStages;
-            const uint32_t phase = (uint32_t)(seq / kStages) & 1u;
+            const int stage = seq % kTmaStages;
+            const uint32_t phase = (uint32_t)(seq / kTmaStages) & 1u;
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t dst = smem_a + stage * kATile + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 16u;
             #pragma unroll
@@ -435,8 +445,8 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const uint64_t bdesc = make_nosw_desc(smem_b);
         int seq = 0, acc = 0; uint32_t acc_phase = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
-            const int stage = seq % kStages;
-            const uint32_t phase = (uint32_t)(seq / kStages) & 1u;
+            const int stage = seq % kTmaStages;
+            const uint32_t phase = (uint32_t)(seq / kTmaStages) & 1u;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -499,7 +509,7 @@ using namespace yms;
 int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* mean, const float* stdv, int batch, int in_h, int in_w,
                        int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream) {
     const int out_h = in_h / 2, out_w = in_w / 2;
-    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && getenv("YMS_STEM_TMA")) {     // opt-in: an intermittent launch failure at 1280x1280 / batch 16 is not understood yet
+    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && !getenv("YMS_STEM_GATHER")) {
         // ---- TMA-fed variant: raw rows through a TMA ring, row-aligned tiles ----
         static thread_local struct Cache2 { const void* in; const void* y; int64_t ps; int b, h, w, c, u8; CUtensorMap min, my; bool ok; } c2 = {};
         const void* in = xu8 ? (const void*)xu8 : (const void*)x;
@@ -535,8 +545,8 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
         q.total_tiles = (int)tiles;
         q.weight = weight; q.bias = bias;
         const size_t raw = (size_t)kRawStages * 2 * (xu8 ? kRawBoxU8 : kRawBoxF32);
-        const size_t smem2 = 1024 + kStages * kATile + 8192 + kTmaEpiGroups * kStageOutBytes + raw + 192 * 4 +
-                             (2 * kStages + 2 * kTmaEpiGroups + 2 * kRawStages) * 8 + 16;
+        const size_t smem2 = 1024 + kTmaStages * kATile + 8192 + kTmaEpiGroups * kStageOutBytes + raw + 192 * 4 +
+                             (2 * kTmaStages + 2 * kTmaEpiGroups + 2 * kRawStages) * 8 + 16;
         static bool attr2 = false;
         if (!attr2) {
             cudaError_t e = cudaFuncSetAttribute(stem_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -577,3 +587,11 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
     else stem_tc_kernel<false><<<grid, kStemThreads, smem, stream>>>(cache.map, p);
     return check_launch("stem_tc_kernel");
 }
+
+#ifdef YMS_PROF
+/* profiling builds only: host-mapped buffer [64] u64 that mbar_wait fills with (block, thread, barrier, parity) before it traps */
+extern "C" int yms_debug_stem_trap_buf(void* host_mapped) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(host_mapped);
+    return (int)cudaMemcpyToSymbol(yms::tc::g_trap_buf, &p, sizeof(p));
+}
+#endif

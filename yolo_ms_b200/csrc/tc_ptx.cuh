@@ -34,17 +34,32 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+#ifdef YMS_PROF
+static __device__ unsigned long long* g_trap_buf = nullptr;   // per translation unit; set by yms_debug_*_trap_buf
+#endif
 // Bounded wait: a protocol bug must fault the launch (trap) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
 #ifdef YMS_PROF
-            printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+    bool recorded = false;
 #endif
-            __trap();
+    while (!mbar_try_wait(bar, parity)) {
+        const long long dt = clock64() - t0;
+#ifdef YMS_PROF
+        // post-mortem: every waiter records itself in HOST-mapped memory (readable after the context is gone) one second
+        // before the first of them traps, so the whole wait-for graph of a deadlock is visible (scripts/stem_stress.py)
+        if (dt > 2000000000LL && !recorded && g_trap_buf && (threadIdx.x & 31) == 0) {
+            recorded = true;
+            const unsigned long long slot = atomicAdd(g_trap_buf, 1ull);
+            if (slot < 63) {
+                g_trap_buf[1 + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)threadIdx.x << 32) |
+                                       ((unsigned long long)(bar & 0xffffffu) << 8) | (parity & 0xffu);
+                __threadfence_system();
+            }
         }
+#endif
+        if (dt > 4000000000LL) __trap();
     }
 }
 // Role-level cycle accounting (only in -DYMS_PROF builds, see scripts/role_prof.py): time spent in a wait.
