@@ -81,6 +81,30 @@ int yms_conv_plan_destroy(yms_conv_plan* plan);
 /* 2*MACs of the plan and the algorithmic bytes (inputs + outputs + weights) it moves. */
 int yms_conv_plan_cost(const yms_conv_plan* plan, double* flops, double* bytes);
 
+/* Head decode fused into a head branch's final convolution.  Turns the plan of the biased 1x1 nn.Conv2d that ends
+ * head.box[i] / head.cls[i] (yolov8/model/yolov8_head.py:86,101; plan created with ksize 1, act 0, f32 output) into one that
+ * does NOT store its logits but decodes them in the epilogue -- DFL.forward (components.py:176-191), the eval branch of
+ * Head.forward incl. make_anchors (yolov8_head.py:127-158) and the candidate selection of the post-process
+ * (tools/test.py:166-179) -- writing the same values yms_head_decode would produce from the stored logits (bit-identical):
+ *   branch 1 (box,   c_out == 64):          pred[b, a, 0:4] = (cx, cy, w, h) * stride,  cand_boxes[b, a] = xyxy
+ *   branch 2 (class, c_out == num_classes): pred[b, a, 4:]  = sigmoid(logits),          cand_scores / cand_labels[b, a] = max / first arg-max
+ * with a = anchor_base + y * map_w + x.  `stride` points to ONE float in DEVICE memory that is read when the plan runs, so
+ * head.stride (a plain attribute in the reference, :79) is honoured at call time even inside a captured CUDA graph.
+ * Limits: num_classes a multiple of 16, <= 128.  Returns YMS_E_UNSUPPORTED otherwise (use yms_head_decode then). */
+typedef struct yms_decode_fusion {
+    int32_t branch;                   /* 1 = box branch, 2 = class branch                                  */
+    int32_t map_h, map_w;             /* feature map of this scale == the plan's in_h, in_w                */
+    int32_t anchor_base;              /* index of the scale's first anchor among an image's anchors        */
+    int32_t anchors;                  /* A: anchors per image over all scales                              */
+    int32_t num_classes;
+    const float* stride;              /* DEVICE f32[1]                                                     */
+    float* pred;                      /* f32 [B, A, 4 + num_classes]                                       */
+    float* cand_boxes;                /* f32 [B, A, 4] (branch 1) or NULL                                  */
+    float* cand_scores;               /* f32 [B, A]    (branch 2) or NULL                                  */
+    int32_t* cand_labels;             /* i32 [B, A]    (branch 2) or NULL; comes with cand_scores          */
+} yms_decode_fusion;
+int yms_conv_plan_fuse_decode(yms_conv_plan* plan, const yms_decode_fusion* f);
+
 /* Stem: first layer backbone.conv0 (yolov8/model/yolov8_backbone.py:39, 3x3 stride 2 on the
  * NCHW fp32 image, components.py:69-77) -> NHWC bf16.  weight f32 [c_out][3][3][3] with BN
  * folded, bias f32 [c_out]. */

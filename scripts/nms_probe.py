@@ -1,0 +1,30 @@
+"""Class-size statistics of the bench workload's NMS input and the kernel time (env knobs: YMS_NMS_GROUPS, YMS_NMS_MASK_TILES)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from yolo_ms_b200 import YOLOv8, synth, ops
+dev = torch.device("cuda", 0)
+model = YOLOv8(version="s", num_classes=80)
+model.load_state_dict(synth.synthetic_state_dict(model, "s", "c2f", seed=1))
+model = model.to(dev).eval(); model.head.stride = torch.tensor([8.0, 16.0, 32.0])
+x = synth.make_images(32, 640, 640, seed=7).to(dev)
+boxes, scores, labels, keep, count = model.detect(x, 0.25, 0.45)
+boxes, scores, labels = boxes.clone(), scores.clone(), labels.clone()
+if "--stats" in sys.argv:
+    for b in (0, 1):
+        valid = scores[b] > 0.25
+        h = torch.bincount(labels[b][valid].long(), minlength=80)
+        kl = labels[b][keep[b, :int(count[b])].long()].long()
+        hk = torch.bincount(kl, minlength=80)
+        top = torch.argsort(h, descending=True)[:8]
+        print(f"image {b}: candidates {int(valid.sum())}, kept {int(count[b])}, classes used {int((h > 0).sum())}; top classes (n, kept):",
+              [(int(h[c]), int(hk[c])) for c in top])
+for _ in range(3):
+    ops.nms_batched(boxes, scores, labels, 0.25, 0.45, 80)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(20):
+    ops.nms_batched(boxes, scores, labels, 0.25, 0.45, 80)
+b.record(); torch.cuda.synchronize()
+print("nms ms:", round(a.elapsed_time(b) / 20, 4), "groups env:", os.environ.get("YMS_NMS_GROUPS"), "mask tiles env:", os.environ.get("YMS_NMS_MASK_TILES"))

@@ -232,6 +232,54 @@ def test_detect_equals_postprocess_of_forward_and_oracle():
         assert np.array_equal(res[i][0].cpu().numpy(), wb) and np.array_equal(res[i][2].cpu().numpy(), wl)
 
 
+@pytest.mark.parametrize("version,hw,batch", [("n", (160, 224), 3), ("s", (96, 96), 5), ("n", (640, 640), 2)])
+def test_fused_decode_is_bit_identical_to_the_decode_kernel(version, hw, batch):
+    """The YOLOv8 program decodes in the epilogue of the head's final 1x1 convs (yms_conv_plan_fuse_decode); the logits
+    it would have stored + the stand-alone decode kernel (yms_head_decode) must give the SAME bits: predictions, xyxy
+    candidates, best score / first-max class.  Map sizes that are not multiples of the 128-pixel tile (tiles straddle
+    images, the last tile is partial) are included; head.stride is re-read on every call."""
+    from oracle import weights as W
+    from yolo_ms_b200 import ops
+    m, _ = _model(version, seed=4)
+    x = W.make_images(batch, hw[0], hw[1], seed=11).to(DEV)
+    prog_pred = m(x)
+    prog = list(m._programs().values())[0][0]
+    assert prog.decoded is not None and len(prog.raw_tail) == 6, "the fused program was not built"
+    boxes, scores, labels, keep, count = m.detect(x, 0.25, 0.45)
+    boxes, scores, labels = boxes.clone(), scores.clone(), labels.clone()
+    raws = m.forward_raw(x)
+    pred, (cb, cs, cl) = ops.head_decode(raws, STRIDES, 80, with_candidates=True)
+    assert torch.equal(prog_pred, pred)
+    assert torch.equal(boxes, cb) and torch.equal(scores, cs) and torch.equal(labels, cl)
+    k2, c2 = ops.nms_batched(cb, cs, cl, 0.25, 0.45, 80)
+    assert torch.equal(count, c2) and torch.equal(keep, k2)
+    # stride is a run-time value of the captured program
+    m.head.stride = torch.tensor([4.0, 10.0, 48.0])
+    assert torch.equal(m(x), ops.head_decode(raws, [4.0, 10.0, 48.0], 80))
+    m.head.stride = torch.zeros(3)
+    z = m(x)
+    assert float(z[..., :4].abs().max()) == 0.0 and torch.equal(z[..., 4:], pred[..., 4:])
+
+
+def test_class_counts_outside_the_fused_epilogue_use_the_decode_kernel():
+    """num_classes that is not a multiple of 16 cannot be decoded in the conv epilogue: the program keeps the logits and
+    the stand-alone decode kernel runs (same API, same results as decoding forward_raw)."""
+    from oracle import weights as W
+    from yolo_ms_b200 import ops
+    from yolo_ms_b200.yolov8 import YOLOv8
+    torch.manual_seed(3)
+    m = randomize_bn(YOLOv8(version="n", num_classes=24), seed=3).to(DEV).eval()
+    m.head.stride = torch.tensor(STRIDES)
+    x = W.make_images(2, 64, 96, seed=2).to(DEV)
+    pred = m(x)
+    prog = list(m._programs().values())[0][0]
+    assert prog.decoded is None and not prog.raw_tail
+    assert pred.shape == (2, 8 * 12 + 4 * 6 + 2 * 3, 28)
+    assert torch.equal(pred, ops.head_decode(m.forward_raw(x), STRIDES, 24))
+    boxes, scores, labels, keep, count = m.detect(x, 0.25, 0.45)
+    assert int(labels.max()) < 24 and int(count.min()) >= 0
+
+
 # ----------------------------------------------------------------------------------------------
 # BASELINE.json configs at full resolution (small batch so the CPU oracle finishes in seconds)
 # ----------------------------------------------------------------------------------------------

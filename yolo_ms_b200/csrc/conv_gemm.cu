@@ -21,6 +21,7 @@
 //                  (or direct fp32 stores for the head's raw logits)
 //     two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_plan.h"
+#include "decode_math.cuh"
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -53,6 +54,92 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int 
     return c;
 }
 
+// Decode-fused epilogue of a head branch's final (biased, linear) 1x1 convolution.  The tile is 128 consecutive pixels of
+// the flat (B*H*W) view; accumulator row `row` = TMEM lane = ONE anchor, its columns = the branch's logits, so the DFL
+// softmax-expectation (box branch) and the sigmoid scores + first-max class (class branch) are thread-local: the fp32
+// logits never travel to HBM and back (yolov8_head.py:127-144, components.py:176-191, tools/test.py:166-179).  The
+// arithmetic is decode_math.cuh, i.e. bit-identical to head_decode_v2_kernel on the logits this conv would have stored.
+// Every lane executes the (warp-collective) tcgen05.ld; only the stores are predicated on the row being a real pixel.
+//
+// Stores: a prediction row is 4 + nc floats, so "one thread stores its row" scatters every warp store over 32 lines (first
+// version: the class branch at 80x80 took 32 us instead of 19 -- one 16-byte packet per lane on the SM -> L2 path).  The
+// class scores therefore go through the warp's 32 rows of the group's staging tile (128 B = 32 scores per row, swizzled
+// like the TMA path) and leave as 128-byte row segments: 8 lanes per row, 4 rows per store instruction.
+__device__ __forceinline__ void epilogue_decode(const DecodeFuse& d, const float* s_bias, int nc, uint32_t t_row, uint32_t s_out,
+                                                int row, int lane, uint32_t m, uint32_t m_total) {
+    int arow = -1, pix = 0;                                       // prediction row of this thread's pixel (-1: past the last pixel)
+    if (m < m_total) {
+        const uint32_t img = m / (uint32_t)d.hw;
+        pix = (int)(m - img * (uint32_t)d.hw);
+        arow = (int)img * d.anchors + d.anchor_base + pix;
+    }
+    if (d.mode == 1) {
+        float dist[4];
+        #pragma unroll
+        for (int side = 0; side < 4; ++side) {
+            uint32_t v[16];
+            tmem_ld16(t_row + (uint32_t)(side * 16), v);
+            tmem_ld_wait();
+            float f[16];
+            #pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + s_bias[side * 16 + k];
+            dist[side] = dfl_expectation(f);
+        }
+        if (arow >= 0) {
+            const int y = pix / d.w, x = pix - y * d.w;
+            const float4 box = dfl_box((float)x + 0.5f, (float)y + 0.5f, make_float4(dist[0], dist[1], dist[2], dist[3]), __ldg(d.stride));
+            *reinterpret_cast<float4*>(d.pred + (size_t)arow * d.nout) = box;
+            if (d.cand_boxes) d.cand_boxes[arow] = to_xyxy(box.x, box.y, box.z, box.w);
+        }
+    } else {
+        float best = -INFINITY; int bi = 0x7fffffff;
+        const uint32_t line = s_out + (uint32_t)row * 128u;
+        const int wrow0 = row - lane;                              // first tile row of this warp
+        #pragma unroll 1
+        for (int cb = 0; cb < nc; cb += 32) {
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c0 = cb + h * 16;
+                if (c0 < nc) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    float f[16];
+                    #pragma unroll
+                    for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]) + s_bias[c0 + k];
+                    float4 r[4]; float cbest; int ci;
+                    cls_chunk16(f, c0, r, cbest, ci);
+                    if (c0 == 0 || cbest > best) { best = cbest; bi = ci; }   // chunks ascend: the first maximum wins (torch.max)
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t addr = line + (((uint32_t)(h * 4 + q) ^ (uint32_t)(row & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(r[q].x), "f"(r[q].y), "f"(r[q].z), "f"(r[q].w) : "memory");
+                    }
+                }
+            }
+            __syncwarp();
+            const int pieces = (nc - cb >= 32 ? 32 : nc - cb) >> 2;          // 16-byte pieces per row in this chunk
+            const int piece = lane & 7;
+            #pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3);                          // row of the warp's 32 this lane helps to store
+                const int src = __shfl_sync(0xffffffffu, arow, rr);
+                if (piece < pieces && src >= 0) {
+                    const int ra = wrow0 + rr;
+                    const uint32_t addr = s_out + (uint32_t)ra * 128u + (((uint32_t)piece ^ (uint32_t)(ra & 7)) << 4);
+                    float4 o;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(addr));
+                    *reinterpret_cast<float4*>(d.pred + (size_t)src * d.nout + 4 + cb + piece * 4) = o;
+                }
+            }
+            __syncwarp();                                                     // the rows are rewritten by the next chunk
+        }
+        if (arow >= 0 && d.cand_scores) { d.cand_scores[arow] = best; d.cand_labels[arow] = bi; }
+    }
+}
+
+// kDec: instantiation with the decode-fused epilogue (its register footprint stays out of the plain convolution kernel)
+template <bool kDec>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
                  const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
@@ -240,7 +327,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 mbar_wait_acc(tfull_bar(stage_id), acc_phase, pw0);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                if (p.out_f32) {
+                if constexpr (kDec) {
+                    epilogue_decode(p.dec, s_bias, p.c_out, t_row, e.s_out, e.row, lane, (uint32_t)(tl.x0 + e.row), (uint32_t)p.out_w);
+                } else if (p.out_f32) {
                     const int n_chunks32 = (p.block_n + 31) >> 5;
                     for (int ch = sub_id; ch < n_chunks32; ch += gps) epilogue_chunk_f32(e, t_row, tl, ch);
                 } else {
@@ -453,11 +542,41 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) { delete pl; return fail((int)e, "conv: smem attribute: %s", cudaGetErrorString(e)); }
         attr_set = true;
     }
     *out = pl;
+    return 0;
+}
+
+extern "C" int yms_conv_plan_fuse_decode(yms_conv_plan* pl, const yms_decode_fusion* f) {
+    if (!pl || !f) return fail(YMS_E_ARG, "fuse_decode: null argument");
+    const ConvKernelParams& kp = pl->kp;
+    if (pl->kind != 0 || kp.ksize != 1 || kp.act || !kp.out_f32 || kp.has_res || kp.n_tiles != 1)
+        return fail(YMS_E_UNSUPPORTED, "fuse_decode: the plan must be a linear 1x1 convolution with f32 output");
+    if (f->branch != 1 && f->branch != 2) return fail(YMS_E_ARG, "fuse_decode: branch must be 1 (box) or 2 (class)");
+    const int nc = f->num_classes;
+    if (nc <= 0 || (nc % 16) || nc > 128) return fail(YMS_E_UNSUPPORTED, "fuse_decode: num_classes must be a multiple of 16, <= 128");
+    if (kp.c_out != (f->branch == 1 ? 4 * kRegMax : nc) || kp.block_n != kp.c_out || kp.acc_stages != kEpiGroups)
+        return fail(YMS_E_ARG, "fuse_decode: c_out must be 64 (box branch) or num_classes (class branch)");
+    const long long hw = (long long)f->map_h * f->map_w;
+    if (f->map_h <= 0 || f->map_w <= 0 || (long long)kp.out_w % hw) return fail(YMS_E_ARG, "fuse_decode: map size does not divide the plan's pixels");
+    if (f->anchor_base < 0 || (long long)f->anchor_base + hw > f->anchors) return fail(YMS_E_ARG, "fuse_decode: anchor range");
+    if (!f->stride || !f->pred || ((uintptr_t)f->pred & 15)) return fail(YMS_E_ARG, "fuse_decode: stride / pred (16-byte aligned) required");
+    if (f->branch == 1 && f->cand_boxes && ((uintptr_t)f->cand_boxes & 15)) return fail(YMS_E_ARG, "fuse_decode: cand_boxes must be 16-byte aligned");
+    if (f->branch == 2 && ((f->cand_scores == nullptr) != (f->cand_labels == nullptr)))
+        return fail(YMS_E_ARG, "fuse_decode: candidate scores and labels must come together");
+    DecodeFuse& d = pl->kp.dec;
+    d.mode = f->branch; d.hw = (int)hw; d.w = f->map_w; d.anchor_base = f->anchor_base; d.anchors = f->anchors; d.nout = 4 + nc;
+    d.stride = f->stride; d.pred = f->pred;
+    d.cand_boxes = f->branch == 1 ? reinterpret_cast<float4*>(f->cand_boxes) : nullptr;
+    d.cand_scores = f->branch == 2 ? f->cand_scores : nullptr;
+    d.cand_labels = f->branch == 2 ? f->cand_labels : nullptr;
+    // algorithmic bytes: the f32 logits are no longer written; the decoded rows are
+    const double m = (double)kp.out_w;
+    pl->bytes += m * ((f->branch == 1 ? 16.0 + (f->cand_boxes ? 16.0 : 0.0) : 4.0 * nc + (f->cand_scores ? 8.0 : 0.0)) - 4.0 * kp.c_out);
     return 0;
 }
 
@@ -466,7 +585,7 @@ extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     if (pl->kind == 1) return conv3_plan_run(pl, (cudaStream_t)stream);
     ConvKernelParams kp = pl->kp;
     kp.prof = g_prof_buf;
-    cudaError_t le = launch_pdl(conv_gemm_kernel, pl->grid, kThreads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
+    cudaError_t le = launch_pdl(kp.dec.mode ? conv_gemm_kernel<true> : conv_gemm_kernel<false>, pl->grid, kThreads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
                                 pl->tm_y, pl->tm_res, kp);
     if (le != cudaSuccess) return fail((int)le, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");

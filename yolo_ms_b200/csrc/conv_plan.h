@@ -13,6 +13,17 @@ namespace yms {
 
 constexpr int kBlockK = 64;                    // bf16 channels per k-block = one 128 B swizzle row
 
+// Head decode fused into the epilogue of a head branch's final 1x1 convolution (conv_gemm.cu, yms_conv_plan_fuse_decode):
+// the accumulator row of a thread is one anchor, so DFL / sigmoid / arg-max are thread-local.
+struct DecodeFuse {
+    int mode;                                  // 0 off, 1 box branch (4 x 16 DFL logits), 2 class branch (nc logits)
+    int hw, w;                                 // anchors (pixels) and width of this scale's map
+    int anchor_base, anchors;                  // first anchor of the scale, anchors per image over all scales
+    int nout;                                  // 4 + nc floats per prediction row
+    const float* stride;                       // DEVICE f32: this scale's stride, read at run time (head.stride is honoured per call)
+    float* pred; float4* cand_boxes; float* cand_scores; int* cand_labels;
+};
+
 struct ConvKernelParams {
     int tiles_x, tiles_y, batch;               // M tiling (output space)
     int tw, th;                                // output pixels per tile (tw*th <= 128)
@@ -29,6 +40,7 @@ struct ConvKernelParams {
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
     const float* bias;
     float* y_f32; long long y_ps;
+    DecodeFuse dec;                            // dec.mode != 0: the epilogue writes predictions / candidates instead of y
     long long* prof;                           // YMS_PROF builds: [grid][16] cycle counters (else unused)
 };
 

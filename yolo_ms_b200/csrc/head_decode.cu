@@ -9,7 +9,7 @@
 // HBM-bound: per anchor it reads (64+nc) logits and writes 4+nc floats.  A CTA stages a tile of
 // 32 anchors x (64+nc) logits in shared memory with 16-byte coalesced loads, computes from
 // shared memory, stages the [32, 4+nc] output tile and streams it out with 16-byte stores.
-#include "common.cuh"
+#include "decode_math.cuh"
 
 #include <stdlib.h>
 
@@ -18,7 +18,6 @@ namespace {
 
 constexpr int kTileAnchors = 32;
 constexpr int kDecodeThreads = 256;
-constexpr int kRegMax = 16;
 
 struct DecodeArgs {
     const void* raw[3];
@@ -31,14 +30,7 @@ struct DecodeArgs {
     float* pred; float4* cand_boxes; float* cand_scores; int32_t* cand_labels;
 };
 
-// ex2/rcp approximations: |error| < 3e-6 on the score (stated tolerance of the decode tests: 5e-6)
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-
-// xyxy exactly as tools/test.py:172-177 (w/2 is exact, so w*0.5f == w/2)
-__device__ __forceinline__ float4 to_xyxy(float cx, float cy, float w, float h) {
-    float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-}
+// sigmoid_f, to_xyxy, dfl_expectation, dfl_box, cls_chunk16: decode_math.cuh (shared with the fused conv epilogue)
 
 template <typename T> struct RawLoad;
 template <> struct RawLoad<float> { static constexpr int kVec = 4; };           // elements per 16 B
@@ -206,27 +198,15 @@ __global__ void __launch_bounds__(kTileAnchors * kMaxGroupsV2) head_decode_v2_ke
         float v[16];
         load16<T>(src + (size_t)tid * 16, v);                                    // chunk tid of the contiguous tile
         if (g < 4) {                                                             // DFL side g: sum_k k * softmax_k
-            float mx = v[0];
-            #pragma unroll
-            for (int k = 1; k < kRegMax; ++k) mx = fmaxf(mx, v[k]);
-            float sum = 0.f, wsum = 0.f;
-            #pragma unroll
-            for (int k = 0; k < kRegMax; ++k) { const float e = __expf(v[k] - mx); sum += e; wsum = fmaf((float)k, e, wsum); }
-            s_dist[an * 4 + g] = wsum / sum;
+            s_dist[an * 4 + g] = dfl_expectation(v);
         } else {                                                                 // 16 class scores
             const int c0 = (g - 4) * 16;
-            float best = -INFINITY; int bi = 0x7fffffff;
+            float best; int bi;
+            float4 r[4];
+            cls_chunk16(v, c0, r, best, bi);                                     // first max wins (torch.max)
             float4* o4 = reinterpret_cast<float4*>(s_out + an * nout + 4 + c0);
             #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 r;
-                r.x = sigmoid_f(v[4 * q]); r.y = sigmoid_f(v[4 * q + 1]); r.z = sigmoid_f(v[4 * q + 2]); r.w = sigmoid_f(v[4 * q + 3]);
-                o4[q] = r;
-                const float rr[4] = {r.x, r.y, r.z, r.w};
-                #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (rr[j] > best || bi == 0x7fffffff) { best = rr[j]; bi = c0 + 4 * q + j; }    // first max wins (torch.max)
-            }
+            for (int q = 0; q < 4; ++q) o4[q] = r[q];
             s_best[an * ncg + (g - 4)] = best;
             s_bidx[an * ncg + (g - 4)] = bi;
         }
@@ -239,12 +219,7 @@ __global__ void __launch_bounds__(kTileAnchors * kMaxGroupsV2) head_decode_v2_ke
         const float ax = (float)(gidx % a.w[sc]) + 0.5f, ay = (float)(gidx / a.w[sc]) + 0.5f;
         const float st = a.stride[sc];
         const float4 d = *reinterpret_cast<const float4*>(s_dist + tid * 4);
-        const float x1 = ax - d.x, y1 = ay - d.y, x2 = ax + d.z, y2 = ay + d.w;
-        float4 box;
-        box.x = ((x1 + x2) / 2.0f) * st;
-        box.y = ((y1 + y2) / 2.0f) * st;
-        box.z = (x2 - x1) * st;
-        box.w = (y2 - y1) * st;
+        const float4 box = dfl_box(ax, ay, d, st);
         *reinterpret_cast<float4*>(s_out + tid * nout) = box;
         if (a.cand_boxes) {
             float best = s_best[tid * ncg]; int bi = s_bidx[tid * ncg];

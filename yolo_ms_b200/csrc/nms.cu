@@ -10,7 +10,9 @@
 // Work decomposition: classes are independent, so every image is handled by G CTAs (host picks
 // G ~ 148 / batch), CTA g owning the contiguous class range [g*nc/G, (g+1)*nc/G).  Per CTA:
 //   A  compact the candidates of its classes into 64-bit keys [label:11 | ~score:32 | index:20]
-//   B  bitonic sort of the keys in shared memory (size = next pow2 of ITS candidate count)
+//   A  ... scattered straight into their class segment (the class histogram gives the offsets: counting sort on the label)
+//   B  per-segment sort by (score desc, index) in shared memory: one warp per small class, the CTA for big ones
+//      (YMS_NMS_SORT=bitonic / key sets beyond shared memory: one bitonic sort of all keys, size = next pow2 of the count)
 //   C  class segment table
 //   D  greedy suppression.  Fast path (<= 8192 candidates: keys AND boxes in shared memory):
 //      segments are cut into chunks of 32 sorted boxes, chunks are dealt round-robin to the 32
@@ -42,6 +44,7 @@ constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kSortTile = 16384;           // u64 keys that fit the 128 KB key region
 constexpr int kFastCap = 8192;             // fast path: 64 KB keys + 128 KB boxes
 constexpr int kMaxClasses = 2047;
+constexpr int kWarpSortMax = 256;          // class segments up to this many keys are sorted by one warp, larger ones by the CTA
 constexpr int kMaxGroups = 16;
 constexpr unsigned long long kInvalidKey = ~0ull;
 constexpr unsigned long long kIdxMask = (1ull << 20) - 1;
@@ -99,6 +102,40 @@ __device__ void bitonic_tile_steps(unsigned long long* s, int tile, int gbase, i
             if ((a > b) == up) { s[i] = b; s[l] = a; }
         }
         __syncthreads();
+    }
+}
+
+// Ascending sort of one class segment s[0, len) in shared memory by `nthreads` cooperating threads (a warp, or the whole CTA
+// when kBlock).  Normalised bitonic network: every merge starts with a MIRROR step (i <-> k-1-i inside a k block) followed
+// by half-cleaners, so every compare-exchange puts the minimum at the LOWER index; positions >= len then behave as +inf
+// without being stored, and a segment of any length is sorted in place (no power-of-two padding region).
+template <bool kBlock>
+__device__ __forceinline__ void segment_sort(unsigned long long* s, int len, int t0, int nthreads) {
+    if (len < 2) return;                                   // uniform over the cooperating threads
+    int P = 2;
+    while (P < len) P <<= 1;
+    const int half_pairs = P >> 1;
+    for (int k = 2, lg = 0; k <= P; k <<= 1, ++lg) {        // lg = log2(k / 2)
+        for (int t = t0; t < half_pairs; t += nthreads) {
+            const int blk = t >> lg, off = t & ((k >> 1) - 1);
+            const int i = blk * k + off, l = blk * k + (k - 1 - off);
+            if (l < len) {
+                const unsigned long long x = s[i], y = s[l];
+                if (x > y) { s[i] = y; s[l] = x; }
+            }
+        }
+        if (kBlock) __syncthreads(); else __syncwarp();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int t = t0; t < half_pairs; t += nthreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                if (l < len) {
+                    const unsigned long long x = s[i], y = s[l];
+                    if (x > y) { s[i] = y; s[l] = x; }
+                }
+            }
+            if (kBlock) __syncthreads(); else __syncwarp();
+        }
     }
 }
 
@@ -301,6 +338,7 @@ struct NmsArgs {
     int n_pad_full;                // pow2(n)
     long long* prof;               // -DYMS_PROF builds: [grid][16] phase time stamps
     int mask_tile_limit;           // bitmask path only when the largest class of the CTA has at most this many 32-box blocks
+    int seg_sort;                  // 1 (default): counting scatter by class + per-segment sorts; 0 (YMS_NMS_SORT=bitonic): one bitonic sort of all keys
     int dbg;                       // YMS_NMS_DBG switches: 1 = broadcast/4-way apply of kept boxes (default), 2 = mask-based chunk
                                    // resolve (measured slower: the phase is issue-bound and it executes more instructions)
 };
@@ -387,6 +425,32 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     __syncthreads();
 
     NMS_STAMP(1);
+    // ---- A1 (segment sort): the histogram already gives every class segment's place, so the keys are scattered straight into
+    // their segment (counting sort on the label; any order inside a segment) and phase B only sorts WITHIN segments ----------
+    const bool seg_sort = in_smem && a.seg_sort;
+    if (seg_sort) {
+        if (warp == 0) {
+            int running = 0;
+            for (int base = 0; base <= ncl; base += 32) {
+                const int c = base + lane;
+                const int v = (c < ncl) ? hist[c_lo + c] : 0;
+                int incl = v;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                if (c <= ncl) cls_start[c] = running + incl - v;
+                if (c < ncl) cls_count[c] = running + incl - v;               // scatter cursor of the class
+                running += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nb; i += kNmsThreads) {
+            const float s = scores[i]; const int lab = labels[i];
+            if (s > a.conf && lab >= c_lo && lab < c_hi) {
+                const int pos = atomicAdd(&cls_count[lab - c_lo], 1);
+                keys[pos] = ((unsigned long long)(lab - c_lo) << 52) | ((unsigned long long)desc_score_bits(s) << 20) | (unsigned long long)i;
+            }
+        }
+    } else
     // ---- A1: compacted keys (any order: the keys are unique and get sorted) ----------------------
     for (int i0 = 0; i0 < nb; i0 += kNmsThreads) {
         const int i = i0 + tid;
@@ -409,7 +473,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
 
     NMS_STAMP(2);
     // ---- B: sort -----------------------------------------------------------------------
-    if (in_smem) {
+    if (seg_sort) {
+        // segments of more than kWarpSortMax keys: the whole CTA, one after the other; the rest: one warp per segment, all
+        // in parallel and without block-wide barriers (bench workload: 54 -> ~15 kcycles for ~2100 keys in ~20 classes)
+        for (int c = 0; c < ncl; ++c) {
+            const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
+            if (len > kWarpSortMax) segment_sort<true>(skeys + s0, len, tid, kNmsThreads);
+        }
+        for (int c = warp; c < ncl; c += kNmsWarps) {
+            const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
+            if (len <= kWarpSortMax) segment_sort<false>(skeys + s0, len, lane, 32);
+        }
+        __syncthreads();
+    } else if (in_smem) {
         for (int k = 2; k <= n_pad; k <<= 1) bitonic_tile_steps(skeys, n_pad, 0, k, k >> 1);
     } else {
         const int tile = kSortTile, ntiles = n_pad / tile;
@@ -782,6 +858,7 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.prof = g_prof_buf;
     { static const int dbg = [] { const char* e = getenv("YMS_NMS_DBG"); return e ? atoi(e) : 1; }(); a.dbg = dbg; }
     { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 8; }(); a.mask_tile_limit = lim; }
+    { static const int seg = [] { const char* e = getenv("YMS_NMS_SORT"); return (e && e[0] == 'b') ? 0 : 1; }(); a.seg_sort = seg; }
     if (groups > 1) {
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
         if (e != cudaSuccess) return fail((int)e, "nms: ticket memset failed");

@@ -57,6 +57,8 @@ class Program:
         self.tuned: list = []          # (layer, chosen variant) of the autotuned 3x3 layers
         self.flops = 0.0
         self.bytes = 0.0
+        self.raw_tail: List[ops.ConvPlan] = []   # decode-fused programs: the plans that store the raw head logits instead
+        self.decoded: Optional[dict] = None      # decode-fused programs: static pred / candidate buffers + the stride tensor
 
     # ---- buffers -------------------------------------------------------------------------
     def buf(self, b: int, h: int, w: int, c: int, dtype=torch.bfloat16) -> torch.Tensor:
@@ -68,8 +70,15 @@ class Program:
         self._keep.extend(ts)
 
     # ---- ops -------------------------------------------------------------------------------
-    def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None):
+    def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None, decode=None, scheduled=True):
+        """decode: kwargs of ConvPlan.fuse_decode (the head's final convs of the fused forward+decode program).
+        scheduled=False: the plan is built and kept but is not part of the program (returned to the caller)."""
         plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
+        if decode is not None:
+            plan.fuse_decode(**decode)
+        if not scheduled:
+            self.hold(weight_packed, bias)
+            return plan
         if (AUTOTUNE and ksize == 3 and stride == 2 and x2 is None and residual is None and y.dtype == torch.bfloat16
                 and x.shape[-1] == 32 and x.stride(-2) == 32 and y.shape[-1] <= 256):
             plan = self._autotune_s2pair(plan, weight_packed, dict(x=x, bias=bias, y=y, act=act))

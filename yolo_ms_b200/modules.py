@@ -18,6 +18,7 @@ no CPU path and no autograd: a CPU input raises ``YmsError``.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -26,6 +27,8 @@ from torch import nn
 from . import ops
 from ._lib import YmsError
 from .engine import Program, fold_conv_bn, nchw_f32_to_nhwc_bf16, nhwc_to_nchw_f32, pack_weight
+
+FUSE_DECODE = os.environ.get("YMS_FUSE_DECODE", "1") != "0"    # decode in the epilogue of the head's final convs (YOLOv8 programs)
 
 _VERSIONS = {  # depth, width, ratio  (components.py:193-209)
     "n": (1 / 3, 1 / 4, 2.0), "s": (1 / 3, 1 / 2, 2.0), "m": (2 / 3, 3 / 4, 1.5),
@@ -409,11 +412,31 @@ class Head(_Compiled):
         self.cls = nn.ModuleList([branch(c, num_classes) for c in chans])
         self.dfl = DFL()                                  # the reference ignores `ch` here too (:113)
 
-    def emit(self, P, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        """-> 3 fp32 raw tensors [B,H,W,64+nc] (box | cls), yolov8_head.py:119-122."""
+    def can_fuse_decode(self) -> bool:
+        """The decode-fused epilogue handles class counts that are a multiple of 16 up to 128 (include/yms_b200.h)."""
+        return FUSE_DECODE and self.ch == 16 and self.num_classes % 16 == 0 and 0 < self.num_classes <= 128
+
+    def emit(self, P, feats: Sequence[torch.Tensor], fuse_decode: bool = False) -> List[torch.Tensor]:
+        """-> 3 fp32 raw tensors [B,H,W,64+nc] (box | cls), yolov8_head.py:119-122.
+
+        fuse_decode: the program's final 1x1 convs decode in their epilogue (pred [B,A,4+nc] + candidates, `P.decoded`)
+        instead of storing the logits; the logit-storing plans are kept in `P.raw_tail` and only run when the raw
+        tensors are asked for (training-mode output, forward_raw)."""
         if self.ch != 16:
             raise RuntimeError("DFL is fixed to 16 bins (the reference builds DFL() with its default ch)")
         raws = []
+        if fuse_decode:
+            b = feats[0].shape[0]
+            anchors = sum(f.shape[1] * f.shape[2] for f in feats)
+            dev = feats[0].device
+            dec = {"pred": torch.empty((b, anchors, 4 + self.num_classes), dtype=torch.float32, device=dev),
+                   "boxes": torch.empty((b, anchors, 4), dtype=torch.float32, device=dev),
+                   "scores": torch.empty((b, anchors), dtype=torch.float32, device=dev),
+                   "labels": torch.empty((b, anchors), dtype=torch.int32, device=dev),
+                   "stride": torch.zeros(4, dtype=torch.float32, device=dev), "stride_vals": None}
+            P.hold(*[v for v in dec.values() if torch.is_tensor(v)])
+            P.decoded = dec
+            base = 0
         P.fork(len(feats))                                   # the scales are independent: parallel graph branches
         for i, f in enumerate(feats):
             P.branch(i)
@@ -430,7 +453,16 @@ class Head(_Compiled):
                 last = seq[2]
                 wl = pack_weight(last.weight.detach().float())
                 bl = last.bias.detach().float().contiguous()
-                P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False)
+                if fuse_decode:
+                    kind = "box" if lo == 0 else "cls"
+                    cand = {"cand_boxes": dec["boxes"]} if lo == 0 else {"cand_scores": dec["scores"], "cand_labels": dec["labels"]}
+                    P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False,
+                           decode=dict(branch=kind, stride=dec["stride"][i:i + 1], pred=dec["pred"], anchor_base=base, **cand))
+                    P.raw_tail.append(P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False, scheduled=False))
+                else:
+                    P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False)
+            if fuse_decode:
+                base += h * w
             raws.append(raw)
         P.join()
         return raws
@@ -471,28 +503,50 @@ class YOLOv8(_Compiled):
         ps = self.backbone.emit(P, img, outs=outs)
         feats = self.neck.emit(P)
         self.__dict__["_taps"] = {"p": ps, "n": feats}      # NHWC bf16 views, for the parity tests
-        return tuple(self.head.emit(P, feats))
+        return tuple(self.head.emit(P, feats, fuse_decode=self.head.can_fuse_decode()))
+
+    def _run(self, x):
+        """Replay the program on x.  Decode-fused programs leave pred / candidates in `prog.decoded`; the stride values
+        live in device memory and follow head.stride (a plain attribute in the reference) from call to call."""
+        prog, io = _get_program(self, (x,), self._build, image_input=True)
+        io["inputs"][0].bind(x)
+        dec = prog.decoded
+        if dec is not None:
+            vals = self.head._stride_list()
+            if dec["stride_vals"] != vals:
+                if len(vals) != 3:
+                    raise YmsError("head.stride must hold 3 values")
+                dec["stride"][:3].copy_(torch.tensor(vals, dtype=torch.float32))
+                dec["stride_vals"] = list(vals)
+        prog.run()
+        return prog, io
 
     def forward_raw(self, x):
         """Run the network; returns the program's static fp32 raw head buffers [B,H,W,64+nc]."""
-        prog, io = _get_program(self, (x,), self._build, image_input=True)
-        io["inputs"][0].bind(x)
-        prog.run()
+        prog, io = self._run(x)
+        for plan in prog.raw_tail:        # decode-fused program: the logits are only stored on request
+            plan.run()
         return io["outputs"]
 
     def forward(self, x):
-        raws = self.forward_raw(x)
         if self.head.training:
-            return [r.permute(0, 3, 1, 2).clone() for r in raws]
-        return self.head.decode(raws)
+            return [r.permute(0, 3, 1, 2).clone() for r in self.forward_raw(x)]
+        prog, io = self._run(x)
+        if prog.decoded is not None:
+            return prog.decoded["pred"].clone()            # the program's buffer is overwritten by the next call
+        return self.head.decode(io["outputs"])
 
     @torch.no_grad()
     def detect(self, x, conf_thresh: float = 0.25, iou_thresh: float = 0.45):
         """Fused forward + decode + class-aware NMS (the reference's tools/test.py:160-218 per
-        batch).  Returns (boxes [B,A,4], scores [B,A], labels [B,A], keep [B,A], count [B])."""
-        raws = self.forward_raw(x)
-        pred, (boxes, scores, labels) = ops.head_decode(raws, self.head._stride_list(), self.head.num_classes,
-                                                        with_candidates=True)
+        batch).  Returns (boxes [B,A,4], scores [B,A], labels [B,A], keep [B,A], count [B]); boxes / scores / labels
+        are the program's static candidate buffers (valid until the next call on this model with the same shape)."""
+        prog, io = self._run(x)
+        if prog.decoded is not None:
+            boxes, scores, labels = prog.decoded["boxes"], prog.decoded["scores"], prog.decoded["labels"]
+        else:
+            _, (boxes, scores, labels) = ops.head_decode(io["outputs"], self.head._stride_list(), self.head.num_classes,
+                                                         with_candidates=True)
         keep, count = ops.nms_batched(boxes, scores, labels, conf_thresh, iou_thresh, self.head.num_classes)
         return boxes, scores, labels, keep, count
 

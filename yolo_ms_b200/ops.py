@@ -15,7 +15,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvParams, YmsError, check
+from ._lib import ConvParams, DecodeFusion, YmsError, check
 
 __all__ = ["ConvPlan", "stem_conv", "stem_conv_u8", "dwconv", "sppf_pool", "upsample2x", "head_decode",
            "select_candidates", "nms_batched", "gather_detections", "YmsError"]
@@ -82,6 +82,36 @@ class ConvPlan:
         self.flops, self.bytes = fl.value, by.value
         self.desc = (f"conv{ksize}x{ksize}/s{stride} {c_in}{'+' + str(c_in2) if c_in2 else ''}->{c_out} @{h}x{w}"
                      f"{' +res' if residual is not None else ''}{' f32' if y.dtype == torch.float32 else ''}")
+
+    def fuse_decode(self, branch: str, stride: torch.Tensor, pred: torch.Tensor, anchor_base: int,
+                    cand_boxes: Optional[torch.Tensor] = None, cand_scores: Optional[torch.Tensor] = None,
+                    cand_labels: Optional[torch.Tensor] = None) -> None:
+        """Turn the plan of a head branch's final biased 1x1 conv (f32 output, act=False) into one that decodes in its
+        epilogue instead of storing logits (yms_conv_plan_fuse_decode).  branch: 'box' | 'cls'; stride: DEVICE f32 [1]
+        view read at run time; pred f32 [B, A, 4+nc]; candidates f32 [B,A,4] / f32 [B,A] / i32 [B,A]."""
+        _need_cuda(stride, pred, cand_boxes, cand_scores, cand_labels)
+        if pred.dtype != torch.float32 or not pred.is_contiguous() or pred.dim() != 3 or stride.dtype != torch.float32:
+            raise YmsError("fuse_decode: pred must be contiguous f32 [B,A,4+nc] and stride f32")
+        for t, dt in ((cand_boxes, torch.float32), (cand_scores, torch.float32), (cand_labels, torch.int32)):
+            if t is not None and (t.dtype != dt or not t.is_contiguous()):
+                raise YmsError("fuse_decode: candidate buffers must be contiguous f32 / f32 / int32")
+        x = self._keep[0]
+        f = DecodeFusion()
+        f.branch = {"box": 1, "cls": 2}[branch]
+        f.map_h, f.map_w = x.shape[1], x.shape[2]
+        f.anchor_base, f.anchors, f.num_classes = int(anchor_base), pred.shape[1], pred.shape[2] - 4
+        f.stride, f.pred = stride.data_ptr(), pred.data_ptr()
+        f.cand_boxes = None if cand_boxes is None else cand_boxes.data_ptr()
+        f.cand_scores = None if cand_scores is None else cand_scores.data_ptr()
+        f.cand_labels = None if cand_labels is None else cand_labels.data_ptr()
+        if pred.shape[0] != x.shape[0]:
+            raise YmsError("fuse_decode: batch mismatch")
+        check(self._lib.yms_conv_plan_fuse_decode(self._h, C.byref(f)), "yms_conv_plan_fuse_decode")
+        self._keep = self._keep + (stride, pred, cand_boxes, cand_scores, cand_labels)
+        fl, by = C.c_double(), C.c_double()
+        self._lib.yms_conv_plan_cost(self._h, C.byref(fl), C.byref(by))
+        self.flops, self.bytes = fl.value, by.value
+        self.desc = self.desc.replace(" f32", "") + f" +decode({branch})"
 
     def run(self) -> None:
         check(self._lib.yms_conv_plan_run(self._h, _stream()), "yms_conv_plan_run")
