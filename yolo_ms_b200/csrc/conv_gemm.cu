@@ -36,7 +36,7 @@ constexpr int kMaxStages = 8;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;      // 16 KB
 using namespace tc;
 constexpr int kThreads = kConvThreads;
-constexpr int kTmemCols = 512;
+constexpr int kSmemLimitHalf = 115712;         // 113 KB: two CTAs (+ 1 KB reserved each) fill the SM's 228 KB
 constexpr int kSmemLimit = 232448;             // 227 KB
 
 struct TileCoord { int n_tile, img, x0, y0; };
@@ -147,7 +147,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     extern __shared__ unsigned char smem_dyn[];
     long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;   // wait-cycle accumulators (dead code unless -DYMS_PROF)
     (void)pw0; (void)pw1; (void)pw2; (void)pw3;
-    YMS_PROF_ONLY(const long long prof_t_entry = clock64(); long long* prof = p.prof ? p.prof + 16 * blockIdx.x : nullptr;)
+    YMS_PROF_ONLY(const long long prof_t_entry = clock64(); long long* prof = (p.prof && blockIdx.x < kNumSMs) ? p.prof + 16 * blockIdx.x : nullptr;)
     // carve-up (1024-byte aligned for SWIZZLE_128B)
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
@@ -161,7 +161,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t smem_bres = base + p.num_stages * stage_bytes;     // resident weight tiles
     const uint32_t smem_out0 = base + ring_bytes;                     // 2 x 16 KB staging
     unsigned char* g_out0 = gbase + ring_bytes;
-    float* s_bias = reinterpret_cast<float*>(g_out0 + kEpiGroups * kStageOutBytes);
+    float* s_bias = reinterpret_cast<float*>(g_out0 + p.epi_groups * kStageOutBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -184,7 +184,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         if (lane < 2 * kMaxStages + 13) {
             const bool is_tempty = lane >= 2 * kMaxStages + 4 && lane < 2 * kMaxStages + 8;
-            mbar_init(bar0 + 8u * lane, is_tempty ? 4 * (kEpiGroups / p.acc_stages) : 1);
+            mbar_init(bar0 + 8u * lane, is_tempty ? 4 * (p.epi_groups / p.acc_stages) : 1);
         }
         fence_barrier_init();
         __syncwarp();
@@ -200,8 +200,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         __syncwarp();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    for (int i = threadIdx.x; i < p.bias_pad; i += kThreads) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.bias_pad; i += blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -214,7 +214,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int num_kb = p.taps * kb_per_tap;
     const int pad = p.ksize >> 1;
     const uint32_t a_bytes = (uint32_t)(p.tw * p.th) * 128u;
-    const int acc_stride = kTmemCols / p.acc_stages;
+    const int acc_stride = p.tmem_cols / p.acc_stages;
     const uint32_t stage_tx = a_bytes + (p.resident ? 0u : (uint32_t)b_tile_bytes);
 
     if (warp == 0) {
@@ -305,7 +305,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     } else {
         // ================= epilogue: up to 4 groups of 4 warps, group e drains accumulator stage e =================
         const int grp = (warp - 2) >> 2;
-        const int gps = kEpiGroups / p.acc_stages;         // groups sharing one accumulator stage
+        const int gps = p.epi_groups / p.acc_stages;       // groups sharing one accumulator stage
         const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
         {
             EpiShared e;
@@ -348,7 +348,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
     YMS_PROF_ONLY(if (prof && threadIdx.x == 0) prof[12] = clock64() - prof_t_entry;)
 }
@@ -493,19 +493,31 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     kp.y_ps = q->y_pixel_stride;
 
     const int b_bytes = (kp.block_n * 128 + 1023) & ~1023;
-    const int fixed = kEpiGroups * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 16) * 8 + 1024 /* alignment slack */;
-    kp.acc_stages = kp.block_n <= 128 ? 4 : 2;
-    kp.mg_n_tiles = fast_div_magic(kp.n_tiles); kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
     const int res_bytes = kp.taps * (kp.kb1 + kp.kb2) * b_bytes;
+    // "half" CTAs (YMS_CONV_HALF=1, experimental): 2 epilogue groups, 2 x 128 TMEM columns, <= 113 KB -> two CTAs per SM.  Only for
+    // N <= 128 (two accumulator stages must remain) and when at least 3 ring stages fit beside resident / streamed weights.
+    static const bool want_half = [] { const char* e = getenv("YMS_CONV_HALF"); return e && e[0] == '1'; }();
+    int groups = kEpiGroups, limit = kSmemLimit;
+    if (want_half && kp.block_n <= 128) {
+        const int fixed_h = 2 * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 16) * 8 + 1024;
+        const bool res_h = kp.n_tiles == 1 && kSmemLimitHalf - fixed_h - res_bytes >= 3 * kATileBytes;
+        if (res_h || (kSmemLimitHalf - fixed_h) / (kATileBytes + b_bytes) >= 3) { groups = 2; limit = kSmemLimitHalf; }
+    }
+    kp.epi_groups = groups; kp.tmem_cols = 128 * groups;
+    const int fixed = groups * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 16) * 8 + 1024 /* alignment slack */;
+    kp.acc_stages = groups == 2 ? 2 : (kp.block_n <= 128 ? 4 : 2);
+    kp.mg_n_tiles = fast_div_magic(kp.n_tiles); kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
     // small weight sets stay resident for the whole persistent CTA (no per-tile re-fetch from L2)
-    kp.resident = (kp.n_tiles == 1 && !getenv("YMS_CONV_STREAM") && kSmemLimit - fixed - res_bytes >= 4 * kATileBytes) ? 1 : 0;
+    kp.resident = (kp.n_tiles == 1 && !getenv("YMS_CONV_STREAM") && limit - fixed - res_bytes >= (groups == 2 ? 3 : 4) * kATileBytes) ? 1 : 0;
     const int stage_bytes = kATileBytes + (kp.resident ? 0 : b_bytes);
-    int stages = (kSmemLimit - fixed - (kp.resident ? res_bytes : 0)) / stage_bytes;
+    int stages = (limit - fixed - (kp.resident ? res_bytes : 0)) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) { delete pl; return fail(YMS_E_UNSUPPORTED, "conv: tile does not fit in shared memory"); }
     kp.num_stages = stages;
     pl->smem = (size_t)stages * stage_bytes + (kp.resident ? res_bytes : 0) + fixed;
-    pl->grid = kp.total_tiles < kNumSMs ? kp.total_tiles : kNumSMs;
+    const int max_ctas = kNumSMs * (groups == 2 ? 2 : 1);
+    pl->grid = kp.total_tiles < max_ctas ? kp.total_tiles : max_ctas;
+    pl->threads = 64 + groups * kEpiGroupThreads;
 
     int rc;
     const int K_total = q->c_in + q->c_in2;
@@ -559,7 +571,7 @@ extern "C" int yms_conv_plan_fuse_decode(yms_conv_plan* pl, const yms_decode_fus
     if (f->branch != 1 && f->branch != 2) return fail(YMS_E_ARG, "fuse_decode: branch must be 1 (box) or 2 (class)");
     const int nc = f->num_classes;
     if (nc <= 0 || (nc % 16) || nc > 128) return fail(YMS_E_UNSUPPORTED, "fuse_decode: num_classes must be a multiple of 16, <= 128");
-    if (kp.c_out != (f->branch == 1 ? 4 * kRegMax : nc) || kp.block_n != kp.c_out || kp.acc_stages != kEpiGroups)
+    if (kp.c_out != (f->branch == 1 ? 4 * kRegMax : nc) || kp.block_n != kp.c_out || kp.acc_stages != kp.epi_groups)
         return fail(YMS_E_ARG, "fuse_decode: c_out must be 64 (box branch) or num_classes (class branch)");
     const long long hw = (long long)f->map_h * f->map_w;
     if (f->map_h <= 0 || f->map_w <= 0 || (long long)kp.out_w % hw) return fail(YMS_E_ARG, "fuse_decode: map size does not divide the plan's pixels");
@@ -585,7 +597,7 @@ extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     if (pl->kind == 1) return conv3_plan_run(pl, (cudaStream_t)stream);
     ConvKernelParams kp = pl->kp;
     kp.prof = g_prof_buf;
-    cudaError_t le = launch_pdl(kp.dec.mode ? conv_gemm_kernel<true> : conv_gemm_kernel<false>, pl->grid, kThreads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
+    cudaError_t le = launch_pdl(kp.dec.mode ? conv_gemm_kernel<true> : conv_gemm_kernel<false>, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
                                 pl->tm_y, pl->tm_res, kp);
     if (le != cudaSuccess) return fail((int)le, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");

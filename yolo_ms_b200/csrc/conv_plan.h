@@ -36,6 +36,10 @@ struct ConvKernelParams {
     int resident;                              // all weight tiles of the (single) N tile stay in smem
     int s2_dense;                              // stride-2 input is a dense NHWC tensor: 5-D parity view, no traversal stride
     int acc_stages;                            // TMEM accumulator stages == active epilogue groups (1, 2 or 4)
+    int epi_groups;                            // epilogue groups of 4 warps: 4 (one 576-thread CTA per SM) or 2 ("half" CTAs: 320
+                                               // threads, <= 113 KB of shared memory, 256 TMEM columns, so that TWO CTAs -- of this
+                                               // layer or of the next one, whose prologue then overlaps this layer's tail -- share an SM)
+    int tmem_cols;                             // 128 * epi_groups
     uint32_t mg_n_tiles, mg_tiles_x, mg_tiles_y;  // fast_div magics
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
     const float* bias;
@@ -105,7 +109,7 @@ struct yms_conv_plan {
     int kind;                   // 0: generic implicit GEMM, 1: 3x3 stride-1 halo kernel
     yms::ConvKernelParams kp;
     yms::Conv3Params k3;
-    int grid;
+    int grid, threads;
     size_t smem;
     double flops, bytes;
 };
