@@ -6,8 +6,8 @@
 
 Workload (BASELINE.json configs[1]): YOLO-MS-S (`version='s'`, 80 classes), 640x640, batch 32 per
 GPU, bf16 storage / fp32 accumulate, synthetic ImageNet-normalised images, seeded random weights
-with calibrated BN statistics.  One "step" = one batch through YOLOv8.detect(): stem + 64 conv /
-glue launches (CUDA graph) + head decode + batched NMS.  N > 1: one process per GPU (torchrun),
+with calibrated BN statistics.  One "step" = one batch through YOLOv8.detect(): stem + the conv /
+glue launches of the program (one CUDA graph; the head decode runs in the epilogue of its last six convs) + batched NMS.  N > 1: one process per GPU (torchrun),
 the batch is sharded by image, no collective on the data path ("scaling": "weak").
 
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.

@@ -105,6 +105,15 @@ typedef struct yms_decode_fusion {
 } yms_decode_fusion;
 int yms_conv_plan_fuse_decode(yms_conv_plan* plan, const yms_decode_fusion* f);
 
+/* Nearest-x2 upsample + channel concat fused into the 1x1 convolution that consumes them (Upsample.forward components.py:159-160,
+ * torch.cat in Neck.forward yolov8_neck.py:77-83, C2f.conv1 components.py:108).  A 1x1 convolution is linear per pixel, so
+ *     conv1x1(cat[upsample2x(a), b]) = upsample2x(W_a . a) + W_b . b          (before bias / activation)
+ * The host runs the first term at HALF resolution as a linear 1x1 plan with f32 output and zero bias (4x fewer MACs, the upsampled
+ * tensor never exists); this call makes `plan` (the 1x1 convolution over b alone, bf16 output, at H x W = out_h x out_w) add
+ * t[n, y/2, x/2, :] to its accumulator before bias and activation.  t: DEVICE f32 [B, out_h/2, out_w/2, c_out] (pixel stride in
+ * floats).  Differs from the unfused computation only in fp32 summation order.  c_out must be a multiple of 16. */
+int yms_conv_plan_add_upsampled(yms_conv_plan* plan, const float* t, int64_t t_pixel_stride, int out_h, int out_w);
+
 /* Stem: first layer backbone.conv0 (yolov8/model/yolov8_backbone.py:39, 3x3 stride 2 on the
  * NCHW fp32 image, components.py:69-77) -> NHWC bf16.  weight f32 [c_out][3][3][3] with BN
  * folded, bias f32 [c_out]. */

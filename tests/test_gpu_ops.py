@@ -83,6 +83,36 @@ def test_conv_gemm_matches_torch_fp32(ops, case, variant):
         assert bool((yfull[..., :8] == 7).all() and (yfull[..., 8 + cout:] == 7).all())
 
 
+@pytest.mark.parametrize("B,H,W,c_low,c_skip,cout", [(2, 40, 40, 512, 256, 256), (3, 20, 28, 256, 128, 128), (1, 80, 80, 64, 32, 32),
+                                                     (2, 10, 6, 576, 384, 384)])
+def test_conv1x1_over_upsampled_concat(ops, B, H, W, c_low, c_skip, cout):
+    """Neck: conv1x1(cat[upsample2x(a), b]) computed as upsample2x(W_a . a) + W_b . b (yms_conv_plan_add_upsampled): a linear fp32
+    1x1 plan at half resolution, then the plan over b adds it before bias + SiLU.  Reference: plain PyTorch fp32 on the same
+    bf16-rounded operands (F.interpolate nearest, cat, conv2d); tolerance = bf16 output rounding, rel-L2 <= 4e-3.  Map sizes whose
+    128-pixel tiles straddle rows and images are included; y is a channel slice of a wider buffer."""
+    g = torch.Generator().manual_seed(c_low + H)
+    a = torch.randn(B, H // 2, W // 2, c_low, generator=g).to(DEV).to(torch.bfloat16)
+    cat = torch.randn(B, H, W, c_low + c_skip, generator=g).to(DEV).to(torch.bfloat16)       # first slot deliberately garbage
+    b = cat[..., c_low:]
+    ktot = c_low + c_skip
+    wt = (torch.randn(cout, ktot, generator=g) / ktot ** 0.5).to(DEV).to(torch.bfloat16)
+    bias = (torch.randn(cout, generator=g) * 0.5).to(DEV)
+    part = torch.empty(B, H // 2, W // 2, cout, device=DEV, dtype=torch.float32)
+    yfull = torch.full((B, H, W, cout + 16), 7.0, device=DEV, dtype=torch.bfloat16)
+    y = yfull[..., 8:8 + cout]
+    ops.ConvPlan(a, wt[:, :c_low].contiguous().view(1, cout, c_low), torch.zeros_like(bias), part, ksize=1, act=False).run()
+    main = ops.ConvPlan(b, wt[:, c_low:].contiguous().view(1, cout, c_skip), bias, y, ksize=1, act=True)
+    main.add_upsampled(part)
+    main.run()
+    up = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    xin = torch.cat([up, b.float().permute(0, 3, 1, 2)], 1)
+    want = F.silu(F.conv2d(xin, wt.float().view(cout, ktot, 1, 1), bias)).permute(0, 2, 3, 1)
+    assert rel_l2(y.float(), want) <= 4e-3
+    assert float(yfull[..., :8].float().min()) == 7.0 and float(yfull[..., 8 + cout:].float().max()) == 7.0
+    with pytest.raises(ops.YmsError):
+        main.add_upsampled(part[:, :, :-1])
+
+
 @pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 64), (1, 40, 24, 48), (1, 320, 320, 64), (2, 36, 52, 128)])
 def test_conv_s2_pair_line_kernel(ops, B, H, W, cout):
     """variant 4: 3x3/s2 with 32 dense input channels on pair-packed weights vs plain PyTorch fp32 conv (and vs the

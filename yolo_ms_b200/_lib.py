@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("YMS_LIB") or os.path.join(_HERE, "libyms_b200.so")   
 
 EXPORTS = [
     "yms_abi_version", "yms_last_error", "yms_launch_count",
-    "yms_conv_plan_create", "yms_conv_plan_run", "yms_conv_plan_destroy", "yms_conv_plan_cost", "yms_conv_plan_fuse_decode",
+    "yms_conv_plan_create", "yms_conv_plan_run", "yms_conv_plan_destroy", "yms_conv_plan_cost", "yms_conv_plan_fuse_decode", "yms_conv_plan_add_upsampled",
     "yms_stem_conv", "yms_stem_conv_u8", "yms_resample_u8", "yms_dwconv", "yms_sppf_pool", "yms_upsample2x",
     "yms_head_decode", "yms_select_candidates",
     "yms_nms_workspace_bytes", "yms_nms_batched", "yms_gather_detections",
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     lib.yms_conv_plan_destroy.argtypes = [vp]
     lib.yms_conv_plan_cost.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
     lib.yms_conv_plan_fuse_decode.argtypes = [vp, C.POINTER(DecodeFusion)]
+    lib.yms_conv_plan_add_upsampled.argtypes = [vp, vp, i64, i32, i32]
     lib.yms_stem_conv.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i64, vp]
     lib.yms_stem_conv_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp, C.POINTER(f32), C.POINTER(f32), vp, i64, vp]
     lib.yms_resample_u8.argtypes = [vp, i32, i32, i32, i64, vp, i32, i32, i64, vp, vp, i32, i32, vp]

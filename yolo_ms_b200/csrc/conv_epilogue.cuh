@@ -32,9 +32,19 @@ struct EpiShared {
 
 // bf16 output of ONE 64-channel chunk through swizzled staging + TMA store (+ residual TMA-loaded
 // into the same buffer).  Callers deal (sub-tile, chunk) units to the groups that share a stage.
-__device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t& res_phase, uint32_t t_row, const EpiTile& tl, int ch) {
+// kUp: `up_row` points at this thread's pixel of an fp32 [.., c_out] tensor of PARTIAL SUMS that is added to the accumulator before
+// bias / activation (the low-resolution half of a 1x1 convolution over cat[upsample2x(a), b], see yms_conv_plan_add_upsampled).
+template <bool kUp = false>
+__device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t& res_phase, uint32_t t_row, const EpiTile& tl, int ch,
+                                                    const float* up_row = nullptr) {
     {
         const int cbase = ch * 64;
+        float4 u[4], un[4];                                  // kUp: partial sums of this / the next 16-channel group (software pipeline:
+        if (kUp) {                                           // the L2 latency of a group's loads hides behind the previous group's work)
+            const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + cbase);
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = __ldg(uq + j);
+        }
         if (e.leader) tma_store_wait_read<0>();            // previous store of this group has left the staging buffer
         group_bar_sync(e.bar_id);
         if (e.has_res) {
@@ -51,8 +61,23 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
             const int c0 = cbase + q16 * 16;
             if (c0 >= e.block_n) break;
             uint32_t v[16];
+            if (kUp && q16 < 3 && c0 + 16 < e.block_n) {
+                const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + c0 + 16);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) un[j] = __ldg(uq + j);
+            }
             tmem_ld16(t_row + (uint32_t)c0, v);
             tmem_ld_wait();
+            if (kUp) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + u[j].x);
+                    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + u[j].y);
+                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + u[j].z);
+                    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + u[j].w);
+                    u[j] = un[j];
+                }
+            }
             float f[16];
             const float4* bq = reinterpret_cast<const float4*>(e.s_bias + tl.n0 + c0);
             if (e.act) {

@@ -332,6 +332,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 } else if (p.out_f32) {
                     const int n_chunks32 = (p.block_n + 31) >> 5;
                     for (int ch = sub_id; ch < n_chunks32; ch += gps) epilogue_chunk_f32(e, t_row, tl, ch);
+                } else if (p.up) {
+                    // this thread's pixel of the half-resolution partial sums (nearest upsample: (y, x) reads (y/2, x/2))
+                    uint32_t m = (uint32_t)(tl.x0 + e.row);
+                    if (m >= (uint32_t)p.out_w) m = (uint32_t)p.out_w - 1u;             // rows past the last pixel are clipped by the store
+                    const uint32_t img = m / (uint32_t)p.up_hw, rem = m - img * (uint32_t)p.up_hw;
+                    const uint32_t y = rem / (uint32_t)p.up_w, x = rem - y * (uint32_t)p.up_w;
+                    const float* up_row = p.up + ((size_t)img * (size_t)(p.up_hw >> 2) + (size_t)(y >> 1) * (size_t)(p.up_w >> 1) + (x >> 1)) * (size_t)p.up_ps;
+                    for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16<true>(e, res_phase, t_row, tl, ch, up_row);
                 } else {
                     for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
                 }
@@ -589,6 +597,20 @@ extern "C" int yms_conv_plan_fuse_decode(yms_conv_plan* pl, const yms_decode_fus
     // algorithmic bytes: the f32 logits are no longer written; the decoded rows are
     const double m = (double)kp.out_w;
     pl->bytes += m * ((f->branch == 1 ? 16.0 + (f->cand_boxes ? 16.0 : 0.0) : 4.0 * nc + (f->cand_scores ? 8.0 : 0.0)) - 4.0 * kp.c_out);
+    return 0;
+}
+
+extern "C" int yms_conv_plan_add_upsampled(yms_conv_plan* pl, const float* t, int64_t t_pixel_stride, int out_h, int out_w) {
+    if (!pl || !t) return fail(YMS_E_ARG, "add_upsampled: null argument");
+    ConvKernelParams& kp = pl->kp;
+    if (pl->kind != 0 || kp.ksize != 1 || kp.out_f32 || kp.dec.mode)
+        return fail(YMS_E_UNSUPPORTED, "add_upsampled: the plan must be a 1x1 convolution with bf16 output");
+    if (out_h <= 0 || out_w <= 0 || ((out_h | out_w) & 1) || (long long)kp.out_w % ((long long)out_h * out_w))
+        return fail(YMS_E_ARG, "add_upsampled: even H, W that divide the plan's pixels are required");
+    if ((kp.c_out % 16) || t_pixel_stride < kp.c_out || (t_pixel_stride % 4) || ((uintptr_t)t & 15))
+        return fail(YMS_E_ARG, "add_upsampled: c_out %% 16, pixel stride %% 4 >= c_out and a 16-byte aligned tensor are required");
+    kp.up = t; kp.up_ps = t_pixel_stride; kp.up_w = out_w; kp.up_hw = out_h * out_w;
+    pl->bytes += 4.0 * (double)(kp.out_w / 4) * kp.c_out;                          // the partial sums are read once
     return 0;
 }
 

@@ -44,6 +44,8 @@ struct ConvKernelParams {
     int bias_pad;                              // floats of shared-memory bias (c_out rounded up to 64)
     const float* bias;
     float* y_f32; long long y_ps;
+    const float* up; long long up_ps;          // fp32 partial sums at HALF resolution added before bias / activation (or null),
+    int up_w, up_hw;                           //   pixel stride in floats; W and H*W of THIS conv's (full-resolution) map
     DecodeFuse dec;                            // dec.mode != 0: the epilogue writes predictions / candidates instead of y
     long long* prof;                           // YMS_PROF builds: [grid][16] cycle counters (else unused)
 };

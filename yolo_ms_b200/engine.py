@@ -70,12 +70,15 @@ class Program:
         self._keep.extend(ts)
 
     # ---- ops -------------------------------------------------------------------------------
-    def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None, decode=None, scheduled=True):
+    def conv(self, weight_packed, bias, x, y, ksize, stride=1, act=True, residual=None, x2=None, decode=None, scheduled=True,
+             up_add=None):
         """decode: kwargs of ConvPlan.fuse_decode (the head's final convs of the fused forward+decode program).
         scheduled=False: the plan is built and kept but is not part of the program (returned to the caller)."""
         plan = ops.ConvPlan(x, weight_packed, bias, y, ksize=ksize, stride=stride, act=act, residual=residual, x2=x2)
         if decode is not None:
             plan.fuse_decode(**decode)
+        if up_add is not None:           # fp32 partial sums at half resolution (ConvPlan.add_upsampled)
+            plan.add_upsampled(up_add)
         if not scheduled:
             self.hold(weight_packed, bias)
             return plan

@@ -30,6 +30,8 @@ from .engine import Program, fold_conv_bn, nchw_f32_to_nhwc_bf16, nhwc_to_nchw_f
 
 FUSE_DECODE = os.environ.get("YMS_FUSE_DECODE", "1") != "0"    # decode in the epilogue of the head's final convs (YOLOv8 programs)
 
+FUSE_UPSAMPLE = os.environ.get("YMS_FUSE_UPSAMPLE", "1") != "0"  # neck: upsample + concat inside the consumer C2f's first 1x1 conv
+
 _VERSIONS = {  # depth, width, ratio  (components.py:193-209)
     "n": (1 / 3, 1 / 4, 2.0), "s": (1 / 3, 1 / 2, 2.0), "m": (2 / 3, 3 / 4, 1.5),
     "l": (1.0, 1.0, 1.0), "x": (1.0, 1.25, 1.0),
@@ -153,11 +155,24 @@ class C2f(_Compiled):
         self.m = nn.ModuleList([Bottleneck(self.mid_channels, self.mid_channels) for _ in range(num_bottlenecks)])
         self.conv2 = Conv((num_bottlenecks + 2) * out_channels // 2, out_channels, kernel_size=1, stride=1, padding=0)
 
-    def emit(self, P, x, out=None):
+    def emit(self, P, x, out=None, up_src=None):
+        """up_src (neck only): x is the concat buffer [upsample2x(up_src) | skip] whose FIRST slot has NOT been written; conv1
+        (1x1, linear per pixel) is then split as  upsample2x(W_a . up_src) + W_b . skip : the first term runs at half resolution
+        as a linear fp32 1x1 conv, the second adds it in its epilogue (yms_conv_plan_add_upsampled) -- no upsample kernel, no
+        upsampled tensor, 4x fewer MACs for that half (components.py:159-160 + yolov8_neck.py:77-83 + components.py:108)."""
         n, h = self.num_bottlenecks, self.mid_channels
         b, hh, ww, _ = x.shape
         cat = P.buf(b, hh, ww, (n + 2) * h)
-        self.conv1.emit(P, x, out=cat[..., n * h:(n + 2) * h])
+        if up_src is not None:
+            c_low = up_src.shape[-1]
+            wf, bf = self.conv1.folded()
+            co = wf.shape[0]
+            part = P.buf(b, hh // 2, ww // 2, co, dtype=torch.float32)
+            P.conv(pack_weight(wf[:, :c_low].contiguous()), torch.zeros_like(bf), up_src, part, ksize=1, stride=1, act=False)
+            P.conv(pack_weight(wf[:, c_low:].contiguous()), bf.contiguous(), x[..., c_low:], cat[..., n * h:(n + 2) * h], ksize=1, stride=1,
+                   act=self.conv1.has_act, up_add=part)
+        else:
+            self.conv1.emit(P, x, out=cat[..., n * h:(n + 2) * h])
         cur = cat[..., n * h:(n + 1) * h]
         for j, blk in enumerate(self.m):
             dst = cat[..., (n - 1 - j) * h:(n - j) * h]
@@ -372,10 +387,18 @@ class Neck(_Compiled):
     def emit(self, P):
         c3, c4, c5 = self.channels
         cat1, cat2, cat3, cat4 = self.__dict__.pop("_cats")
-        self.up.emit(P, cat4[..., c4:], cat1[..., :c5])
-        res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:])
-        self.up.emit(P, res2, cat2[..., :c4])
-        out1 = self.c2f_2.emit(P, cat2)
+        # C2f consumers take the upsample + concat inside their first 1x1 conv (C2f.emit, up_src); other blocks read the
+        # concat buffer that upsample2x_kernel fills
+        if FUSE_UPSAMPLE and isinstance(self.c2f_1, C2f) and c4 % 16 == 0:
+            res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:], up_src=cat4[..., c4:])
+        else:
+            self.up.emit(P, cat4[..., c4:], cat1[..., :c5])
+            res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:])
+        if FUSE_UPSAMPLE and isinstance(self.c2f_2, C2f) and c3 % 16 == 0:
+            out1 = self.c2f_2.emit(P, cat2, up_src=res2)
+        else:
+            self.up.emit(P, res2, cat2[..., :c4])
+            out1 = self.c2f_2.emit(P, cat2)
         self.conv1.emit(P, out1, out=cat3[..., :c3])
         out2 = self.c2f_3.emit(P, cat3)
         self.conv2.emit(P, out2, out=cat4[..., :c4])

@@ -113,6 +113,21 @@ class ConvPlan:
         self.flops, self.bytes = fl.value, by.value
         self.desc = self.desc.replace(" f32", "") + f" +decode({branch})"
 
+    def add_upsampled(self, t: torch.Tensor) -> None:
+        """Add nearest-upsampled fp32 partial sums t [B, H/2, W/2, c_out] to the accumulator before bias / activation
+        (yms_conv_plan_add_upsampled: the upsample + concat half of a 1x1 conv over cat[upsample2x(a), b])."""
+        _need_cuda(t)
+        x, y = self._keep[0], self._keep[3]
+        b, h, w, _ = x.shape
+        if t.dtype != torch.float32 or tuple(t.shape) != (b, h // 2, w // 2, y.shape[-1]):
+            raise YmsError(f"add_upsampled: t must be f32 [{b},{h // 2},{w // 2},{y.shape[-1]}], got {tuple(t.shape)} {t.dtype}")
+        check(self._lib.yms_conv_plan_add_upsampled(self._h, t.data_ptr(), _pixel_stride(t), h, w), "yms_conv_plan_add_upsampled")
+        self._keep = self._keep + (t,)
+        fl, by = C.c_double(), C.c_double()
+        self._lib.yms_conv_plan_cost(self._h, C.byref(fl), C.byref(by))
+        self.flops, self.bytes = fl.value, by.value
+        self.desc += " +up(f32)"
+
     def run(self) -> None:
         check(self._lib.yms_conv_plan_run(self._h, _stream()), "yms_conv_plan_run")
 
