@@ -34,7 +34,7 @@ want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM rd"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"), ("launch__registers_per_thread", "regs"),
         ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("smsp__inst_executed.sum", "warp insts")]
-for part in ("gemm", "conv3", "post", "dw"):
+for part in ("gemm", "conv3", "post", "dec", "dw"):
     f = os.path.join(src, f"prof_{part}_{tag}_raw.csv")
     if not os.path.exists(f): continue
     rows = list(csv.reader(open(f)))

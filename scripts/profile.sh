@@ -22,6 +22,8 @@ prof() {  # name regex skip count
 prof gemm conv_gemm_kernel 0 6           # c2f_2.conv1 (1x1 64->64 @160), c2f_2.conv2, conv3 (3x3/s2), c2f_4.conv1, c2f_4.conv2, conv5
 prof conv3 conv3x3_kernel 0 5            # conv1 (pair-line s2), the two 160x160 bottleneck convs, first two 80x80
 prof post 'nms_kernel|head_decode|stem_t' 0 3
+prof dec conv_gemm_kernel 26 9           # the LAST conv_gemm launches of the step: the six decode-fused final head convs (75 registers)
+                                         # + the head's 20x20 3x3 layers the autotuner gave to the generic kernel
 du -sh $OUT; ls $OUT | grep $TAG
 # 3. MS-Block variant: the depthwise kernels (launch list + --set full of four of them)
 CMDMS="python bench.py --block ms --profile-step --warmup 3"
