@@ -113,6 +113,43 @@ def test_conv1x1_over_upsampled_concat(ops, B, H, W, c_low, c_skip, cout):
         main.add_upsampled(part[:, :, :-1])
 
 
+def test_fuse_decode_and_add_upsampled_reject_unsupported_plans(ops):
+    """yms_conv_plan_fuse_decode only takes the linear f32-output 1x1 conv that ends a head branch (c_out 64 for the box branch,
+    num_classes -- a multiple of 16, <= 128 -- for the class branch); yms_conv_plan_add_upsampled only bf16-output 1x1 convs with
+    c_out % 16 == 0 on even maps.  Everything else is an error, never a silent fallback."""
+    B, H, W = 1, 8, 12
+    x = torch.zeros(B, H, W, 64, device=DEV, dtype=torch.bfloat16)
+    w1 = torch.zeros(1, 64, 64, device=DEV, dtype=torch.bfloat16)
+    bias = torch.zeros(64, device=DEV)
+    pred = torch.zeros(B, H * W, 4 + 80, device=DEV)
+    stride = torch.ones(1, device=DEV)
+    boxes = torch.zeros(B, H * W, 4, device=DEV)
+    yf = torch.zeros(B, H, W, 64, device=DEV)
+    yb = torch.zeros(B, H, W, 64, device=DEV, dtype=torch.bfloat16)
+    ok = ops.ConvPlan(x, w1, bias, yf, ksize=1, act=False)
+    ok.fuse_decode("box", stride, pred, 0, cand_boxes=boxes)                           # the supported case
+    ok.run()
+    torch.cuda.synchronize()
+    assert float(pred[..., 2:4].min()) == 15.0 and float(pred[..., 2:4].max()) == 15.0 and float(pred[0, 13, 0]) == (1 + 0.5) and float(pred[0, 13, 1]) == (1 + 0.5)   # zero logits: l=t=r=b=7.5
+    for plan, args in [
+        (ops.ConvPlan(x, w1, bias, yb, ksize=1, act=False), ("box", stride, pred, 0)),                       # bf16 output
+        (ops.ConvPlan(x, w1, bias, yf, ksize=1, act=True), ("box", stride, pred, 0)),                        # activation
+        (ops.ConvPlan(x, torch.zeros(9, 64, 64, device=DEV, dtype=torch.bfloat16), bias, yf, ksize=3, act=False), ("box", stride, pred, 0)),
+        (ops.ConvPlan(x, w1, bias, yf, ksize=1, act=False), ("cls", stride, pred, 0)),                       # c_out 64 != 80 classes
+        (ops.ConvPlan(x, w1, bias, yf, ksize=1, act=False), ("box", stride, torch.zeros(B, H * W, 4 + 24, device=DEV), 0)),   # 24 classes
+        (ops.ConvPlan(x, w1, bias, yf, ksize=1, act=False), ("box", stride, pred, 8)),                       # anchor range overflow
+    ]:
+        with pytest.raises(ops.YmsError):
+            plan.fuse_decode(*args)
+    part = torch.zeros(B, H // 2, W // 2, 64, device=DEV)
+    with pytest.raises(ops.YmsError):
+        ops.ConvPlan(x, w1, bias, yf, ksize=1, act=False).add_upsampled(part)                                # f32 output
+    with pytest.raises(ops.YmsError):
+        ops.ConvPlan(x, torch.zeros(9, 64, 64, device=DEV, dtype=torch.bfloat16), bias, yb, ksize=3).add_upsampled(part)
+    with pytest.raises(ops.YmsError):
+        ops.ConvPlan(x, w1, bias, yb, ksize=1).add_upsampled(part.to(torch.bfloat16))
+
+
 @pytest.mark.parametrize("B,H,W,cout", [(2, 64, 96, 64), (1, 40, 24, 48), (1, 320, 320, 64), (2, 36, 52, 128)])
 def test_conv_s2_pair_line_kernel(ops, B, H, W, cout):
     """variant 4: 3x3/s2 with 32 dense input channels on pair-packed weights vs plain PyTorch fp32 conv (and vs the
