@@ -41,7 +41,6 @@ using namespace tc;
 
 constexpr int kThreads3 = kConvThreads;
 constexpr int kHaloPitch = 10;                         // lines (pixels) per halo row
-constexpr int kHaloStageBytes = 23552;                 // 180 lines = 23040 B, rounded up to 1024 (max; plans use p.halo_stage)
 constexpr int kRing = 8;                               // max ring depth (barrier array size)
 constexpr int kSmemLimit3 = 232448;
 
@@ -49,13 +48,6 @@ constexpr int kSmemLimit3 = 232448;
 constexpr int kBarAFull = 0, kBarAEmpty = kRing, kBarBFull = 2 * kRing, kBarBEmpty = 3 * kRing;
 constexpr int kBarTFull = 4 * kRing, kBarTEmpty = 4 * kRing + 4, kBarRes = 4 * kRing + 8, kBarW = 4 * kRing + 12;
 constexpr int kNumBars = 4 * kRing + 14;
-
-__device__ __forceinline__ uint64_t make_a_desc(uint32_t addr, int desc_mode) {
-    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) |
-                 (1ull << 46) | (2ull << 61);
-    if (desc_mode == 1) d |= (uint64_t)((addr >> 7) & 7u) << 49;
-    return d;
-}
 
 struct Item { int n_tile, img, sx, ty; };
 __device__ __forceinline__ Item decode_item(const Conv3Params& p, int t) {

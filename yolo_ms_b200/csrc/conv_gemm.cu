@@ -145,8 +145,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                  const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ ConvKernelParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;   // wait-cycle accumulators (dead code unless -DYMS_PROF)
-    (void)pw0; (void)pw1; (void)pw2; (void)pw3;
+    long long pw0 = 0, pw1 = 0, pw2 = 0;            // wait-cycle accumulators (dead code unless -DYMS_PROF)
+    (void)pw0; (void)pw1; (void)pw2;
     YMS_PROF_ONLY(const long long prof_t_entry = clock64(); long long* prof = (p.prof && blockIdx.x < kNumSMs) ? p.prof + 16 * blockIdx.x : nullptr;)
     // carve-up (1024-byte aligned for SWIZZLE_128B)
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;

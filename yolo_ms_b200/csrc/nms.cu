@@ -189,7 +189,6 @@ __device__ __forceinline__ unsigned resolve_chunk(const float4& bj, float aj, bo
 //            sweep over the diagonal tile decides which rows survive, the words of the survivors against later
 //            columns are OR-reduced (__reduce_or_sync) into `removed` (lane w holds word w, so W <= 32).
 // Same pair predicate and same order as the reference => bit-identical keep lists.
-__device__ __forceinline__ int tile_row_offset(int W, int k) { return k * W - ((k * (k - 1)) >> 1); }   // tiles before row k
 
 // Pair predicate for FINITE boxes (the bitmask path is only taken when every box of the CTA is finite): fmaxf/fminf
 // equal std::max/std::min on finite values up to the sign of zero (which cannot make `inter > 0` true), every
