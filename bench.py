@@ -288,6 +288,8 @@ def run_native(args):
         copy_s.synchronize()
         d2h_s.synchronize()
 
+    model.detect(u8in[0].copy_(u8_host), CONF, IOU)        # build the uint8-input program (it reuses the autotuner's decisions) on a quiet device,
+    torch.cuda.synchronize()                               # not inside the pipelined loop
     e2e_u8_loop(max(args.warmup, 3))
     barrier()
     t0 = time.perf_counter()
