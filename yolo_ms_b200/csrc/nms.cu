@@ -337,6 +337,7 @@ struct NmsArgs {
     int n_pad_full;                // pow2(n)
     long long* prof;               // -DYMS_PROF builds: [grid][16] phase time stamps
     int mask_tile_limit;           // bitmask path only when the largest class of the CTA has at most this many 32-box blocks
+    int poll_ns;                   // back-off unit of the pipelined greedy path's progress polling (YMS_NMS_POLL, default 256 ns per chunk ahead)
     int seg_sort;                  // 1 (default): counting scatter by class + per-segment sorts; 0 (YMS_NMS_SORT=bitonic): one bitonic sort of all keys
     int dbg;                       // YMS_NMS_DBG switches: 1 = broadcast/4-way apply of kept boxes (default), 2 = mask-based chunk
                                    // resolve (measured slower: the phase is issue-bound and it executes more instructions)
@@ -666,8 +667,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                     if (a.dbg & 1) removed = apply_kept_smem<kFinite>(sbox + s0, applied, kept, bj, aj, removed, a.thr_f);
                     else removed = apply_kept([&](int q) { return sbox[s0 + q]; }, applied, kept, bj, aj, removed, a.thr_f, lane);
                     applied = kept;
-                    if ((int)(st >> 16) == j) break;           // every earlier chunk of this class is final
-                    if (applied == kept) __nanosleep(32);
+                    const int ahead = j - (int)(st >> 16);     // chunks of this class that are not final yet
+                    if (ahead == 0) break;                     // every earlier chunk of this class is final
+                    // Back-off by distance: only the chunk whose predecessor is being resolved polls fast.  With a flat 32 ns
+                    // sleep the up to 31 waiting warps of the CTA (7 per scheduler, ~18 instructions + a fence per poll)
+                    // saturated the issue ports and starved the one warp per class that is on the critical chain.
+                    __nanosleep(ahead <= 1 ? 32u : (unsigned)min(a.poll_ns * ahead, 4096));
                 }
                 const unsigned surv = (a.dbg & 2) ? resolve_chunk_smem<kFinite>(sbox + s0 + 32 * j, min(32, s1 - s0 - 32 * j), bj, aj, removed, a.thr_f, lane)
                                                   : resolve_chunk(bj, aj, removed, a.thr_f, lane);
@@ -857,6 +862,7 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.prof = g_prof_buf;
     { static const int dbg = [] { const char* e = getenv("YMS_NMS_DBG"); return e ? atoi(e) : 1; }(); a.dbg = dbg; }
     { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 8; }(); a.mask_tile_limit = lim; }
+    { static const int poll = [] { const char* e = getenv("YMS_NMS_POLL"); return e ? atoi(e) : 256; }(); a.poll_ns = poll < 16 ? 16 : poll; }
     { static const int seg = [] { const char* e = getenv("YMS_NMS_SORT"); return (e && e[0] == 'b') ? 0 : 1; }(); a.seg_sort = seg; }
     if (groups > 1) {
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
