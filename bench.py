@@ -22,6 +22,11 @@ import sys
 import threading
 import time
 
+# The e2e leg drives three streams (upload, compute, read-back) next to a CUDA graph with parallel branches.  With the default
+# 8 hardware work queues, unrelated streams can share a queue and serialise behind each other (false dependencies): the compute
+# stream's GPU time per step then varies from run to run (1.7 - 3.7 ms observed).  Must be set before CUDA is initialised.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -271,7 +276,9 @@ def run_native(args):
     u8_host = torch.randint(0, 256, (B, HW, HW, 3), generator=g8, dtype=torch.uint8).pin_memory()
     u8in = [torch.empty((B, HW, HW, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
 
-    def e2e_u8_loop(n):
+    step_evs = []                                          # (start, end) events of every step's compute: where the time goes when
+                                                           # e2e falls behind `value` (GPU busy vs. waiting for the host / copies)
+    def e2e_u8_loop(n, record=False):
         for i in range(n):
             b = i & 1
             with torch.cuda.stream(copy_s):
@@ -280,9 +287,15 @@ def run_native(args):
                 ev_copied[b].record(copy_s)
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(ev_copied[b])
+                if record:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(comp_s)
                 boxes, scores, labels, keep, count = model.detect(u8in[b], CONF, IOU)
                 dets = ops.gather_detections(boxes, scores, labels, keep, count, MAXD)
                 ev_done[b].record(comp_s)
+                if record:
+                    e1.record(comp_s)
+                    step_evs.append((e0, e1))
             read_back(dets, count, b)
         comp_s.synchronize()
         copy_s.synchronize()
@@ -291,13 +304,21 @@ def run_native(args):
     model.detect(u8in[0].copy_(u8_host), CONF, IOU)        # build the uint8-input program (it reuses the autotuner's decisions) on a quiet device,
     torch.cuda.synchronize()                               # not inside the pipelined loop
     e2e_u8_loop(max(args.warmup, 3))
+    sampler_e = ClockSampler(local)
+    if rank == 0:
+        sampler_e.start()
+        time.sleep(0.2)
     barrier()
+    tw0 = time.time()
     t0 = time.perf_counter()
-    e2e_u8_loop(args.steps)
+    e2e_u8_loop(args.steps, record=True)
     barrier()
     u8_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
+    e2e_clocks = sampler_e.stop(tw0, time.time()) if rank == 0 else None
+    gpu_busy_ms = sum(a.elapsed_time(b) for a, b in step_evs) / max(len(step_evs), 1)
     e2e = {"value": round(world * B / (u8_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(u8_host.numel()),
            "d2h_bytes_per_step": int(B * MAXD * 6 * 4 + B * 4), "ms_per_step": round(u8_ms, 3),
+           "compute_ms_per_step": round(gpu_busy_ms, 3), "clocks": e2e_clocks,
            "pipelined": "H2D of step i+1 and the read-back of step i-1 overlap compute of step i (3 streams, 2 buffers)",
            "input": "uint8 RGB HWC host images [B,640,640,3] (what tools/test.py holds after decode + resize); ToTensor+Normalize run "
                     "inside the stem kernel; public call: YOLOv8.detect(uint8 batch) + gather_detections"}
