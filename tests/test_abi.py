@@ -35,6 +35,37 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.yms_nms_batched(None, None, None, None, 1, 10, 5000, 0.25, 0.45, None, None, None, 0, None) == -2
 
 
+def test_plan_modifiers_report_argument_errors_without_a_gpu():
+    """yms_conv_plan_fuse_decode / yms_conv_plan_add_upsampled validate their arguments before touching the device."""
+    import ctypes as C
+    from yolo_ms_b200 import _lib
+    lib = _lib.load()
+    f = _lib.DecodeFusion()
+    assert lib.yms_conv_plan_fuse_decode(None, C.byref(f)) == -1 and b"null" in lib.yms_last_error()
+    assert lib.yms_conv_plan_add_upsampled(None, None, 64, 8, 8) == -1
+
+
+def test_host_side_fusion_switches():
+    """Which programs decode in the conv epilogue is host logic: class counts that are a multiple of 16 up to 128 (the fused
+    epilogue's limits, include/yms_b200.h); everything else keeps the stand-alone decode kernel.  The autotuner's cache key
+    separates layers that differ only in buffer strides (a channel slice of a concat buffer vs a dense tensor)."""
+    from yolo_ms_b200 import engine
+    from yolo_ms_b200.model.yolov8_head import Head
+    assert Head(version="n", num_classes=80).can_fuse_decode()
+    assert Head(version="n", num_classes=16).can_fuse_decode()
+    assert not Head(version="n", num_classes=24).can_fuse_decode()
+    assert not Head(version="n", num_classes=144).can_fuse_decode()
+    assert not Head(version="n", num_classes=80, ch=8).can_fuse_decode()
+    dense = torch.empty(2, 8, 8, 32)
+    sliced = torch.empty(2, 8, 8, 64)[..., :32]
+    y = torch.empty(2, 8, 8, 32)
+    k1 = engine._tune_key("3x3", dense, y, 3, 1, True, None)
+    assert k1 == engine._tune_key("3x3", torch.empty(2, 8, 8, 32), torch.empty(2, 8, 8, 32), 3, 1, True, None)
+    assert k1 != engine._tune_key("3x3", sliced, y, 3, 1, True, None)
+    assert k1 != engine._tune_key("3x3", dense, y, 3, 1, True, y)
+    assert k1 != engine._tune_key("s2pair", dense, y, 3, 1, True, None)
+
+
 def test_cpu_tensors_raise_not_fall_back():
     from yolo_ms_b200 import YmsError, ops, postprocess
     from yolo_ms_b200.yolov8 import YOLOv8
