@@ -111,7 +111,8 @@ int yms_conv_plan_fuse_decode(yms_conv_plan* plan, const yms_decode_fusion* f);
  * The host runs the first term at HALF resolution as a linear 1x1 plan with f32 output and zero bias (4x fewer MACs, the upsampled
  * tensor never exists); this call makes `plan` (the 1x1 convolution over b alone, bf16 output, at H x W = out_h x out_w) add
  * t[n, y/2, x/2, :] to its accumulator before bias and activation.  t: DEVICE f32 [B, out_h/2, out_w/2, c_out] (pixel stride in
- * floats).  Differs from the unfused computation only in fp32 summation order.  c_out must be a multiple of 16. */
+ * floats).  Differs from the unfused computation only in fp32 summation order.  c_out must be a multiple of 16 (of 64 beyond 256
+ * channels, where the kernel tiles N); YMS_E_UNSUPPORTED otherwise (run yms_upsample2x + the plain convolution then). */
 int yms_conv_plan_add_upsampled(yms_conv_plan* plan, const float* t, int64_t t_pixel_stride, int out_h, int out_w);
 
 /* Stem: first layer backbone.conv0 (yolov8/model/yolov8_backbone.py:39, 3x3 stride 2 on the

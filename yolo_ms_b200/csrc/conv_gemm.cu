@@ -607,8 +607,10 @@ extern "C" int yms_conv_plan_add_upsampled(yms_conv_plan* pl, const float* t, in
         return fail(YMS_E_UNSUPPORTED, "add_upsampled: the plan must be a 1x1 convolution with bf16 output");
     if (out_h <= 0 || out_w <= 0 || ((out_h | out_w) & 1) || (long long)kp.out_w % ((long long)out_h * out_w))
         return fail(YMS_E_ARG, "add_upsampled: even H, W that divide the plan's pixels are required");
-    if ((kp.c_out % 16) || t_pixel_stride < kp.c_out || (t_pixel_stride % 4) || ((uintptr_t)t & 15))
-        return fail(YMS_E_ARG, "add_upsampled: c_out %% 16, pixel stride %% 4 >= c_out and a 16-byte aligned tensor are required");
+    if ((kp.c_out % 16) || kp.n_tiles * kp.block_n != kp.c_out)      // every accumulator column must be a real channel of t
+        return fail(YMS_E_UNSUPPORTED, "add_upsampled: c_out must be a multiple of 16 (of 64 beyond 256 channels)");
+    if (t_pixel_stride < kp.c_out || (t_pixel_stride % 4) || ((uintptr_t)t & 15))
+        return fail(YMS_E_ARG, "add_upsampled: pixel stride %% 4 >= c_out and a 16-byte aligned tensor are required");
     kp.up = t; kp.up_ps = t_pixel_stride; kp.up_w = out_w; kp.up_hw = out_h * out_w;
     pl->bytes += 4.0 * (double)(kp.out_w / 4) * kp.c_out;                          // the partial sums are read once
     return 0;

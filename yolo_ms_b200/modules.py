@@ -389,12 +389,14 @@ class Neck(_Compiled):
         cat1, cat2, cat3, cat4 = self.__dict__.pop("_cats")
         # C2f consumers take the upsample + concat inside their first 1x1 conv (C2f.emit, up_src); other blocks read the
         # concat buffer that upsample2x_kernel fills
-        if FUSE_UPSAMPLE and isinstance(self.c2f_1, C2f) and c4 % 16 == 0:
+        def foldable(block, c_out):       # limits of yms_conv_plan_add_upsampled
+            return FUSE_UPSAMPLE and isinstance(block, C2f) and c_out % (16 if c_out <= 256 else 64) == 0
+        if foldable(self.c2f_1, c4):
             res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:], up_src=cat4[..., c4:])
         else:
             self.up.emit(P, cat4[..., c4:], cat1[..., :c5])
             res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:])
-        if FUSE_UPSAMPLE and isinstance(self.c2f_2, C2f) and c3 % 16 == 0:
+        if foldable(self.c2f_2, c3):
             out1 = self.c2f_2.emit(P, cat2, up_src=res2)
         else:
             self.up.emit(P, res2, cat2[..., :c4])
