@@ -113,6 +113,23 @@ def test_conv1x1_over_upsampled_concat(ops, B, H, W, c_low, c_skip, cout):
         main.add_upsampled(part[:, :, :-1])
 
 
+def test_half_cta_mode_in_a_subprocess():
+    """YMS_CONV_HALF=1 (opt-in): conv_gemm_kernel with 2 epilogue groups / 320 threads / 256 TMEM columns /
+    <= 113 KB so that two CTAs share an SM.  The switch is read once per process, so the generic-kernel parity cases and the
+    decode-fused program are re-run in a child interpreter with the variable set."""
+    import subprocess
+    import sys
+    env = dict(os.environ, YMS_CONV_HALF="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_gpu_ops.py"), os.path.join(here, "test_gpu_model.py"),
+                        "-k", "(test_conv_gemm_matches_torch_fp32 and (1x1 or s2)) or test_conv1x1_over_upsampled_concat or "
+                              "test_fused_decode_is_bit_identical"],
+                       env=env, cwd=os.path.dirname(here), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_fuse_decode_and_add_upsampled_reject_unsupported_plans(ops):
     """yms_conv_plan_fuse_decode only takes the linear f32-output 1x1 conv that ends a head branch (c_out 64 for the box branch,
     num_classes -- a multiple of 16, <= 128 -- for the class branch); yms_conv_plan_add_upsampled only bf16-output 1x1 convs with
