@@ -59,3 +59,47 @@ def test_normalised_bitonic_network_sorts_any_length_in_place():
         want = sorted(keys)
         _segment_sort(keys)
         assert keys == want, n
+
+
+def _warp_sort_regs(s, e):
+    """Index logic of scripts/ubench/seg_sort.cu::warp_sort_regs<E> (32 lanes x E keys in registers; element = lane * E + r;
+    strides >= E cross lanes by shuffle; the lower index keeps the minimum; positions >= len hold +inf)."""
+    inf = (1 << 64) - 1
+    n = len(s)
+    v = [[(s[l * e + r] if l * e + r < n else inf) for r in range(e)] for l in range(32)]
+    k = 2
+    while k <= 32 * e:
+        if k <= e:
+            for l in range(32):
+                for r in range(e):
+                    q = r ^ (k - 1)
+                    if q > r and v[l][r] > v[l][q]:
+                        v[l][r], v[l][q] = v[l][q], v[l][r]
+        else:
+            mm = k // e - 1
+            o = [[v[l ^ mm][e - 1 - r] for r in range(e)] for l in range(32)]
+            for l in range(32):
+                lower = (l & ((mm + 1) >> 1)) == 0
+                for r in range(e):
+                    v[l][r] = min(v[l][r], o[l][r]) if lower else max(v[l][r], o[l][r])
+        j = k >> 2
+        while j > 0:
+            if j < e:
+                for l in range(32):
+                    for r in range(e):
+                        if (r & j) == 0 and v[l][r] > v[l][r | j]:
+                            v[l][r], v[l][r | j] = v[l][r | j], v[l][r]
+            else:
+                m = j // e
+                v = [[(min(v[l][r], v[l ^ m][r]) if (l & m) == 0 else max(v[l][r], v[l ^ m][r])) for r in range(e)] for l in range(32)]
+            j >>= 1
+        k <<= 1
+    return [v[i // e][i % e] for i in range(n)]
+
+
+def test_register_shuffle_network_of_the_prepared_ubench():
+    rnd = random.Random(5)
+    for e in (1, 2, 4, 8):
+        for n in {2, 3, 31, 32 * e - 1, 32 * e, 16 * e + 3}:
+            keys = [rnd.randrange(1 << 60) for _ in range(min(n, 32 * e))]
+            assert _warp_sort_regs(keys, e) == sorted(keys), (e, n)
