@@ -145,6 +145,47 @@ int yms_resample_u8(const uint8_t* src, int src_h, int src_w, int channels, int6
 int yms_dwconv(const void* x, int64_t x_pixel_stride, int batch, int h, int w, int channels, int ksize,
                const float* weight, const float* bias, void* y, int64_t y_pixel_stride, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MS-Block branch layer (repo-local block built from the reference's Conv unit, components.py:69-77, incl. its `groups`
+ * argument; the reference only sketches the block, annotations.md:66-133):
+ *        x [c_in (+ c_in2)] --1x1 (pw1)--> e [e_ch] --depthwise k x k--> d [e_ch] --1x1 (pw2)--> y [c_out]
+ * every step = Conv2d(bias=False) + BatchNorm2d(eval) folded into weight / bias by the host + SiLU.  One kernel, three modes:
+ *   mode 0: depthwise only            y = SiLU(dw(e) + dw_bias)                        (the kernel behind yms_dwconv)
+ *   mode 1: depthwise -> pw2          y = act2(W2 . SiLU(dw(e) + dw_bias) + bias2)     (d never reaches HBM)
+ *   mode 2: pw1 -> depthwise -> pw2   e = SiLU(W1 . cat[x, x2] + bias1) computed on the halo of every 16 x 8 output tile,
+ *                                     zero outside the image (the depthwise padding) -- neither e nor d reaches HBM.
+ * Activations NHWC bf16 (channel slices allowed: pixel strides in elements); depthwise in fp32 on the CUDA cores
+ * (fma.rn.f32x2), 1x1 convolutions on tcgen05 with fp32 accumulation.
+ * Limits: ksize in {3,5,7,9}; channels % 8 == 0; modes 1/2: c_out % 16 == 0, <= 256; mode 2 additionally needs the layer's
+ * operands to fit in shared memory / TMEM (small c): YMS_E_UNSUPPORTED otherwise -- fall back to a lower mode.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct yms_ms_params {
+    int32_t mode;                     /* 0, 1, 2 (above)                                                   */
+    int32_t batch, h, w;
+    int32_t ksize;                    /* depthwise kernel size, padding ksize/2, stride 1                  */
+    int32_t e_ch;                     /* expanded (depthwise) channels                                     */
+    int32_t c_out;                    /* pw2 output channels (modes 1, 2)                                  */
+    int32_t act2;                     /* pw2 activation: 0 identity, 1 SiLU                                */
+    int32_t c_in, c_in2;              /* pw1 input channels of x / x2 (mode 2; c_in2 = 0: one source)      */
+    const void* e;  int64_t e_pixel_stride;    /* bf16 [B,H,W,e_ch]  (modes 0, 1)                          */
+    const void* x;  int64_t x_pixel_stride;    /* bf16 [B,H,W,c_in]  (mode 2)                              */
+    const void* x2; int64_t x2_pixel_stride;   /* bf16 [B,H,W,c_in2] (mode 2) or NULL                      */
+    void* y;        int64_t y_pixel_stride;    /* bf16 [B,H,W,c_out] (mode 0: [B,H,W,e_ch])                */
+    const void* w1;                   /* bf16 [e_ch][c_in + c_in2]  (mode 2)                               */
+    const float* bias1;               /* f32 [e_ch]                 (mode 2)                               */
+    const float* dw_weight;           /* f32 [ksize*ksize][e_ch]    (tap-major)                            */
+    const float* dw_bias;             /* f32 [e_ch]                                                        */
+    const void* w2;                   /* bf16 [c_out][e_ch]         (modes 1, 2)                           */
+    const float* bias2;               /* f32 [c_out]                (modes 1, 2)                           */
+} yms_ms_params;
+
+typedef struct yms_ms_plan yms_ms_plan;       /* opaque: encoded tensor maps + launch geometry */
+int yms_ms_plan_create(const yms_ms_params* p, yms_ms_plan** plan);
+int yms_ms_plan_run(const yms_ms_plan* plan, void* stream);
+int yms_ms_plan_destroy(yms_ms_plan* plan);
+/* 2*MACs and algorithmic bytes (inputs + outputs + weights that must cross HBM in this mode). */
+int yms_ms_plan_cost(const yms_ms_plan* plan, double* flops, double* bytes);
+
 /* SPPF pooling (components.py:141-146): x1 = maxpool5(x), x2 = maxpool5(x1), x3 = maxpool5(x2)
  * (5x5, stride 1, pad 2), written as channel slots 1..3 of the concat buffer whose slot 0
  * already holds x.  buf: bf16 [B,H,W,4*c] (pixel stride given). */

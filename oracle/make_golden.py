@@ -11,6 +11,9 @@ Outputs (all small, committed):
   post_n.npz                   reference post-process (tools/test.py:166-218 with the real
                                torchvision.ops.nms) on a reference prediction
   nms_cases.npz                torchvision.ops.nms keep lists on adversarial box sets
+  dwconv_ref.npz               the reference's own Conv unit run as a depthwise layer, Conv(c, c, k, 1, k//2, groups=c)
+                               (components.py:69-77; the reference never instantiates it that way, but the class supports it),
+                               k = 3/5/7/9, and the MS-Block branch layer pw1 -> dw -> pw2 composed of three reference Conv units
 """
 from __future__ import annotations
 
@@ -168,6 +171,56 @@ def dump_nms():
     np.savez_compressed(os.path.join(GOLD, "nms_cases.npz"), **out)
 
 
+def _randomize_bn(mod, g):
+    for m in mod.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            n = m.num_features
+            m.weight.data = torch.rand(n, generator=g) * 0.8 + 0.6
+            m.bias.data = torch.randn(n, generator=g) * 0.2
+            m.running_mean.data = torch.randn(n, generator=g) * 0.2
+            m.running_var.data = torch.rand(n, generator=g) * 0.8 + 0.6
+
+
+@torch.no_grad()
+def dump_dwconv():
+    """Depthwise unit and MS-Block branch layer computed by the REFERENCE's Conv class (fp32, eval)."""
+    from yolov8.model.components import Conv            # the real reference
+    out = {}
+    g = torch.Generator().manual_seed(123)
+    bf = lambda t: t.to(torch.bfloat16).float()          # inputs / conv weights are bf16-representable (the GPU contract stores them so)
+    for k, (c, h, w) in ((3, (64, 20, 24)), (5, (24, 19, 37)), (7, (72, 20, 20)), (9, (16, 12, 33))):
+        m = Conv(c, c, k, 1, k // 2, groups=c).eval()
+        m.conv.weight.data = torch.randn(c, 1, k, k, generator=g) / k
+        _randomize_bn(m, g)
+        x = bf(torch.randn(1, c, h, w, generator=g))
+        out[f"dw{k}_x"] = x.numpy()
+        out[f"dw{k}_y"] = m(x.clone()).numpy()
+        for name, t in m.state_dict().items():
+            out[f"dw{k}_{name}"] = t.numpy()
+    # branch layer: x (+ x2) -> Conv(c, 2c, 1) -> Conv(2c, 2c, k, groups=2c) -> Conv(2c, c, 1)
+    for tag, (k, c, h, w, two) in (("a", (3, 32, 24, 40, True)), ("b", (3, 64, 17, 21, False)), ("c", (5, 128, 12, 20, True)),
+                                   ("d", (7, 48, 9, 13, False))):
+        pw1, dw, pw2 = Conv(c, 2 * c, 1, 1, 0).eval(), Conv(2 * c, 2 * c, k, 1, k // 2, groups=2 * c).eval(), Conv(2 * c, c, 1, 1, 0).eval()
+        pw1.conv.weight.data = bf(torch.randn(2 * c, c, 1, 1, generator=g) / c ** 0.5)
+        dw.conv.weight.data = torch.randn(2 * c, 1, k, k, generator=g) / k
+        pw2.conv.weight.data = bf(torch.randn(c, 2 * c, 1, 1, generator=g) / (2 * c) ** 0.5)
+        for m in (pw1, dw, pw2):
+            _randomize_bn(m, g)
+        x = bf(torch.randn(1, c, h, w, generator=g))
+        x2 = bf(torch.randn(1, c, h, w, generator=g)) if two else None
+        y = pw2(dw(pw1(x + x2 if two else x.clone())))
+        out[f"ms{tag}_x"] = x.numpy()
+        if two:
+            out[f"ms{tag}_x2"] = x2.numpy()
+        out[f"ms{tag}_y"] = y.numpy()
+        out[f"ms{tag}_k"] = np.array(k)
+        for nm, m in (("pw1", pw1), ("dw", dw), ("pw2", pw2)):
+            for name, t in m.state_dict().items():
+                out[f"ms{tag}_{nm}.{name}"] = t.numpy()
+    np.savez_compressed(os.path.join(GOLD, "dwconv_ref.npz"), **out)
+    print("dwconv_ref", {k: v.shape for k, v in out.items() if k.endswith("_y")})
+
+
 def dump_bn_fixtures():
     """BN running statistics of the calibrated synthetic weights (seed 1) for bench.py / smoke():
     yolo_ms_b200/synth_bn/bn_{version}_{block}_seed1.npz."""
@@ -190,3 +243,4 @@ if __name__ == "__main__":
     dump_model("s", 1, 64, 64, seed=2)
     dump_post()
     dump_nms()
+    dump_dwconv()

@@ -98,3 +98,21 @@ def test_oracle_matches_live_reference(version):
     assert float((got[..., 4:] - ref[..., 4:]).abs().max()) < 1e-5
     for a, b in zip(raw, raw_ref):
         assert close(a, b, 1e-5)
+
+
+def test_oracle_conv_unit_matches_reference_conv_as_depthwise_and_ms_layer():
+    """tests/golden/dwconv_ref.npz was produced by the reference's own Conv class (components.py:69-77) run with groups=c and
+    as the pw1 -> dw -> pw2 chain of an MS-Block branch layer (oracle/make_golden.py::dump_dwconv): pins the oracle's conv unit
+    for the depthwise case, which the reference model itself never instantiates."""
+    g = np.load(os.path.join(GOLDEN, "dwconv_ref.npz"))
+    for k in (3, 5, 7, 9):
+        sd = {"u." + n[len(f"dw{k}_"):]: torch.from_numpy(g[n]) for n in g.files if n.startswith(f"dw{k}_") and n[len(f"dw{k}_")] in "cb"}
+        y = O.conv_unit(sd, "u", torch.from_numpy(g[f"dw{k}_x"]))
+        assert float((y - torch.from_numpy(g[f"dw{k}_y"])).abs().max()) < 2e-5
+    for tag in "abcd":
+        sd = {n[len(f"ms{tag}_"):]: torch.from_numpy(g[n]) for n in g.files if n.startswith(f"ms{tag}_") and "." in n}
+        x = torch.from_numpy(g[f"ms{tag}_x"])
+        if f"ms{tag}_x2" in g.files:
+            x = x + torch.from_numpy(g[f"ms{tag}_x2"])
+        y = O.conv_unit(sd, "pw2", O.conv_unit(sd, "dw", O.conv_unit(sd, "pw1", x)))
+        assert float((y - torch.from_numpy(g[f"ms{tag}_y"])).abs().max()) < 2e-5

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("YMS_LIB") or os.path.join(_HERE, "libyms_b200.so")   
 EXPORTS = [
     "yms_abi_version", "yms_last_error", "yms_launch_count",
     "yms_conv_plan_create", "yms_conv_plan_run", "yms_conv_plan_destroy", "yms_conv_plan_cost", "yms_conv_plan_fuse_decode", "yms_conv_plan_add_upsampled",
+    "yms_ms_plan_create", "yms_ms_plan_run", "yms_ms_plan_destroy", "yms_ms_plan_cost",
     "yms_stem_conv", "yms_stem_conv_u8", "yms_resample_u8", "yms_dwconv", "yms_sppf_pool", "yms_upsample2x",
     "yms_head_decode", "yms_select_candidates",
     "yms_nms_workspace_bytes", "yms_nms_batched", "yms_gather_detections",
@@ -50,6 +51,20 @@ class DecodeFusion(C.Structure):
     ]
 
 
+class MsParams(C.Structure):
+    """yms_ms_params (include/yms_b200.h)."""
+    _fields_ = [
+        ("mode", C.c_int32), ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("ksize", C.c_int32),
+        ("e_ch", C.c_int32), ("c_out", C.c_int32), ("act2", C.c_int32), ("c_in", C.c_int32), ("c_in2", C.c_int32),
+        ("e", C.c_void_p), ("e_pixel_stride", C.c_int64),
+        ("x", C.c_void_p), ("x_pixel_stride", C.c_int64),
+        ("x2", C.c_void_p), ("x2_pixel_stride", C.c_int64),
+        ("y", C.c_void_p), ("y_pixel_stride", C.c_int64),
+        ("w1", C.c_void_p), ("bias1", C.c_void_p), ("dw_weight", C.c_void_p), ("dw_bias", C.c_void_p),
+        ("w2", C.c_void_p), ("bias2", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -78,6 +93,10 @@ def load() -> C.CDLL:
     lib.yms_conv_plan_cost.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
     lib.yms_conv_plan_fuse_decode.argtypes = [vp, C.POINTER(DecodeFusion)]
     lib.yms_conv_plan_add_upsampled.argtypes = [vp, vp, i64, i32, i32]
+    lib.yms_ms_plan_create.argtypes = [C.POINTER(MsParams), C.POINTER(vp)]
+    lib.yms_ms_plan_run.argtypes = [vp, vp]
+    lib.yms_ms_plan_destroy.argtypes = [vp]
+    lib.yms_ms_plan_cost.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
     lib.yms_stem_conv.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i64, vp]
     lib.yms_stem_conv_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp, C.POINTER(f32), C.POINTER(f32), vp, i64, vp]
     lib.yms_resample_u8.argtypes = [vp, i32, i32, i32, i64, vp, i32, i32, i64, vp, vp, i32, i32, vp]

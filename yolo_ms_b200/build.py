@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyms_b200.so")
-SOURCES = ["capi.cu", "conv_gemm.cu", "conv3x3.cu", "stem_tc.cu", "glue.cu", "head_decode.cu", "nms.cu"]
+SOURCES = ["capi.cu", "conv_gemm.cu", "conv3x3.cu", "stem_tc.cu", "glue.cu", "ms_fused.cu", "head_decode.cu", "nms.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

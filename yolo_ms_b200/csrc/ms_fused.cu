@@ -1,0 +1,721 @@
+// MS-Block branch layer on one SM pass: depthwise k x k (CUDA cores, packed fp32 FMAs) fused with the 1x1
+// convolutions around it (tcgen05), so that the EXPANDED tensor of the layer never travels to HBM.
+//
+// The repo-local MS-Block layer (yolo_ms_b200/modules.py::MSBlock, built from the reference's Conv unit
+// yolov8/model/components.py:69-77 with its `groups` argument) is
+//        x [c] --pw1 1x1--> e [E = 2c] --depthwise k x k--> d [E] --pw2 1x1--> y [c]
+// each step followed by the folded BN bias and SiLU.  Unfused it moves 11c elements per pixel through HBM
+// (the two expanded tensors are written once and read once each); the kernel below has three modes:
+//   mode 0  depthwise only            e (TMA halo tiles) -> d -> TMA store            (yms_dwconv: Conv(c, c, k, groups=c))
+//   mode 1  depthwise -> pw2          e (TMA halo tiles) -> d (smem, UMMA A operand) -> tcgen05.mma -> epilogue -> y
+//   mode 2  pw1 -> depthwise -> pw2   x halo tile (TMA) -> tcgen05.mma -> e (TMEM -> bias/SiLU -> smem, zero outside the image)
+//                                     -> d -> tcgen05.mma -> epilogue -> y        (3c elements per pixel)
+// Work decomposition: output tile = 16 x 8 pixels of one image (M = 128 rows of the pw2 GEMM); the expanded channels are walked
+// in chunks of 64 (one 128-byte swizzle row); chunk j of pw2's K dimension is produced by the depthwise stage while the
+// tensor core consumes chunk j-1.
+//
+// Depthwise stage (the CUDA-core part; HBM-bound for k = 3, FMA-bound for k >= 5):
+//   * halo rows live in shared memory at a pitch of 24 pixels (a multiple of 8), 128 B per pixel, 16-byte chunks XOR-swizzled
+//     by (pixel & 7) -- exactly what TMA SWIZZLE_128B writes when every halo row is its own box at a 3072-byte pitch.  With
+//     strips that start at x = 0 or 8 the swizzle term of every tap is a compile-time constant: one IADD per load.
+//   * thread = 4 channels x 8 consecutive output pixels of one row: per kernel row it loads 8+k-1 pixels (LDS.64), converts
+//     bf16 -> fp32 with a shift / mask, and issues k FFMA2 (fma.rn.f32x2) per pixel per channel pair against the k weights
+//     of that row held in registers; fp32 accumulation throughout (the repo's numeric contract).
+//   * the result (bias, SiLU, bf16) is written as a [128 x 64] K-major SWIZZLE_128B tile = the A operand of pw2's MMAs
+//     (or the source of a TMA store in mode 0).
+#include "conv_plan.h"
+
+#include <string.h>
+#include <new>
+
+namespace yms {
+namespace {
+using namespace tc;
+
+constexpr int kTW = 16, kTH = 8;                 // output pixels per tile
+constexpr int kPitch = 24;                       // halo-row pitch in pixels
+constexpr int kRowPitchBytes = kPitch * 128;     // 3072
+constexpr int kMaxE = 4;                         // e-ring stages
+constexpr int kDTile = 128 * 128;                // one [128 x 64] bf16 tile
+constexpr int kGroupThreads = 256;               // threads of one depthwise group
+constexpr int kFirstDwWarp = 6;                  // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. depthwise groups
+constexpr int kSmemLimit = 232448;
+
+struct MsParams {
+    int mode, ksize;
+    int tiles_x, tiles_y, batch, total_tiles;
+    uint32_t mg_tiles_x, mg_tiles_y;
+    int e_ch, n_chunks, tail_ksteps;             // expanded channels, 64-channel chunks, k-steps of the last chunk
+    int c_out, block_n, act2;
+    int e_stages, dw_groups;
+    int w2_resident, w2_tile_bytes;
+    int acc_stride, tmem_cols;
+    int stage_bytes, off_dww, off_dwb, off_w2;   // layout of one e stage
+    int so_x, so_e, so_d, so_w2, so_out, so_w1, so_bias;   // shared-memory carve-up (bytes from the 1024-aligned base)
+    int x_kb_stride;                             // mode 2: bytes between the halo tiles of consecutive K blocks (hp * 128 rounded up to 1 KB)
+    uint32_t stage_tx;                           // bytes TMA delivers per stage
+    int bias_pad;
+    const float* bias2;
+    // mode 2
+    int c_in1, c_in2, kb1, kb2;                  // pw1 sources (K-concatenated), 64-channel blocks of each
+    int mt;                                      // M tiles (128 halo pixels each) of the pw1 GEMM
+    int hp;                                      // halo pixels = (16+k-1) * (8+k-1)
+    int img_w, img_h;
+    int w1_tile_bytes;                           // one [64 x 64] weight tile = 8192
+    int g1_stride;                               // TMEM columns between the two pw1 accumulator stages
+    int g1_base;                                 // first TMEM column of the pw1 accumulators
+    const float* bias1;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void dwg_bar_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ unsigned long long pack64(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack64(unsigned long long v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a); hi = __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+struct TileXY { int img, x0, y0; };
+__device__ __forceinline__ TileXY decode_tile(const MsParams& p, int t) {
+    TileXY c;
+    uint32_t q = fast_div((uint32_t)t, p.mg_tiles_x);
+    const int tx = t - (int)q * p.tiles_x;
+    const uint32_t q2 = fast_div(q, p.mg_tiles_y);
+    const int ty = (int)(q - q2 * p.tiles_y);
+    c.img = (int)q2; c.x0 = tx * kTW; c.y0 = ty * kTH;
+    return c;
+}
+
+// Depthwise accumulation of one work item: 8 output pixels (row oy, x0 .. x0+7) x 4 channels, taps from the halo tile at e_base.
+// acc[o][0] = channels (4q, 4q+1), acc[o][1] = channels (4q+2, 4q+3) of output pixel o, as packed f32x2.
+template <int K>
+__device__ __forceinline__ void dw_accumulate(uint32_t e_base, uint32_t w_base, const uint32_t (&tbl)[8], int oy, int x0,
+                                              unsigned long long (&acc)[8][2]) {
+    #pragma unroll
+    for (int o = 0; o < 8; ++o) { acc[o][0] = 0ull; acc[o][1] = 0ull; }
+    #pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        unsigned long long w[K][2];
+        #pragma unroll
+        for (int kx = 0; kx < K; ++kx)
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w[kx][0]), "=l"(w[kx][1]) : "r"(w_base + (uint32_t)((ky * K + kx) * 256)));
+        const uint32_t rowbase = e_base + (uint32_t)(((oy + ky) * kPitch + x0) * 128);
+        #pragma unroll
+        for (int j = 0; j < 8 + K - 1; ++j) {
+            uint32_t v0, v1;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(rowbase + tbl[j & 7] + (uint32_t)(j * 128)));
+            const unsigned long long p0 = pack64(v0 << 16, v0 & 0xffff0000u);
+            const unsigned long long p1 = pack64(v1 << 16, v1 & 0xffff0000u);
+            #pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int o = j - kx;
+                if (o >= 0 && o < 8) {
+                    acc[o][0] = fma2(p0, w[kx][0], acc[o][0]);
+                    acc[o][1] = fma2(p1, w[kx][1], acc[o][1]);
+                }
+            }
+        }
+    }
+}
+
+// bias + SiLU + bf16, written to row (oy*16 + x0 + o) of the [128 x 64] swizzled tile at d_base
+__device__ __forceinline__ void dw_store(uint32_t d_base, uint32_t b_addr, const uint32_t (&tbl)[8], int oy, int x0,
+                                         const unsigned long long (&acc)[8][2]) {
+    float4 b;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(b_addr));
+    b.x *= 0.5f; b.y *= 0.5f; b.z *= 0.5f; b.w *= 0.5f;
+    const uint32_t rowbase = d_base + (uint32_t)((oy * kTW + x0) * 128);
+    #pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        float a0, a1, a2, a3;
+        unpack64(acc[o][0], a0, a1);
+        unpack64(acc[o][1], a2, a3);
+        const uint32_t o0 = pack_bf16x2(silu_from_half(fmaf(a0, 0.5f, b.x)), silu_from_half(fmaf(a1, 0.5f, b.y)));
+        const uint32_t o1 = pack_bf16x2(silu_from_half(fmaf(a2, 0.5f, b.z)), silu_from_half(fmaf(a3, 0.5f, b.w)));
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rowbase + tbl[o] + (uint32_t)(o * 128)), "r"(o0), "r"(o1) : "memory");
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(704, 1)
+ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_dww,
+                const __grid_constant__ CUtensorMap tm_dwb, const __grid_constant__ CUtensorMap tm_w2,
+                const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_x,
+                const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_w1,
+                const __grid_constant__ MsParams p) {
+    constexpr int HWX = kTW + K - 1, HWY = kTH + K - 1, PAD = K / 2;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+    // carve-up (host: yms_ms_plan_create): [mode 2: x halo tiles][e stages][d x 2][W2 resident][staging][mode 2: W1][bias][barriers].
+    // The x tiles come first: the last M tile of a K block reads 128 rows even when the halo has fewer, i.e. past the tile
+    // into whatever follows (harmless garbage rows of the accumulator) -- that must still be inside the allocation.
+    const uint32_t s_x = base + (uint32_t)p.so_x;
+    const uint32_t s_e0 = base + (uint32_t)p.so_e;
+    const uint32_t s_d0 = base + (uint32_t)p.so_d;
+    const uint32_t s_w2 = base + (uint32_t)p.so_w2;
+    const uint32_t s_out = base + (uint32_t)p.so_out;
+    const uint32_t s_w1 = base + (uint32_t)p.so_w1;
+    const uint32_t w1_bytes = p.mode == 2 ? (uint32_t)(p.n_chunks * (p.kb1 + p.kb2) * p.w1_tile_bytes) : 0u;
+    const uint32_t s_biasu = base + (uint32_t)p.so_bias;
+    float* s_bias = reinterpret_cast<float*>(gbase + (s_biasu - base));          // pw2 bias (0.5 x when act), then pw1 bias (mode 2)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto e_full = [&](int s) { return bar0 + 8u * s; };
+    auto e_empty = [&](int s) { return bar0 + 8u * (kMaxE + s); };
+    auto d_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + s); };
+    auto d_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 2 + s); };
+    auto acc_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 4 + s); };
+    auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 6 + s); };
+    const uint32_t res_bar = bar0 + 8u * (2 * kMaxE + 8);
+    const uint32_t w_bar = bar0 + 8u * (2 * kMaxE + 9);
+    auto g1_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 10 + s); };      // mode 2: pw1 accumulator stage ready
+    auto g1_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 12 + s); };
+    const uint32_t x_full = bar0 + 8u * (2 * kMaxE + 14);                        // mode 2: x halo tile landed / may be overwritten
+    const uint32_t x_empty = bar0 + 8u * (2 * kMaxE + 15);
+    constexpr int kNumBars = 2 * kMaxE + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int dw_warps = p.dw_groups * 8;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            prefetch_tmap(&tm_dww); prefetch_tmap(&tm_dwb); prefetch_tmap(&tm_y);
+            if (p.mode != 2) prefetch_tmap(&tm_e);
+            if (p.mode >= 1) prefetch_tmap(&tm_w2);
+            if (p.mode == 2) { prefetch_tmap(&tm_x); prefetch_tmap(&tm_w1); if (p.kb2) prefetch_tmap(&tm_x2); }
+        }
+        if (lane < kNumBars) {
+            uint32_t cnt = 1;
+            if (lane >= kMaxE && lane < 2 * kMaxE) cnt = 8u + ((p.mode >= 1 && !p.w2_resident) ? 1u : 0u);   // e_empty: the 8 warps of a group (+ MMA commit)
+            else if (lane >= 2 * kMaxE && lane < 2 * kMaxE + 2) cnt = 8u;                                     // d_full: the 8 warps of a group
+            else if (lane >= 2 * kMaxE + 6 && lane < 2 * kMaxE + 8) cnt = 4u;                                 // acc_empty: 4 epilogue warps
+            else if (lane >= 2 * kMaxE + 12 && lane < 2 * kMaxE + 14) cnt = 8u;                               // g1_empty: the 8 warps of a group
+            mbar_init(bar0 + 8u * lane, cnt);
+        }
+        fence_barrier_init();
+        __syncwarp();
+        if (p.mode >= 1 && elect_one()) {                      // constants of the program: fetched before the grid dependency resolves
+            uint32_t tx = 0;
+            if (p.w2_resident) tx += (uint32_t)(p.n_chunks * p.w2_tile_bytes);
+            if (p.mode == 2) tx += w1_bytes;
+            if (tx) {
+                mbar_expect_tx(w_bar, tx);
+                if (p.w2_resident)
+                    for (int j = 0; j < p.n_chunks; ++j) tma_load_3d(s_w2 + (uint32_t)(j * p.w2_tile_bytes), &tm_w2, w_bar, j * 64, 0, 0);
+                if (p.mode == 2) {
+                    const int kbt = p.kb1 + p.kb2;
+                    for (int j = 0; j < p.n_chunks; ++j)
+                        for (int kb = 0; kb < kbt; ++kb)
+                            tma_load_3d(s_w1 + (uint32_t)((j * kbt + kb) * p.w1_tile_bytes), &tm_w1, w_bar,
+                                        kb < p.kb1 ? kb * 64 : p.c_in1 + (kb - p.kb1) * 64, j * 64, 0);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (warp == 1 && p.mode >= 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.bias_pad; i += blockDim.x) {
+        float v = 0.f;
+        if (p.mode >= 1 && i < p.c_out) v = p.act2 ? 0.5f * p.bias2[i] : p.bias2[i];
+        else if (p.mode == 2 && i >= 256 && i - 256 < p.e_ch) v = 0.5f * p.bias1[i - 256];
+        s_bias[i] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = p.mode >= 1 ? *tmem_slot : 0u;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            uint32_t n = 0;                                    // chunk counter over the CTA's tiles
+            uint32_t xphase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileXY tc = decode_tile(p, t);
+                if (p.mode == 2) {                             // the tile's input halo, all K blocks (single buffer, released by the last pw1 MMA)
+                    mbar_wait(x_empty, xphase ^ 1u);
+                    const int kbt = p.kb1 + p.kb2;
+                    mbar_expect_tx(x_full, (uint32_t)(kbt * HWX * HWY * 128));
+                    for (int kb = 0; kb < kbt; ++kb)
+                        tma_load_4d(s_x + (uint32_t)(kb * p.x_kb_stride), kb < p.kb1 ? &tm_x : &tm_x2, x_full,
+                                    (kb < p.kb1 ? kb : kb - p.kb1) * 64, tc.x0 - PAD, tc.y0 - PAD, tc.img);
+                    xphase ^= 1u;
+                }
+                for (int j = 0; j < p.n_chunks; ++j, ++n) {
+                    const int s = (int)(n % (uint32_t)p.e_stages);
+                    const uint32_t ph = (n / (uint32_t)p.e_stages) & 1u;
+                    mbar_wait(e_empty(s), ph ^ 1u);
+                    const uint32_t st = s_e0 + (uint32_t)(s * p.stage_bytes);
+                    mbar_expect_tx(e_full(s), p.stage_tx);
+                    if (p.mode != 2) {
+                        #pragma unroll 1
+                        for (int hy = 0; hy < HWY; ++hy)
+                            tma_load_4d(st + (uint32_t)(hy * kRowPitchBytes), &tm_e, e_full(s), j * 64, tc.x0 - PAD, tc.y0 - PAD + hy, tc.img);
+                    }
+                    tma_load_2d(st + (uint32_t)p.off_dww, &tm_dww, e_full(s), j * 64, 0);
+                    tma_load_2d(st + (uint32_t)p.off_dwb, &tm_dwb, e_full(s), j * 64, 0);
+                    if (p.mode >= 1 && !p.w2_resident) tma_load_3d(st + (uint32_t)p.off_w2, &tm_w2, e_full(s), j * 64, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one elected thread) =================
+        if (p.mode >= 1 && elect_one()) {
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            if (p.w2_resident || p.mode == 2) mbar_wait(w_bar, 0u);     // armed in the prologue only in these cases
+            tc_fence_after();
+            uint32_t n = 0, ti = 0, xphase = 0;
+            const int kbt = p.kb1 + p.kb2;
+            const int tail1 = p.mode == 2 ? (((p.c_in1 - (p.kb1 - 1) * 64) + 15) >> 4) : 4;
+            const int tail2 = (p.mode == 2 && p.kb2) ? (((p.c_in2 - (p.kb2 - 1) * 64) + 15) >> 4) : 4;
+            auto issue_g1 = [&](uint32_t gn, int j) {
+                const int gs = (int)(gn & 1u);
+                mbar_wait(g1_empty(gs), ((gn >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                for (int m = 0; m < p.mt; ++m) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
+                    for (int kb = 0; kb < kbt; ++kb) {
+                        const uint32_t a16 = ((s_x + (uint32_t)(kb * p.x_kb_stride + m * kDTile)) & 0x3FFFFu) >> 4;
+                        const uint32_t b16 = ((s_w1 + (uint32_t)((j * kbt + kb) * p.w1_tile_bytes)) & 0x3FFFFu) >> 4;
+                        const int ks = (kb == p.kb1 - 1) ? tail1 : ((kb == kbt - 1) ? tail2 : 4);
+                        for (int k = 0; k < ks; ++k)
+                            umma_bf16(d_tmem, hi | (uint64_t)(a16 + 2 * k), hi | (uint64_t)(b16 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(g1_full(gs));
+            };
+            // mode 2: the pw1 GEMM runs one chunk AHEAD of the pw2 GEMM, also across tile boundaries (the x halo tile is a single
+            // buffer: it is released by the last pw1 MMA of its tile and refilled while the tile's remaining chunks are processed)
+            auto first_g1_of_tile = [&](uint32_t gn) {
+                mbar_wait(x_full, xphase); xphase ^= 1u;
+                tc_fence_after();
+                issue_g1(gn, 0);
+                if (p.n_chunks == 1) umma_commit(x_empty);
+            };
+            if (p.mode == 2 && (int)blockIdx.x < p.total_tiles) first_g1_of_tile(0);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+                const int as = (int)(ti & 1u);
+                mbar_wait(acc_empty(as), ((ti >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
+                for (int j = 0; j < p.n_chunks; ++j, ++n) {
+                    if (p.mode == 2) {
+                        if (j + 1 < p.n_chunks) {
+                            issue_g1(n + 1, j + 1);
+                            if (j + 2 == p.n_chunks) umma_commit(x_empty);       // every pw1 MMA of this tile has been issued
+                        } else if (t + (int)gridDim.x < p.total_tiles) {
+                            first_g1_of_tile(n + 1);
+                        }
+                    }
+                    const int ds = (int)(n & 1u);
+                    const int s = (int)(n % (uint32_t)p.e_stages);
+                    if (!p.w2_resident) mbar_wait(e_full(s), (n / (uint32_t)p.e_stages) & 1u);
+                    mbar_wait(d_full(ds), (n >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t a16 = ((s_d0 + (uint32_t)ds * kDTile) & 0x3FFFFu) >> 4;
+                    const uint32_t b16 = ((p.w2_resident ? s_w2 + (uint32_t)(j * p.w2_tile_bytes)
+                                                         : s_e0 + (uint32_t)(s * p.stage_bytes + p.off_w2)) & 0x3FFFFu) >> 4;
+                    const int ks = (j == p.n_chunks - 1) ? p.tail_ksteps : 4;
+                    for (int k = 0; k < ks; ++k)
+                        umma_bf16(d_tmem, hi | (uint64_t)(a16 + 2 * k), hi | (uint64_t)(b16 + 2 * k), idesc2, (j | k) ? 1u : 0u);
+                    umma_commit(d_empty(ds));
+                    if (!p.w2_resident) umma_commit(e_empty(s));
+                    if (j == p.n_chunks - 1) umma_commit(acc_full(as));
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < kFirstDwWarp) {
+        // ================= pw2 epilogue: TMEM -> bias / SiLU -> bf16 -> swizzled staging -> TMA store =================
+        if (p.mode >= 1) {
+            EpiShared e;
+            e.tm_y = &tm_y; e.tm_res = &tm_y;
+            e.res_bar = res_bar;
+            e.s_out = s_out;
+            e.s_bias = s_bias;
+            e.block_n = p.block_n; e.c_out = p.c_out; e.act = p.act2; e.has_res = 0;
+            e.out_bytes = (uint32_t)kDTile;
+            e.bar_id = 1;
+            e.leader = (warp == 2) && lane == 0;
+            e.row = (warp & 3) * 32 + lane;
+            const int n_chunks_out = (p.block_n + 63) >> 6;
+            uint32_t res_phase = 0u, ti = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+                const int as = (int)(ti & 1u);
+                const TileXY tc = decode_tile(p, t);
+                EpiTile tl; tl.n0 = 0; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
+                mbar_wait(acc_full(as), (ti >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(as * p.acc_stride);
+                for (int ch = 0; ch < n_chunks_out; ++ch) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(as));
+            }
+            if (e.leader) tma_store_wait_read<0>();
+        }
+    } else if (warp < kFirstDwWarp + dw_warps) {
+        // ================= depthwise groups: group g takes the chunks n = g (mod groups) =================
+        const int dwt = (int)threadIdx.x - kFirstDwWarp * 32;
+        const int g = dwt >> 8, tg = dwt & 255;
+        const int q = tg & 15, strip = tg >> 4;
+        const int oy = strip >> 1, x0 = (strip & 1) * 8;
+        uint32_t tbl[8];
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) tbl[i] = ((uint32_t)((q >> 1) ^ i) << 4) + (uint32_t)((q & 1) * 8);
+        const bool leader = tg == 0;
+        const int bar_id = 2 + g;
+        uint32_t n = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileXY tc = decode_tile(p, t);
+            for (int j = 0; j < p.n_chunks; ++j, ++n) {
+                if ((int)(n % (uint32_t)p.dw_groups) != g) continue;
+                const int s = (int)(n % (uint32_t)p.e_stages);
+                const uint32_t st = s_e0 + (uint32_t)(s * p.stage_bytes);
+                const int ds = (int)(n & 1u);
+                const uint32_t d_base = s_d0 + (uint32_t)ds * kDTile;
+                if (p.mode == 2) {
+                    // ---- pw1 epilogue: accumulator rows (halo pixels) -> bias / SiLU -> bf16 -> halo tile of this stage, zero outside the image
+                    // the stage is free (its previous halo tile has been consumed by whichever group used it) once the producer
+                    // could arm it for this chunk's depthwise weights
+                    mbar_wait(e_full(s), (n / (uint32_t)p.e_stages) & 1u);
+                    const int gs = (int)(n & 1u);
+                    mbar_wait(g1_full(gs), (n >> 1) & 1u);
+                    tc_fence_after();
+                    const int wq = warp & 3;                                      // TMEM lane quadrant this warp may read
+                    const int wsub = (warp - kFirstDwWarp) & 7;                   // warp index inside the group
+                    for (int m = wsub >> 2; m < p.mt; m += 2) {
+                        const int hpix = m * 128 + wq * 32 + lane;                // halo pixel of this thread = accumulator row
+                        const int hy = hpix / HWX, hx = hpix - hy * HWX;
+                        const int gx = tc.x0 - PAD + hx, gy = tc.y0 - PAD + hy;
+                        const bool inside = hpix < p.hp && gx >= 0 && gx < p.img_w && gy >= 0 && gy < p.img_h;
+                        const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
+                        const uint32_t line = st + (uint32_t)((hy * kPitch + hx) * 128);
+                        #pragma unroll 1
+                        for (int q16 = 0; q16 < 4; ++q16) {
+                            uint32_t v[16];
+                            tmem_ld16(t_row + (uint32_t)(q16 * 16), v);
+                            tmem_ld_wait();
+                            if (hpix < p.hp) {
+                                const float4* bq = reinterpret_cast<const float4*>(s_bias + 256 + j * 64 + q16 * 16);
+                                uint32_t o[8];
+                                #pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 hb = bq[i];
+                                    const float f0 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 0]), 0.5f, hb.x));
+                                    const float f1 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, hb.y));
+                                    const float f2 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, hb.z));
+                                    const float f3 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, hb.w));
+                                    o[2 * i] = inside ? pack_bf16x2(f0, f1) : 0u;
+                                    o[2 * i + 1] = inside ? pack_bf16x2(f2, f3) : 0u;
+                                }
+                                #pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint32_t addr = line + (((uint32_t)(q16 * 2 + h) ^ (uint32_t)(hx & 7)) << 4);
+                                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[4 * h]), "r"(o[4 * h + 1]), "r"(o[4 * h + 2]), "r"(o[4 * h + 3]) : "memory");
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(g1_empty(gs));
+                    dwg_bar_sync(bar_id);                                         // the whole halo tile is written
+                } else {
+                    mbar_wait(e_full(s), (n / (uint32_t)p.e_stages) & 1u);
+                }
+                unsigned long long acc[8][2];
+                dw_accumulate<K>(st, st + (uint32_t)p.off_dww + (uint32_t)(q * 16), tbl, oy, x0, acc);
+                // the halo tile has been consumed (every load fed an FMA above); the stage may be refilled
+                if (p.mode == 0) {
+                    if (leader) { if (p.dw_groups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+                    dwg_bar_sync(bar_id);
+                } else {
+                    mbar_wait(d_empty(ds), ((n >> 1) & 1u) ^ 1u);
+                }
+                dw_store(d_base, st + (uint32_t)p.off_dwb + (uint32_t)(q * 16), tbl, oy, x0, acc);
+                fence_proxy_async_smem();
+                if (p.mode == 0) {
+                    dwg_bar_sync(bar_id);
+                    if (leader) { tma_store_4d(&tm_y, d_base, j * 64, tc.x0, tc.y0, tc.img); tma_store_commit(); }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(e_empty(s));
+                } else {
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(d_full(ds)); mbar_arrive(e_empty(s)); }
+                }
+            }
+        }
+        if (p.mode == 0 && leader) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1 && p.mode >= 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+}  // namespace
+}  // namespace yms
+
+using namespace yms;
+
+struct yms_ms_plan {
+    CUtensorMap tm_e, tm_dww, tm_dwb, tm_w2, tm_y, tm_x, tm_x2, tm_w1;
+    MsParams kp;
+    int grid, threads;
+    size_t smem;
+    double flops, bytes;
+};
+
+namespace yms {
+namespace {
+
+int encode_plain(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* addr, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, const char* what) {
+    auto fn = get_encode();
+    if (!fn) return fail(YMS_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    uint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(addr), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(YMS_E_DRIVER, "cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+    return 0;
+}
+
+template <int K> cudaError_t set_attr() {
+    return cudaFuncSetAttribute(ms_layer_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+}
+
+}  // namespace
+}  // namespace yms
+
+extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
+    if (!q || !out) return fail(YMS_E_ARG, "ms: null argument");
+    *out = nullptr;
+    const int k = q->ksize;
+    if (k != 3 && k != 5 && k != 7 && k != 9) return fail(YMS_E_UNSUPPORTED, "ms: ksize must be 3, 5, 7 or 9");
+    if (q->mode < 0 || q->mode > 2) return fail(YMS_E_ARG, "ms: mode must be 0, 1 or 2");
+    if (q->batch <= 0 || q->h <= 0 || q->w <= 0 || q->e_ch <= 0 || (q->e_ch % 8)) return fail(YMS_E_ARG, "ms: bad sizes (channels % 8 == 0)");
+    auto al16 = [](const void* p) { return p && ((uintptr_t)p & 15) == 0; };
+    if (!al16(q->dw_weight) || !al16(q->dw_bias) || !al16(q->y) || (q->y_pixel_stride % 8)) return fail(YMS_E_ARG, "ms: null or misaligned pointer");
+    if (q->mode != 2 && (!al16(q->e) || (q->e_pixel_stride % 8) || q->e_pixel_stride < q->e_ch)) return fail(YMS_E_ARG, "ms: bad expanded input");
+    if (q->mode >= 1) {
+        if (q->c_out <= 0 || (q->c_out % 16) || q->c_out > 256) return fail(YMS_E_UNSUPPORTED, "ms: c_out must be a multiple of 16, <= 256");
+        if (!al16(q->w2) || !q->bias2 || q->y_pixel_stride < q->c_out) return fail(YMS_E_ARG, "ms: bad pw2 operands");
+    } else if (q->y_pixel_stride < q->e_ch) return fail(YMS_E_ARG, "ms: bad output pixel stride");
+    if (q->mode == 2) {
+        if (q->c_in <= 0 || (q->c_in % 8) || q->c_in2 < 0 || (q->c_in2 % 8)) return fail(YMS_E_ARG, "ms: bad pw1 channels");
+        if (!al16(q->x) || (q->x_pixel_stride % 8) || q->x_pixel_stride < q->c_in || !al16(q->w1) || !q->bias1) return fail(YMS_E_ARG, "ms: bad pw1 operands");
+        if (q->c_in2 && (!al16(q->x2) || (q->x2_pixel_stride % 8) || q->x2_pixel_stride < q->c_in2)) return fail(YMS_E_ARG, "ms: bad second pw1 source");
+        if (q->e_ch > 1024) return fail(YMS_E_UNSUPPORTED, "ms: fused pw1 needs e_ch <= 1024");
+    }
+    yms_ms_plan* pl = new (std::nothrow) yms_ms_plan();
+    if (!pl) return fail(YMS_E_ARG, "ms: out of host memory");
+    MsParams& kp = pl->kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.mode = q->mode; kp.ksize = k;
+    kp.tiles_x = ceil_div(q->w, kTW); kp.tiles_y = ceil_div(q->h, kTH); kp.batch = q->batch;
+    const long long total = (long long)kp.tiles_x * kp.tiles_y * q->batch;
+    if (total > 0x3fffffffLL) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: too many tiles"); }
+    kp.total_tiles = (int)total;
+    kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
+    kp.e_ch = q->e_ch; kp.n_chunks = ceil_div(q->e_ch, 64);
+    kp.tail_ksteps = ((q->e_ch - (kp.n_chunks - 1) * 64) + 15) >> 4;
+    kp.c_out = q->mode >= 1 ? q->c_out : 0; kp.block_n = kp.c_out; kp.act2 = q->act2 ? 1 : 0;
+    kp.bias2 = q->bias2; kp.bias1 = q->bias1;
+    kp.img_w = q->w; kp.img_h = q->h;
+    const int hwx = kTW + k - 1, hwy = kTH + k - 1;
+    kp.hp = hwx * hwy; kp.mt = ceil_div(kp.hp, 128);
+    kp.c_in1 = q->c_in; kp.c_in2 = q->c_in2;
+    kp.kb1 = q->mode == 2 ? ceil_div(q->c_in, 64) : 0; kp.kb2 = q->mode == 2 ? ceil_div(q->c_in2, 64) : 0;
+    kp.w1_tile_bytes = 64 * 128;
+    kp.w2_tile_bytes = kp.block_n * 128;
+    // one e stage: halo rows | depthwise weights [k*k][64] f32 | bias [64] f32 | (streamed pw2 weight chunk)
+    const int e_rows = hwy * kRowPitchBytes;
+    kp.off_dww = e_rows; kp.off_dwb = e_rows + k * k * 256;
+    int stage = kp.off_dwb + 256;
+    stage = (stage + 1023) & ~1023;
+    kp.off_w2 = stage;
+    // TMEM: pw2 accumulators (2 stages) then, in mode 2, the pw1 accumulators (2 stages x mt x 64 columns)
+    int cols = 0;
+    if (q->mode >= 1) {
+        kp.acc_stride = kp.block_n <= 32 ? 32 : (kp.block_n <= 64 ? 64 : (kp.block_n <= 128 ? 128 : 256));
+        cols = 2 * kp.acc_stride;
+        if (q->mode == 2) { kp.g1_base = cols; kp.g1_stride = kp.mt * 64; cols += 2 * kp.g1_stride; }
+        if (cols > 512) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: accumulators exceed the 512 TMEM columns"); }
+        int pow2 = 32; while (pow2 < cols) pow2 <<= 1;
+        kp.tmem_cols = pow2;
+    }
+    kp.bias_pad = q->mode == 2 ? 256 + kp.n_chunks * 64 : 256;
+    const int kbt = kp.kb1 + kp.kb2;
+    kp.x_kb_stride = (kp.hp * 128 + 1023) & ~1023;
+    const int x_bytes = q->mode == 2 ? kbt * kp.x_kb_stride : 0;
+    const int w1_bytes = q->mode == 2 ? kp.n_chunks * kbt * kp.w1_tile_bytes : 0;
+    const int out_bytes = q->mode >= 1 ? kDTile : 0;
+    const int tail_bytes = kp.bias_pad * 4 + (2 * kMaxE + 16) * 8 + 16;
+    const int fixed = x_bytes + 2 * kDTile + out_bytes + w1_bytes + tail_bytes + 1024 /* alignment slack */;
+    const int w2_all = kp.n_chunks * kp.w2_tile_bytes;
+    int budget = kSmemLimit - fixed;
+    kp.w2_resident = 0;
+    if (q->mode >= 1) {
+        // resident pw2 weights when at least 2 (mode 2) / 3 stages remain, else streamed with the halo chunk
+        const int need = (q->mode == 2 ? 2 : 3) * stage;
+        if (budget - w2_all >= need) { kp.w2_resident = 1; budget -= w2_all; }
+        else stage += kp.w2_tile_bytes;
+    }
+    kp.stage_bytes = stage;
+    int stages = budget / stage;
+    if (stages > kMaxE) stages = kMaxE;
+    if (stages < 2) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: the layer does not fit in shared memory (use the unfused kernels)"); }
+    kp.e_stages = stages;
+    kp.dw_groups = 2;
+    kp.stage_tx = (uint32_t)((q->mode != 2 ? hwx * hwy * 128 : 0) + k * k * 256 + 256 + ((q->mode >= 1 && !kp.w2_resident) ? kp.w2_tile_bytes : 0));
+    kp.so_x = 0;
+    kp.so_e = x_bytes;
+    kp.so_d = kp.so_e + stages * stage;
+    kp.so_w2 = kp.so_d + 2 * kDTile;
+    kp.so_out = kp.so_w2 + (kp.w2_resident ? w2_all : 0);
+    kp.so_w1 = kp.so_out + out_bytes;
+    kp.so_bias = kp.so_w1 + w1_bytes;
+    pl->smem = (size_t)kp.so_bias + tail_bytes + 1024;
+    if (pl->smem > (size_t)kSmemLimit) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: shared-memory budget exceeded"); }
+    pl->grid = kp.total_tiles < kNumSMs ? kp.total_tiles : kNumSMs;
+    pl->threads = 64 + 128 + kp.dw_groups * kGroupThreads;
+
+    int rc = 0;
+    const uint64_t W = (uint64_t)q->w, H = (uint64_t)q->h, N = (uint64_t)q->batch;
+    auto act_map = [&](CUtensorMap* m, const void* ptr, int c, int64_t ps, int bx, int by, const char* what) {
+        uint64_t dims[4] = {(uint64_t)c, W, H, N};
+        uint64_t strides[3] = {(uint64_t)ps * 2, (uint64_t)ps * 2 * W, (uint64_t)ps * 2 * W * H};
+        uint32_t box[4] = {64, (uint32_t)bx, (uint32_t)by, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, what);
+    };
+    if (q->mode != 2) rc = act_map(&pl->tm_e, q->e, q->e_ch, q->e_pixel_stride, hwx, 1, "ms e");
+    else {
+        rc = act_map(&pl->tm_x, q->x, q->c_in, q->x_pixel_stride, hwx, hwy, "ms x");
+        if (!rc && q->c_in2) rc = act_map(&pl->tm_x2, q->x2, q->c_in2, q->x2_pixel_stride, hwx, hwy, "ms x2");
+        if (!rc) {
+            const uint64_t K1 = (uint64_t)(q->c_in + q->c_in2);
+            uint64_t dims[3] = {K1, (uint64_t)q->e_ch, 1};
+            uint64_t strides[2] = {K1 * 2, K1 * 2 * (uint64_t)q->e_ch};
+            uint32_t box[3] = {64, 64, 1};
+            uint32_t es[3] = {1, 1, 1};
+            rc = encode_map(&pl->tm_w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q->w1, dims, strides, box, es, "ms w1");
+        }
+    }
+    if (q->mode != 2) { pl->tm_x = pl->tm_e; pl->tm_w1 = pl->tm_e; }
+    if (q->mode != 2 || !q->c_in2) pl->tm_x2 = pl->tm_x;
+    if (q->mode == 2) pl->tm_e = pl->tm_x;
+    if (!rc) rc = act_map(&pl->tm_y, q->y, q->mode >= 1 ? q->c_out : q->e_ch, q->y_pixel_stride, kTW, kTH, "ms y");
+    if (!rc) {
+        uint64_t dims[2] = {(uint64_t)q->e_ch, (uint64_t)(k * k)};
+        uint64_t strides[1] = {(uint64_t)q->e_ch * 4};
+        uint32_t box[2] = {64, (uint32_t)(k * k)};
+        rc = encode_plain(&pl->tm_dww, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, q->dw_weight, dims, strides, box, "ms dw weight");
+    }
+    if (!rc) {
+        uint64_t dims[2] = {(uint64_t)q->e_ch, 1};
+        uint64_t strides[1] = {(uint64_t)q->e_ch * 4};
+        uint32_t box[2] = {64, 1};
+        rc = encode_plain(&pl->tm_dwb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, q->dw_bias, dims, strides, box, "ms dw bias");
+    }
+    if (!rc && q->mode >= 1) {
+        uint64_t dims[3] = {(uint64_t)q->e_ch, (uint64_t)q->c_out, 1};
+        uint64_t strides[2] = {(uint64_t)q->e_ch * 2, (uint64_t)q->e_ch * 2 * (uint64_t)q->c_out};
+        uint32_t box[3] = {64, (uint32_t)kp.block_n, 1};
+        uint32_t es[3] = {1, 1, 1};
+        rc = encode_map(&pl->tm_w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q->w2, dims, strides, box, es, "ms w2");
+    } else if (!rc) pl->tm_w2 = pl->tm_y;
+    if (rc) { delete pl; return rc; }
+
+    const double px = (double)q->batch * q->h * q->w;
+    pl->flops = 2.0 * px * q->e_ch * k * k;
+    pl->bytes = (double)(k * k + 1) * q->e_ch * 4.0;
+    if (q->mode == 0) pl->bytes += 2.0 * px * q->e_ch * 2.0;
+    if (q->mode == 1) { pl->flops += 2.0 * px * q->e_ch * q->c_out; pl->bytes += 2.0 * px * (q->e_ch + q->c_out) + 2.0 * q->e_ch * q->c_out; }
+    if (q->mode == 2) {
+        const double K1 = q->c_in + q->c_in2;
+        pl->flops += 2.0 * px * q->e_ch * (q->c_out + K1);
+        pl->bytes += 2.0 * px * (K1 + q->c_out) + 2.0 * q->e_ch * (q->c_out + K1);
+    }
+
+    cudaError_t e = cudaSuccess;        // per call: the attribute is per device, and plan creation is not a hot path
+    switch (k) {
+        case 3: e = set_attr<3>(); break;
+        case 5: e = set_attr<5>(); break;
+        case 7: e = set_attr<7>(); break;
+        default: e = set_attr<9>(); break;
+    }
+    if (e != cudaSuccess) { delete pl; return fail((int)e, "ms: smem attribute: %s", cudaGetErrorString(e)); }
+    *out = pl;
+    return 0;
+}
+
+extern "C" int yms_ms_plan_run(const yms_ms_plan* pl, void* stream) {
+    if (!pl) return fail(YMS_E_ARG, "ms: null plan");
+    cudaError_t le;
+    cudaStream_t st = (cudaStream_t)stream;
+#define YMS_MS_LAUNCH(K) le = launch_pdl(ms_layer_kernel<K>, pl->grid, pl->threads, pl->smem, st, pl->tm_e, pl->tm_dww, pl->tm_dwb, pl->tm_w2, \
+                                         pl->tm_y, pl->tm_x, pl->tm_x2, pl->tm_w1, pl->kp)
+    switch (pl->kp.ksize) {
+        case 3: YMS_MS_LAUNCH(3); break;
+        case 5: YMS_MS_LAUNCH(5); break;
+        case 7: YMS_MS_LAUNCH(7); break;
+        default: YMS_MS_LAUNCH(9); break;
+    }
+#undef YMS_MS_LAUNCH
+    if (le != cudaSuccess) return fail((int)le, "ms_layer_kernel launch: %s", cudaGetErrorString(le));
+    return check_launch("ms_layer_kernel");
+}
+
+extern "C" int yms_ms_plan_destroy(yms_ms_plan* pl) {
+    delete pl;
+    return 0;
+}
+
+extern "C" int yms_ms_plan_cost(const yms_ms_plan* pl, double* flops, double* bytes) {
+    if (!pl) return fail(YMS_E_ARG, "ms: null plan");
+    if (flops) *flops = pl->flops;
+    if (bytes) *bytes = pl->bytes;
+    return 0;
+}
+
+/* Conv(c, c, k, 1, k//2, groups=c) of components.py:69-77: mode 0 of the kernel above (tensor maps are encoded per call; inside a
+ * captured CUDA graph that cost is paid once). */
+extern "C" int yms_dwconv(const void* x, int64_t xps, int batch, int h, int w, int channels, int ksize,
+                          const float* weight, const float* bias, void* y, int64_t yps, void* stream) {
+    yms_ms_params q;
+    memset(&q, 0, sizeof(q));
+    q.mode = 0; q.batch = batch; q.h = h; q.w = w; q.ksize = ksize; q.e_ch = channels;
+    q.e = x; q.e_pixel_stride = xps; q.y = y; q.y_pixel_stride = yps;
+    q.dw_weight = weight; q.dw_bias = bias;
+    yms_ms_plan* pl = nullptr;
+    int rc = yms_ms_plan_create(&q, &pl);
+    if (rc) return rc;
+    rc = yms_ms_plan_run(pl, stream);
+    delete pl;
+    return rc;
+}

@@ -186,6 +186,13 @@ class Program:
         best.desc = default_plan.desc + (f" [v{best.variant}]" if best.variant else "")
         return best
 
+    def ms_layer(self, plan: "ops.MsLayerPlan"):
+        """A fused MS-Block layer (ops.MsLayerPlan): one launch, costed like a convolution plan."""
+        self.plans.append(plan)
+        self._push(plan.run, plan.desc)
+        self.flops += plan.flops
+        self.bytes += plan.bytes
+
     def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0, name: str = "op"):
         self._push(fn, name)
         self.costs[len(self.steps) - 1] = (flops, nbytes)

@@ -30,6 +30,9 @@ from .engine import Program, fold_conv_bn, nchw_f32_to_nhwc_bf16, nhwc_to_nchw_f
 
 FUSE_DECODE = os.environ.get("YMS_FUSE_DECODE", "1") != "0"    # decode in the epilogue of the head's final convs (YOLOv8 programs)
 
+MS_FUSE = int(os.environ.get("YMS_MS_FUSE", "2"))               # MS-Block layers: 2 = pw1 -> depthwise -> pw2 in one kernel where it
+                                                                # fits, 1 = depthwise -> pw2, 0 = three launches
+
 FUSE_UPSAMPLE = os.environ.get("YMS_FUSE_UPSAMPLE", "1") != "0"  # neck: upsample + concat inside the consumer C2f's first 1x1 conv
 
 _VERSIONS = {  # depth, width, ratio  (components.py:193-209)
@@ -93,6 +96,12 @@ class Conv(_Compiled):
         return fold_conv_bn(self.conv.weight.detach(), self.bn.weight.detach(), self.bn.bias.detach(),
                             self.bn.running_mean, self.bn.running_var, self.bn.eps)
 
+    def dw_folded(self):
+        """Depthwise unit: (f32 [k*k, C] tap-major weights, f32 [C] bias) with BN folded."""
+        w, b = self.folded()
+        co, k = self.conv.out_channels, self.conv.kernel_size[0]
+        return w.reshape(co, k * k).t().contiguous(), b.contiguous()
+
     @property
     def has_act(self):
         return isinstance(self.activation, nn.SiLU)
@@ -113,11 +122,9 @@ class Conv(_Compiled):
                 w = torch.cat([w, w], 1)
             P.conv(pack_weight(w), b.contiguous(), x, out, ksize=k, stride=s, act=self.has_act, residual=residual, x2=x2)
         elif conv.groups == conv.in_channels == co and s == 1 and self.has_act and residual is None and x2 is None:
-            wk = w.reshape(co, k * k).t().contiguous()          # [k*k, C]
-            bb = b.contiguous()
+            wk, bb = self.dw_folded()
             P.hold(wk, bb)
-            P.add(lambda: ops.dwconv(x, wk, bb, out, k), nbytes=4.0 * bsz * h * wd * co, flops=2.0 * bsz * h * wd * co * k * k,
-                  name=f"dwconv{k}x{k} {co} @{h}x{wd}")
+            P.ms_layer(ops.MsLayerPlan(0, out, k, wk, bb, e=x))
         else:
             raise YmsError("Conv: only groups=1 or depthwise stride-1 convolutions are implemented")
         return out
@@ -208,6 +215,44 @@ class MSBlock(_Compiled):
         self.branches = nn.ModuleList(branches)
         self.out_conv = Conv(3 * c, out_channels, kernel_size=1, stride=1, padding=0)
 
+    def _emit_layer(self, P, layer, src, src2, dst):
+        """One branch layer pw1 -> dw -> pw2 over src (+ src2: conv(src + src2) as a K-concatenated GEMM with repeated
+        weights).  Fused as far as the layer fits the kernel's budgets (csrc/ms_fused.cu): whole layer, dw -> pw2, or unfused."""
+        k = self.kernel_size
+        b, hh, ww, c = src.shape
+        wd, bd = layer.dw.dw_folded()
+        w2f, b2 = layer.pw2.folded()
+        w2 = w2f.reshape(w2f.shape[0], -1).contiguous().to(torch.bfloat16)
+        b2 = b2.contiguous()
+        if dst is None:
+            dst = P.buf(b, hh, ww, w2.shape[0])
+        plain = layer.pw1.has_act and layer.dw.has_act and layer.dw.conv.stride[0] == 1
+        if MS_FUSE >= 2 and plain:
+            w1f, b1 = layer.pw1.folded()
+            w1 = w1f.reshape(w1f.shape[0], -1)
+            if src2 is not None:
+                w1 = torch.cat([w1, w1], 1)
+            w1 = w1.contiguous().to(torch.bfloat16)
+            b1 = b1.contiguous()
+            try:
+                plan = ops.MsLayerPlan(2, dst, k, wd, bd, x=src, x2=src2, w1=w1, bias1=b1, w2=w2, bias2=b2, act2=layer.pw2.has_act)
+                P.hold(wd, bd, w1, b1, w2, b2)
+                P.ms_layer(plan)
+                return dst
+            except YmsError:
+                pass
+        e = layer.pw1.emit(P, src, x2=src2, dup_k=src2 is not None)
+        if MS_FUSE >= 1 and plain:
+            try:
+                plan = ops.MsLayerPlan(1, dst, k, wd, bd, e=e, w2=w2, bias2=b2, act2=layer.pw2.has_act)
+                P.hold(wd, bd, w2, b2)
+                P.ms_layer(plan)
+                return dst
+            except YmsError:
+                pass
+        d = layer.dw.emit(P, e)
+        return layer.pw2.emit(P, d, out=dst)
+
     def emit(self, P, x, out=None):
         c = self.mid_channels
         b, hh, ww, _ = x.shape
@@ -218,13 +263,11 @@ class MSBlock(_Compiled):
             xi = y[..., (bi + 1) * c:(bi + 2) * c]
             t = None
             for li, layer in enumerate(layers):
-                if li == 0:   # conv(x_i + y_{i-1}) = K-concatenated GEMM with repeated weights
-                    e = layer.pw1.emit(P, xi, x2=prev, dup_k=True)
-                else:
-                    e = layer.pw1.emit(P, t)
-                d = layer.dw.emit(P, e)
                 dst = tail[..., bi * c:(bi + 1) * c] if li == len(layers) - 1 else None
-                t = layer.pw2.emit(P, d, out=dst)
+                if li == 0:   # conv(x_i + y_{i-1}) = K-concatenated GEMM with repeated weights
+                    t = self._emit_layer(P, layer, xi, prev, dst)
+                else:
+                    t = self._emit_layer(P, layer, t, None, dst)
             prev = t
         return self.out_conv.emit(P, y[..., :c], out=out, x2=tail)
 

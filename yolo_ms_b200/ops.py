@@ -15,10 +15,10 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvParams, DecodeFusion, YmsError, check
+from ._lib import ConvParams, DecodeFusion, MsParams, YmsError, check
 
-__all__ = ["ConvPlan", "stem_conv", "stem_conv_u8", "dwconv", "sppf_pool", "upsample2x", "head_decode",
-           "select_candidates", "nms_batched", "gather_detections", "YmsError"]
+__all__ = ["ConvPlan", "MsLayerPlan", "stem_conv", "stem_conv_u8", "dwconv", "sppf_pool", "upsample2x", "head_decode",
+           "select_candidates", "nms_batched", "gather_detections", "PostBuffers", "YmsError"]
 
 
 def _stream() -> int:
@@ -141,6 +141,80 @@ class ConvPlan:
             self._h = None
 
 
+class MsLayerPlan:
+    """One MS-Block branch layer  pw1 (1x1) -> depthwise k x k -> pw2 (1x1)  bound to fixed NHWC bf16 buffers
+    (yms_ms_plan_create).  mode 0: depthwise only (e -> y); mode 1: depthwise -> pw2 (e -> y); mode 2: the whole layer
+    (x [+ x2] -> y), the expanded tensors never reach HBM.
+
+    dw_weight f32 [k*k, E], dw_bias f32 [E]; w1 bf16 [E, c_in (+ c_in2)], bias1 f32 [E]; w2 bf16 [c_out, E], bias2 f32 [c_out].
+    Raises YmsError (YMS_E_UNSUPPORTED) when the mode does not fit the hardware budgets -- callers fall back to a lower mode."""
+
+    def __init__(self, mode, y, ksize, dw_weight, dw_bias, e=None, x=None, x2=None, w1=None, bias1=None, w2=None, bias2=None,
+                 act2=True):
+        _need_cuda(y, dw_weight, dw_bias, e, x, x2, w1, bias1, w2, bias2)
+        src = e if mode != 2 else x
+        if src is None or src.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
+            raise YmsError("ms layer: activations must be bf16")
+        b, h, w, _ = src.shape
+        e_ch = dw_weight.shape[1]
+        if tuple(dw_weight.shape) != (ksize * ksize, e_ch) or dw_weight.dtype != torch.float32 or not dw_weight.is_contiguous() \
+                or dw_bias.dtype != torch.float32 or tuple(dw_bias.shape) != (e_ch,):
+            raise YmsError("ms layer: dw_weight must be contiguous f32 [k*k, E] and dw_bias f32 [E]")
+        if tuple(y.shape[:3]) != (b, h, w):
+            raise YmsError("ms layer: output spatial shape mismatch")
+        p = MsParams()
+        p.mode, p.batch, p.h, p.w, p.ksize, p.e_ch = int(mode), b, h, w, int(ksize), e_ch
+        p.act2 = int(bool(act2))
+        p.y, p.y_pixel_stride = y.data_ptr(), _pixel_stride(y)
+        p.dw_weight, p.dw_bias = dw_weight.data_ptr(), dw_bias.data_ptr()
+        if mode != 2:
+            if e.shape[-1] != e_ch:
+                raise YmsError("ms layer: e must have E channels")
+            p.e, p.e_pixel_stride = e.data_ptr(), _pixel_stride(e)
+        else:
+            c_in, c_in2 = x.shape[-1], (0 if x2 is None else x2.shape[-1])
+            if w1 is None or w1.dtype != torch.bfloat16 or tuple(w1.shape) != (e_ch, c_in + c_in2) or not w1.is_contiguous() \
+                    or bias1 is None or bias1.dtype != torch.float32:
+                raise YmsError(f"ms layer: w1 must be contiguous bf16 [{e_ch},{c_in + c_in2}] and bias1 f32")
+            p.c_in, p.c_in2 = c_in, c_in2
+            p.x, p.x_pixel_stride = x.data_ptr(), _pixel_stride(x)
+            if x2 is not None:
+                p.x2, p.x2_pixel_stride = x2.data_ptr(), _pixel_stride(x2)
+            p.w1, p.bias1 = w1.data_ptr(), bias1.data_ptr()
+        if mode >= 1:
+            c_out = y.shape[-1]
+            if w2 is None or w2.dtype != torch.bfloat16 or tuple(w2.shape) != (c_out, e_ch) or not w2.is_contiguous() \
+                    or bias2 is None or bias2.dtype != torch.float32:
+                raise YmsError(f"ms layer: w2 must be contiguous bf16 [{c_out},{e_ch}] and bias2 f32")
+            p.c_out = c_out
+            p.w2, p.bias2 = w2.data_ptr(), bias2.data_ptr()
+        elif y.shape[-1] != e_ch:
+            raise YmsError("ms layer: mode 0 output must have E channels")
+        self._keep = (y, dw_weight, dw_bias, e, x, x2, w1, bias1, w2, bias2)
+        self.mode = int(mode)
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        check(self._lib.yms_ms_plan_create(C.byref(p), C.byref(self._h)), "yms_ms_plan_create")
+        fl, by = C.c_double(), C.c_double()
+        self._lib.yms_ms_plan_cost(self._h, C.byref(fl), C.byref(by))
+        self.flops, self.bytes = fl.value, by.value
+        what = {0: f"dw{ksize}x{ksize} {e_ch}", 1: f"dw{ksize}x{ksize} {e_ch} ->pw2 {y.shape[-1]}",
+                2: f"ms-layer {'' if x is None else x.shape[-1]}{'' if x2 is None else '+' + str(x2.shape[-1])}->{e_ch} dw{ksize}x{ksize} ->{y.shape[-1]}"}
+        self.desc = f"{what[self.mode]} @{h}x{w}"
+
+    def run(self) -> None:
+        check(self._lib.yms_ms_plan_run(self._h, _stream()), "yms_ms_plan_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.yms_ms_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
 def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torch.Tensor) -> None:
     """x f32 NCHW [B,3,H,W]; weight f32 [c_out,3,3,3] (BN folded); y bf16 [B,H/2,W/2,c_out]."""
     _need_cuda(x, weight, bias, y)
@@ -241,36 +315,56 @@ def select_candidates(pred: torch.Tensor):
     return boxes, scores, labels
 
 
+class PostBuffers:
+    """Pre-allocated outputs + workspace of the post-process for a fixed [B, N] candidate shape: keep / count (yms_nms_batched),
+    its workspace, and optionally the padded detection rows (yms_gather_detections).  Lets a whole step be captured in ONE
+    CUDA graph with zero allocations per call."""
+
+    def __init__(self, batch: int, n: int, device, max_det: Optional[int] = None):
+        lib = _lib.load()
+        self.keep = torch.empty((batch, n), dtype=torch.int32, device=device)
+        self.count = torch.empty((batch,), dtype=torch.int32, device=device)
+        self.ws_bytes = lib.yms_nms_workspace_bytes(batch, n)
+        self.ws = torch.empty((max(self.ws_bytes, 8),), dtype=torch.uint8, device=device)
+        self.dets = None if max_det is None else torch.empty((batch, max_det, 6), dtype=torch.float32, device=device)
+
+
+def _f32(v: float) -> float:
+    """float(np.float32(v)): the reference compares fp32 scores with the Python scalar cast to fp32 (no device work)."""
+    return C.c_float(v).value
+
+
 def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, conf_thr: float, iou_thr: float,
-                num_classes: int, n_valid: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                num_classes: int, n_valid: Optional[torch.Tensor] = None, out: Optional[PostBuffers] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
     """boxes f32 [B,N,4] xyxy, scores f32 [B,N], labels int32 [B,N].
-    Returns (keep int32 [B,N] padded with -1, keep_count int32 [B])."""
+    Returns (keep int32 [B,N] padded with -1, keep_count int32 [B]); with `out` nothing is allocated."""
     _need_cuda(boxes, scores, labels, n_valid)
     if boxes.dtype != torch.float32 or scores.dtype != torch.float32 or labels.dtype != torch.int32:
         raise YmsError("nms_batched: dtypes must be f32/f32/int32")
     boxes, scores, labels = boxes.contiguous(), scores.contiguous(), labels.contiguous()
     b, n = scores.shape
-    keep = torch.empty((b, n), dtype=torch.int32, device=boxes.device)
-    count = torch.empty((b,), dtype=torch.int32, device=boxes.device)
-    lib = _lib.load()
-    ws_bytes = lib.yms_nms_workspace_bytes(b, n)
-    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=boxes.device)
+    if out is None:
+        out = PostBuffers(b, n, boxes.device)
+    elif tuple(out.keep.shape) != (b, n):
+        raise YmsError("nms_batched: `out` was allocated for another shape")
     nv = None
     if n_valid is not None:
         nv = n_valid.to(torch.int32).contiguous()
-    # float(np.float32(conf)): the reference compares fp32 scores with the Python scalar cast to fp32
-    conf32 = float(torch.tensor(conf_thr, dtype=torch.float32))
-    check(lib.yms_nms_batched(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(),
-                              None if nv is None else nv.data_ptr(), b, n, num_classes, conf32, float(iou_thr),
-                              keep.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "yms_nms_batched")
-    return keep, count
+    check(_lib.load().yms_nms_batched(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(),
+                                      None if nv is None else nv.data_ptr(), b, n, num_classes, _f32(conf_thr), float(iou_thr),
+                                      out.keep.data_ptr(), out.count.data_ptr(), out.ws.data_ptr(), out.ws_bytes, _stream()),
+          "yms_nms_batched")
+    return out.keep, out.count
 
 
-def gather_detections(boxes, scores, labels, keep, count, max_det: int) -> torch.Tensor:
+def gather_detections(boxes, scores, labels, keep, count, max_det: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """-> f32 [B, max_det, 6] rows (x1,y1,x2,y2,score,label); unused rows have label -1."""
     _need_cuda(boxes, scores, labels, keep, count)
     b, n = scores.shape
-    dets = torch.empty((b, max_det, 6), dtype=torch.float32, device=boxes.device)
+    dets = out if out is not None else torch.empty((b, max_det, 6), dtype=torch.float32, device=boxes.device)
+    if tuple(dets.shape) != (b, max_det, 6) or dets.dtype != torch.float32 or not dets.is_contiguous():
+        raise YmsError("gather_detections: `out` must be contiguous f32 [B, max_det, 6]")
     check(_lib.load().yms_gather_detections(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr(),
                                             count.data_ptr(), b, n, max_det, dets.data_ptr(), _stream()),
           "yms_gather_detections")
