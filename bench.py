@@ -4,17 +4,23 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU
 
-Workload (BASELINE.json configs[1]): YOLO-MS-S (`version='s'`, 80 classes), 640x640, batch 32 per
-GPU, bf16 storage / fp32 accumulate, synthetic ImageNet-normalised images, seeded random weights
-with calibrated BN statistics.  One "step" = one batch through YOLOv8.detect(): stem + the conv /
-glue launches of the program (one CUDA graph; the head decode runs in the epilogue of its last six convs) + batched NMS.  N > 1: one process per GPU (torchrun),
-the batch is sharded by image, no collective on the data path ("scaling": "weak").
+Headline workload (BASELINE.json configs[1]): YOLO-MS-S (`version='s'`, 80 classes), 640x640, batch 32 per GPU, bf16
+storage / fp32 accumulate, synthetic images, seeded random weights with calibrated BN statistics.  One "step" = one batch
+through YOLOv8.detect(): stem + the conv / glue launches of the program (the head decode runs in the epilogue of its last six
+convs) + batched NMS (+ the gather of the kept detections in the e2e leg) -- replayed as ONE CUDA graph per input buffer.
+N > 1: one process per GPU (torchrun), the batch is sharded by image, no collective on the data path ("scaling": "weak").
+
+The same run also puts the other BASELINE configs on the record (`configs` object): the MS-Block model (`block='ms'`),
+`m` / batch 256 sharded over the GPUs, the decode + NMS operator stress, `s` at 1280x1280 -- each a short leg with its own
+numbers -- plus the same-box library bar (`gpu_library_baseline`: the reference's ATen ops through cuDNN bf16 channels_last +
+its per-class torchvision.ops.nms loop) and a post-run self-check (`verified`).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -22,9 +28,8 @@ import sys
 import threading
 import time
 
-# The e2e leg drives three streams (upload, compute, read-back) next to a CUDA graph with parallel branches.  With the default
-# 8 hardware work queues, unrelated streams can share a queue and serialise behind each other (false dependencies): the compute
-# stream's GPU time per step then varies from run to run (1.7 - 3.7 ms observed).  Must be set before CUDA is initialised.
+# The e2e leg drives three streams (upload, compute, read-back) next to CUDA graphs with parallel branches.  With the default
+# 8 hardware work queues, unrelated streams can share a queue and serialise behind each other (false dependencies).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +38,7 @@ sys.path.insert(0, ROOT)
 METRIC = "images/sec (640^2, fwd+NMS)"
 UNIT = "images/s"
 CONF, IOU = 0.25, 0.45
-MAX_DET = None     # the reference has no max-det: every kept detection is read back ([B, A, 6] padded + counts)
+STRIDES = [8.0, 16.0, 32.0]
 
 
 def _peaks():
@@ -92,6 +97,30 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node BEFORE pinned buffers are allocated (first touch puts
+    them on that node), so that 8 ranks do not stage through one socket.  Best effort; returns a description."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"pci": bus, "numa_node": node, "bound": False}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"pci": bus, "numa_node": node, "cpus": len(allowed), "bound": bool(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": str(e)[:80]}
+
+
 # ================================================================================================
 # reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
 # ================================================================================================
@@ -102,7 +131,7 @@ def cpu_reference_run(version, hw, images_per_step, steps, warmup):
     from oracle import postprocess as PP
     from oracle import weights as W
     from oracle import yolov8_oracle as O
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     sd = W.calibrated_state_dict(version, seed=1)
     g8 = torch.Generator().manual_seed(11)
@@ -148,248 +177,485 @@ def run_reference(args):
 # ================================================================================================
 # native arm
 # ================================================================================================
-def run_native(args):
-    import torch
-    import torch.distributed as dist
-    from yolo_ms_b200 import YOLOv8, launch_count, ops, synth
-    from yolo_ms_b200.dist import max_over_ranks
+class Ctx:
+    """Per-process CUDA / distributed state shared by the legs."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, HW = args.batch, args.hw
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(self.local)
+        torch.set_num_threads(max(1, min(8, len(os.sched_getaffinity(0)) // max(1, min(self.world, 8)))))
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    model = YOLOv8(version=args.version, num_classes=80, block=args.block)
-    model.load_state_dict(synth.synthetic_state_dict(model, args.version, args.block, seed=1))
-    model = model.to(dev).eval()
-    model.head.stride = torch.tensor([8.0, 16.0, 32.0])
-    x_host = synth.make_images(B, HW, HW, seed=7 + rank).pin_memory()
-    x = x_host.to(dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def step(inp):
-        return model.detect(inp, CONF, IOU)
+    def max_over_ranks(self, v):
+        from yolo_ms_b200.dist import max_over_ranks
+        return max_over_ranks(v, self.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        out = step(x)
+def build_model(ctx, version, block, num_classes=80):
+    from yolo_ms_b200 import YOLOv8, synth
+    torch = ctx.torch
+    model = YOLOv8(version=version, num_classes=num_classes, block=block)
+    model.load_state_dict(synth.synthetic_state_dict(model, version, block, seed=1))
+    model = model.to(ctx.dev).eval()
+    model.head.stride = torch.tensor(STRIDES)
+    return model
+
+
+def free(ctx, *objs):
+    del objs
+    gc.collect()
+    ctx.torch.cuda.empty_cache()
+
+
+def timed_value(ctx, model, x, steps, warmup, sampler=None):
+    """Device-resident throughput: `steps` x detect(x) between CUDA events (graph replay after the second call)."""
+    torch = ctx.torch
+    for _ in range(max(warmup, 3)):
+        out = model.detect(x, CONF, IOU)
     torch.cuda.synchronize()
-    prog = list(model._programs().values())[0][0]
-    fused = prog.decoded is not None                # decode runs in the epilogue of the head's final convs
-    launches_per_step = prog.launches + (1 if fused else 2)     # + nms (+ head_decode when it is a kernel of its own)
-    MAXD = MAX_DET or int(out[0].shape[1])          # rows of the padded detection buffer (= anchors per image)
-
-    if args.profile_step:        # ncu --profile-from-start off: exactly one steady-state step inside the capture range
-        torch.cuda.synchronize()
-        torch.cuda.profiler.start()
-        out = step(x)
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        emit({"profiled_step": True, "launches_per_step": launches_per_step})
-        return
-
-    # ------------------------------------------------------------------ device-resident throughput
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
         time.sleep(0.3)
-    barrier()
-    l0 = launch_count()
+    ctx.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
+    t0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
-        out = step(x)
+    for _ in range(steps):
+        out = model.detect(x, CONF, IOU)
     ev1.record()
-    barrier()
-    t_wall1 = time.time()
-    ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    api_launches = launch_count() - l0              # launches issued through the C ABI (graph replays excluded)
-    value = world * B * args.steps / (ms / 1e3)
-    kept = out[4].tolist()
+    ctx.barrier()
+    t1 = time.time()
+    ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    return ms, out, clocks
 
-    # ------------------------------------------------------------------ end to end from HOST buffers
-    # every step: H2D of the fp32 batch from pinned memory, detect, gather detections, D2H of
-    # [B, A, 6] (all kept detections, padded) + counts into pinned memory.  Uploads are double-buffered on a copy stream,
-    # read-backs run on a third stream.
-    copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    xin = [torch.empty_like(x) for _ in range(2)]
-    dets_host = [torch.empty((B, MAXD, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-    cnt_host = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
-    ev_copied = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
-    d2h_s = torch.cuda.Stream(dev)                    # results go back on their own stream (PCIe is full duplex)
-    ev_read = [torch.cuda.Event() for _ in range(2)]
 
-    def read_back(dets, count, b):
-        """device -> pinned host copy of the step's detections + counts, overlapping the next step's compute"""
-        ev = torch.cuda.Event()
-        ev.record(comp_s)
-        with torch.cuda.stream(d2h_s):
-            d2h_s.wait_event(ev)
-            dets_host[b].copy_(dets, non_blocking=True)
-            cnt_host[b].copy_(count, non_blocking=True)
-            dets.record_stream(d2h_s); count.record_stream(d2h_s)
-            ev_read[b].record(d2h_s)
-
-    def e2e_loop(n):
-        for i in range(n):
-            b = i & 1
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(ev_done[b])                 # buffer b free again (step i-2 finished)
-                xin[b].copy_(x_host, non_blocking=True)
-                ev_copied[b].record(copy_s)
-            with torch.cuda.stream(comp_s):
-                comp_s.wait_event(ev_copied[b])
-                boxes, scores, labels, keep, count = model.detect(xin[b], CONF, IOU)
-                dets = ops.gather_detections(boxes, scores, labels, keep, count, MAXD)
-                ev_done[b].record(comp_s)                     # input buffer b may be refilled
-            read_back(dets, count, b)
-        comp_s.synchronize()
-        copy_s.synchronize()
-        d2h_s.synchronize()
-
-    e2e_loop(max(args.warmup, 3))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
-    e2e_f32 = {"value": round(world * B / (e2e_ms / 1e3), 1), "unit": UNIT,
-               "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(B * MAXD * 6 * 4 + B * 4),
-               "ms_per_step": round(e2e_ms, 3), "pipelined": "H2D of step i+1 and the read-back of step i-1 overlap compute of step i (3 streams, 2 buffers)",
-               "input": "the reference's forward interface: normalised fp32 [B,3,H,W] host tensors (PCIe-bound: 157 MB per step)"}
-
-    # ------------------------------------------------------------------ same, raw uint8 HWC host images
-    # (SURVEY 8f-1: ToTensor + Normalize fused into the stem; 4x less PCIe traffic than the fp32 interface)
-    g8 = torch.Generator().manual_seed(11 + rank)
+def e2e_u8(ctx, model, B, HW, steps, warmup, seed, sample_clocks):
+    """End to end from HOST buffers through the public call: every step uploads a pinned uint8 HWC batch, runs
+    YOLOv8.detect(batch, conf, iou, max_det=A) -- ONE graph launch: stem (ToTensor + Normalize inside), convs, decode, NMS,
+    gather -- and copies ALL kept detections ([B, A, 6] padded) + counts back to pinned memory.  Two input / output buffers;
+    H2D of step i+1 and D2H of step i-1 overlap compute of step i (three streams).  Nothing is allocated inside the loop."""
+    torch = ctx.torch
+    dev = ctx.dev
+    g8 = torch.Generator().manual_seed(seed)
     u8_host = torch.randint(0, 256, (B, HW, HW, 3), generator=g8, dtype=torch.uint8).pin_memory()
     u8in = [torch.empty((B, HW, HW, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    A = (HW // 8) ** 2 + (HW // 16) ** 2 + (HW // 32) ** 2
+    dets_host = [torch.empty((B, A, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    cnt_host = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    copy_s, comp_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    outs = []
+    for b in range(2):                                       # builds the uint8 program, then (second call) captures the one-graph step
+        u8in[b].copy_(u8_host)
+        for _ in range(2):
+            o = model.detect(u8in[b], CONF, IOU, max_det=A)
+        outs.append(o)
+    torch.cuda.synchronize()
+    n_ev = max(steps, warmup, 3)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_read = [torch.cuda.Event() for _ in range(2)]
+    c0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    c1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    fin = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
 
-    step_evs = []                                          # (start, end) events of every step's compute: where the time goes when
-                                                           # e2e falls behind `value` (GPU busy vs. waiting for the host / copies)
-    def e2e_u8_loop(n, record=False):
+    def loop(n):
         for i in range(n):
             b = i & 1
             with torch.cuda.stream(copy_s):
-                copy_s.wait_event(ev_done[b])
+                copy_s.wait_event(ev_done[b])                 # input buffer b free again (step i-2 has consumed it)
                 u8in[b].copy_(u8_host, non_blocking=True)
                 ev_copied[b].record(copy_s)
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(ev_copied[b])
-                if record:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(comp_s)
-                boxes, scores, labels, keep, count = model.detect(u8in[b], CONF, IOU)
-                dets = ops.gather_detections(boxes, scores, labels, keep, count, MAXD)
+                comp_s.wait_event(ev_read[b])                 # output buffers b have been read back (step i-2)
+                c0[i].record(comp_s)
+                o = model.detect(u8in[b], CONF, IOU, max_det=A)      # one CUDA-graph launch
+                c1[i].record(comp_s)
                 ev_done[b].record(comp_s)
-                if record:
-                    e1.record(comp_s)
-                    step_evs.append((e0, e1))
-            read_back(dets, count, b)
-        comp_s.synchronize()
-        copy_s.synchronize()
-        d2h_s.synchronize()
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(ev_done[b])
+                dets_host[b].copy_(o[5], non_blocking=True)
+                cnt_host[b].copy_(o[4], non_blocking=True)
+                ev_read[b].record(d2h_s)
+                fin[i].record(d2h_s)
+        comp_s.synchronize(); copy_s.synchronize(); d2h_s.synchronize()
 
-    model.detect(u8in[0].copy_(u8_host), CONF, IOU)        # build the uint8-input program (it reuses the autotuner's decisions) on a quiet device,
-    torch.cuda.synchronize()                               # not inside the pipelined loop
-    e2e_u8_loop(max(args.warmup, 3))
-    sampler_e = ClockSampler(local)
-    if rank == 0:
-        sampler_e.start()
+    loop(max(warmup, 3))
+    sampler = ClockSampler(ctx.local) if sample_clocks else None
+    if sampler is not None:
+        sampler.start()
         time.sleep(0.2)
-    barrier()
+    ctx.barrier()
     tw0 = time.time()
     t0 = time.perf_counter()
-    e2e_u8_loop(args.steps, record=True)
-    barrier()
-    u8_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
-    e2e_clocks = sampler_e.stop(tw0, time.time()) if rank == 0 else None
-    gpu_busy_ms = sum(a.elapsed_time(b) for a, b in step_evs) / max(len(step_evs), 1)
-    e2e = {"value": round(world * B / (u8_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(u8_host.numel()),
-           "d2h_bytes_per_step": int(B * MAXD * 6 * 4 + B * 4), "ms_per_step": round(u8_ms, 3),
-           "compute_ms_per_step": round(gpu_busy_ms, 3), "clocks": e2e_clocks,
-           "pipelined": "H2D of step i+1 and the read-back of step i-1 overlap compute of step i (3 streams, 2 buffers)",
-           "input": "uint8 RGB HWC host images [B,640,640,3] (what tools/test.py holds after decode + resize); ToTensor+Normalize run "
-                    "inside the stem kernel; public call: YOLOv8.detect(uint8 batch) + gather_detections"}
+    loop(steps)
+    ctx.barrier()
+    wall_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    clocks = sampler.stop(tw0, time.time()) if sampler is not None else None
+    comp = sorted(c0[i].elapsed_time(c1[i]) for i in range(steps))
+    gaps = sorted(fin[i - 1].elapsed_time(fin[i]) for i in range(1, steps))
+    pct = lambda v, q: round(v[min(len(v) - 1, int(q * len(v)))], 4) if v else None
+    kept = int(cnt_host[(steps - 1) & 1].sum())
+    return {"value": round(ctx.world * B / (wall_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(u8_host.numel()),
+            "d2h_bytes_per_step": int(B * A * 6 * 4 + B * 4), "ms_per_step": round(wall_ms, 4), "steps": steps,
+            "step_ms_p50": pct(gaps, 0.5), "step_ms_p95": pct(gaps, 0.95),
+            "compute_ms_per_step": round(sum(comp) / len(comp), 4), "compute_ms_p50": pct(comp, 0.5), "compute_ms_p95": pct(comp, 0.95),
+            "clocks": clocks, "kept_detections_last_step": kept,
+            "host_calls_per_step": "1 graph launch + 1 H2D + 2 D2H copies; 0 allocations",
+            "pipelined": "H2D of step i+1 and the read-back of step i-1 overlap compute of step i (3 streams, 2 buffers)",
+            "input": f"uint8 RGB HWC host images [B,{HW},{HW},3] (what tools/test.py holds after decode + resize); ToTensor+Normalize run "
+                     "inside the stem kernel; public call: YOLOv8.detect(uint8 batch, conf, iou, max_det)"}
 
-    # ------------------------------------------------------------------ per-kernel roofline (rank 0)
-    roof, cpu_base, breakdown = None, None, None
-    if rank == 0:
-        peaks = _peaks()
-        reps = 5
-        per = [0.0] * len(prog.steps)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in prog.steps]
-        prog.steps[0]()
-        for _ in range(reps):
-            for (a, b), st in zip(evs, prog.steps):
-                a.record(); st(); b.record()
-            torch.cuda.synchronize()
-            for i, (a, b) in enumerate(evs):
-                per[i] += a.elapsed_time(b) / reps
-        conv_eager_ms = conv_fl = conv_by = 0.0
-        n_conv = 0
-        conv_steps = []
-        for t, st in zip(per, prog.steps):
-            pl = getattr(st, "__self__", None)
-            if pl is not None and hasattr(pl, "flops"):
-                conv_eager_ms += t; conv_fl += pl.flops; conv_by += pl.bytes; n_conv += 1
-                conv_steps.append(st)
-        # the conv launches alone, back to back in ONE CUDA graph: device time without host launch gaps (the eager
-        # per-launch events above include the host's launch latency whenever a kernel is shorter than it)
+
+def e2e_f32(ctx, model, x_host, steps, warmup):
+    """Same loop fed with the reference forward's own input type: normalised fp32 [B,3,H,W] host tensors (4x the bytes)."""
+    torch = ctx.torch
+    dev = ctx.dev
+    B, HW = x_host.shape[0], x_host.shape[2]
+    A = (HW // 8) ** 2 + (HW // 16) ** 2 + (HW // 32) ** 2
+    xin = [torch.empty_like(x_host, device=dev) for _ in range(2)]
+    dets_host = [torch.empty((B, A, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    cnt_host = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    copy_s, comp_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for b in range(2):
+        xin[b].copy_(x_host)
+        for _ in range(2):
+            model.detect(xin[b], CONF, IOU, max_det=A)
+    torch.cuda.synchronize()
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_read = [torch.cuda.Event() for _ in range(2)]
+
+    def loop(n):
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_done[b])
+                xin[b].copy_(x_host, non_blocking=True)
+                ev_copied[b].record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(ev_copied[b]); comp_s.wait_event(ev_read[b])
+                o = model.detect(xin[b], CONF, IOU, max_det=A)
+                ev_done[b].record(comp_s)
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(ev_done[b])
+                dets_host[b].copy_(o[5], non_blocking=True)
+                cnt_host[b].copy_(o[4], non_blocking=True)
+                ev_read[b].record(d2h_s)
+        comp_s.synchronize(); copy_s.synchronize(); d2h_s.synchronize()
+
+    loop(max(warmup, 3))
+    ctx.barrier()
+    t0 = time.perf_counter()
+    loop(steps)
+    ctx.barrier()
+    ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    return {"value": round(ctx.world * B / (ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+            "d2h_bytes_per_step": int(B * A * 6 * 4 + B * 4), "ms_per_step": round(ms, 3), "steps": steps,
+            "input": "the reference forward's interface: normalised fp32 [B,3,H,W] host tensors (PCIe-bound: 157 MB per step at batch 32)"}
+
+
+def program_of(model):
+    return list(model._programs().values())[0][0]
+
+
+def roofline_of(ctx, prog, peaks, reps=10):
+    """Device time of the step's tensor-core conv launches (and, separately, of its fused MS-Block layer launches) replayed back to
+    back in a CUDA graph; algorithmic bytes / FLOPs from the plans' cost functions."""
+    torch = ctx.torch
+    dev = ctx.dev
+
+    def graph_ms(fns):
+        if not fns:
+            return 0.0
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for st in conv_steps:
-                st()
+            for f in fns:
+                f()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
-        gconv = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gconv):
-            for st in conv_steps:
-                st()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for f in fns:
+                f()
         for _ in range(3):
-            gconv.replay()
-        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eg0.record()
-        for _ in range(10):
-            gconv.replay()
-        eg1.record()
+            g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
         torch.cuda.synchronize()
-        conv_ms = eg0.elapsed_time(eg1) / 10
-        # decode / nms timed alone (the stand-alone decode kernel: it is NOT part of the step when decode is fused into
-        # the head's final convs -- the number is kept as the cost the fusion removes)
+        return a.elapsed_time(b) / reps
+
+    from yolo_ms_b200 import ops
+    conv, ms = [], []
+    for st in prog.steps:
+        pl = getattr(st, "__self__", None)
+        if isinstance(pl, ops.MsLayerPlan):
+            ms.append(pl)
+        elif pl is not None and hasattr(pl, "flops"):
+            conv.append(pl)
+    out = {}
+    for name, plans in (("conv", conv), ("ms_layer", ms)):
+        if not plans:
+            continue
+        t = graph_ms([pl.run for pl in plans])
+        fl, by = sum(pl.flops for pl in plans), sum(pl.bytes for pl in plans)
+        out[name] = {"launches": len(plans), "ms": round(t, 4), "algorithmic_bytes": by, "algorithmic_flops": fl,
+                     "GBs": round(by / (t / 1e3) / 1e9, 1), "TFLOPs": round(fl / (t / 1e3) / 1e12, 1),
+                     "hbm_frac": round(by / (t / 1e3) / 1e9 / peaks["hbm_gbs"], 4),
+                     "tensor_frac": round(fl / (t / 1e3) / 1e12 / peaks["bf16_tflops_sustained"], 4)}
+    return out
+
+
+def quick_leg(ctx, version, block, B, HW, steps, peaks, with_e2e=False, with_roofline=True):
+    """One of the other BASELINE configs as a short leg: device-resident value (+ e2e, + the conv / MS-layer roofline)."""
+    from yolo_ms_b200 import synth
+    torch = ctx.torch
+    model = build_model(ctx, version, block)
+    x = synth.make_images(B, HW, HW, seed=7 + ctx.rank).to(ctx.dev)
+    ms, out, _ = timed_value(ctx, model, x, steps, 3)
+    prog = program_of(model)
+    leg = {"workload": f"version '{version}', block {block}, {HW}x{HW}, batch {B} per GPU x {ctx.world} GPU(s)",
+           "value": round(ctx.world * B * steps / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms / steps, 4), "steps": steps,
+           "launches_per_step": prog.launches + 1, "kept_detections_rank0": int(out[4].sum())}
+    if with_roofline and ctx.rank == 0:
+        leg["roofline"] = roofline_of(ctx, prog, peaks, reps=5)
+    if with_e2e:
+        e = e2e_u8(ctx, model, B, HW, max(steps, 50), 3, 11 + ctx.rank, False)
+        leg["e2e"] = {k: e[k] for k in ("value", "unit", "ms_per_step", "compute_ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    del model, x, out, prog
+    free(ctx)
+    return leg
+
+
+def decode_stress(ctx, peaks, reps=10):
+    """BASELINE configs[3], decode half: raw [64, 144, 8400] logits (fp32 and bf16) -> pred [64, 8400, 84] + candidates, one kernel
+    (yms_head_decode; yolov8_head.py:127-144).  Algorithmic bytes per anchor: 144 * s_in + 84 * 4 + 24."""
+    torch = ctx.torch
+    from yolo_ms_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, out = 64, {}
+    for name, dt, s_in in (("f32", torch.float32, 4), ("bf16", torch.bfloat16, 2)):
+        raws = [(torch.randn(B, h, h, 144, generator=g) * 2).to(ctx.dev).to(dt) for h in (80, 40, 20)]
+        for _ in range(3):
+            ops.head_decode(raws, STRIDES, 80, with_candidates=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ops.head_decode(raws, STRIDES, 80, with_candidates=True)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        by = B * 8400 * (144 * s_in + 84 * 4 + 24)
+        out[name] = {"ms": round(ms, 4), "bytes_per_anchor": 144 * s_in + 84 * 4 + 24, "GBs": round(by / (ms / 1e3) / 1e9, 1),
+                     "hbm_frac": round(by / (ms / 1e3) / 1e9 / peaks["hbm_gbs"], 4)}
+        del raws
+    out["note"] = "stand-alone decode kernel incl. the per-call allocation of its outputs; inside YOLOv8.detect the decode runs in the head convs' epilogue"
+    return out
+
+
+def nms_stress(ctx, reps=5):
+    """BASELINE configs[3], NMS half: 30 000 boxes x 80 classes x batch 64, conf 0.25, iou 0.45: uniform, clustered
+    (300 centres x 100 jittered boxes) and tie-heavy (scores quantised to 1/256) variants.  pair tests = sum over classes of
+    n_c (n_c - 1) / 2 among the boxes that pass the confidence filter (the work a full IoU bitmask would do)."""
+    torch = ctx.torch
+    from yolo_ms_b200 import ops
+    B, N, NC = 64, 30000, 80
+    out = {}
+    for name in ("uniform", "clustered", "ties"):
+        g = torch.Generator().manual_seed({"uniform": 0, "clustered": 1, "ties": 2}[name])
+        if name == "clustered":
+            c = torch.rand(B, 300, 1, 2, generator=g) * 500 + 50
+            xy = (c + torch.randn(B, 300, 100, 2, generator=g) * 4).reshape(B, N, 2)
+            wh = 40 + torch.randn(B, N, 2, generator=g) * 3
+        else:
+            xy = torch.rand(B, N, 2, generator=g) * 600
+            wh = torch.rand(B, N, 2, generator=g) * 60 + 4
+        sc = torch.rand(B, N, generator=g)
+        if name == "ties":
+            sc = torch.floor(sc * 256) / 256
+        lb = torch.randint(0, NC, (B, N), generator=g, dtype=torch.int32)
+        boxes = torch.cat([xy, xy + wh], -1).contiguous().to(ctx.dev)
+        sc, lb = sc.to(ctx.dev), lb.to(ctx.dev)
+        pb = ops.PostBuffers(B, N, ctx.dev)
+        for _ in range(2):
+            keep, cnt = ops.nms_batched(boxes, sc, lb, CONF, IOU, NC, out=pb)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            keep, cnt = ops.nms_batched(boxes, sc, lb, CONF, IOU, NC, out=pb)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        ok = sc > CONF
+        n_c = torch.stack([((lb == c) & ok).sum(1) for c in range(NC)], 1).double()
+        pairs = float((n_c * (n_c - 1) / 2).sum())
+        out[name] = {"ms": round(ms, 4), "boxes_per_s": round(B * N / (ms / 1e3)), "pair_tests": round(pairs),
+                     "pairs_per_s": round(pairs / (ms / 1e3)), "kept": int(cnt.sum()),
+                     "mandatory_GBs": round((B * N * 24 + 4 * int(cnt.sum())) / (ms / 1e3) / 1e9, 2)}
+        del boxes, sc, lb, pb, keep, cnt
+    return out
+
+
+def gpu_library_baseline(ctx, version, B, HW, steps=5):
+    """The same-box LIBRARY bar: what the unmodified reference reaches when run on this GPU -- its ATen ops in eager
+    PyTorch, bf16 channels_last (cuDNN's sm_100 convolutions; BN and SiLU as separate passes, components.py:69-77), fp32 decode,
+    then the reference's per-image, per-class Python loop around torchvision.ops.nms (tools/test.py:166-218).  Same weights, same
+    synthetic images, same thresholds as the headline leg.  The functional restatement in oracle/ issues exactly those ops."""
+    torch = ctx.torch
+    from oracle import postprocess as PP
+    from oracle import weights as W
+    from oracle import yolov8_oracle as O
+    from yolo_ms_b200 import synth
+    torch.backends.cudnn.benchmark = True
+    sd32 = W.calibrated_state_dict(version, seed=1)
+    sd = {}
+    for k, v in sd32.items():
+        v = v.to(ctx.dev)
+        if v.is_floating_point():
+            v = v.to(torch.bfloat16)
+            if v.dim() == 4:
+                v = v.contiguous(memory_format=torch.channels_last)
+        sd[k] = v
+    x = synth.make_images(B, HW, HW, seed=7).to(ctx.dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+    def fwd():
+        with torch.no_grad():
+            p3, p4, p5 = O.backbone(sd, x)
+            feats = O.neck(sd, p3, p4, p5)
+            raw = [r.float() for r in O.head_raw(sd, list(feats))]
+            return O.decode(raw, STRIDES)
+
+    def post(pred):
+        return sum(int(PP.torch_postprocess_image(pred[i], CONF, IOU)[0].numel()) for i in range(pred.shape[0]))
+
+    for _ in range(3):
+        pred = fwd()
+    post(pred)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    f_ms = p_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e[0].record()
+        pred = fwd()
+        e[1].record()
+        kept = post(pred)
+        e[2].record()
+        torch.cuda.synchronize()
+        f_ms += e[0].elapsed_time(e[1]) / steps
+        p_ms += e[1].elapsed_time(e[2]) / steps
+    wall = (time.perf_counter() - t0) * 1e3 / steps
+    del sd, x, pred
+    return {"value": round(B / (wall / 1e3), 1), "unit": UNIT, "ms_per_step": round(wall, 3), "forward_ms": round(f_ms, 3),
+            "postprocess_ms": round(p_ms, 3), "kept_detections": kept, "steps": steps,
+            "what": "oracle port run on the GPU: eager PyTorch bf16 channels_last (cuDNN convs, separate BN + SiLU passes), fp32 decode, "
+                    "per-image per-class torchvision.ops.nms loop (tools/test.py:166-218); same weights / images / thresholds",
+            "cudnn": torch.backends.cudnn.version(), "kind": "port"}
+
+
+def verify(ctx, model, x, out):
+    """Post-run self-check of what was timed (rank 0): (1) the keep lists of three images of the batch against the C oracle of the
+    reference's post-process run on OUR decoded predictions -- bit-exact; (2) the raw head logits of image 0 against the CPU
+    oracle under the same numeric contract (bf16 storage, fp32 accumulate) -- rel-L2 under the random-weight bf16 gate of the
+    test-suite.  The oracle is the checker here, never the thing measured."""
+    import numpy as np
+    torch = ctx.torch
+    from oracle import postprocess as PP
+    from oracle import weights as W
+    from oracle import yolov8_oracle as O
+    prog = program_of(model)
+    res = {"nms_bit_exact": None, "images_checked": [], "forward_rel_l2_image0": None}
+    try:
+        nc = model.head.num_classes
+        pred = prog.decoded["pred"][..., :4 + nc].cpu().numpy()
+        keep, count = out[3].cpu().numpy(), out[4].cpu().numpy()
+        ok = True
+        B = pred.shape[0]
+        for i in sorted({0, B // 2, B - 1}):
+            want = PP.postprocess_image(pred[i], CONF, IOU, PP.greedy_nms_c)[0]
+            ok &= bool(count[i] == want.size and np.array_equal(keep[i, :count[i]].astype(np.int64), want))
+            res["images_checked"].append(i)
+        res["nms_bit_exact"] = ok
+        sd = W.calibrated_state_dict("s", seed=1)
         raws = model.forward_raw(x)
-        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        dec_ms = nms_ms = 0.0
-        for it in range(2 + reps):                      # 2 warm-up rounds (allocator, first-launch attributes), then the mean
-            ea.record()
-            pred, (cb, cs, cl) = ops.head_decode(raws, [8.0, 16.0, 32.0], 80, with_candidates=True)
-            eb.record()
-            ops.nms_batched(cb, cs, cl, CONF, IOU, 80)
-            ec.record()
-            torch.cuda.synchronize()
-            if it >= 2:
-                dec_ms += ea.elapsed_time(eb) / reps
-                nms_ms += eb.elapsed_time(ec) / reps
-        A = pred.shape[1]
-        dec_bytes = B * A * (144 * 4 + 84 * 4 + 24)
-        ai = conv_fl / conv_by
+        with torch.no_grad():
+            emu = O.forward_bf16_contract(sd, x[:1].cpu(), return_parts=True)
+        rel = max(float((a[:1, ..., :64 + nc].permute(0, 3, 1, 2).float().cpu() - b).norm() / b.norm()) for a, b in zip(raws, emu["raw"]))
+        res["forward_rel_l2_image0"] = round(rel, 4)
+        res["forward_gate"] = 0.15
+        res["ok"] = bool(ok and rel < 0.15)
+    except Exception as e:  # noqa: BLE001
+        res["ok"] = False
+        res["error"] = repr(e)[:200]
+    return res
+
+
+def run_native(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    from yolo_ms_b200 import launch_count, ops, synth
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    B, HW = args.batch, args.hw
+    peaks = _peaks()
+
+    model = build_model(ctx, args.version, args.block)
+    x_host = synth.make_images(B, HW, HW, seed=7 + rank).pin_memory()
+    x = x_host.to(dev)
+
+    if args.profile_step:        # ncu --profile-from-start off: exactly one steady-state step inside the capture range
+        for _ in range(3):
+            model.detect(x, CONF, IOU)
+        prog = program_of(model)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        model.detect(x, CONF, IOU)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        emit({"profiled_step": True, "launches_per_step": prog.launches + 1})
+        return
+
+    # ------------------------------------------------------------------ device-resident throughput (headline `value`)
+    l0 = launch_count()
+    ms, out, clocks = timed_value(ctx, model, x, args.steps, args.warmup, ClockSampler(ctx.local) if rank == 0 else None)
+    api_launches = launch_count() - l0
+    value = world * B * args.steps / (ms / 1e3)
+    prog = program_of(model)
+    fused = prog.decoded is not None
+    launches_per_step = prog.launches + (1 if fused else 2)     # + nms (+ head_decode when it is a kernel of its own)
+    kept = int(out[4].sum())
+
+    # ------------------------------------------------------------------ end to end from HOST buffers (headline `e2e`)
+    e2e = e2e_u8(ctx, model, B, HW, max(args.steps, args.e2e_steps), args.warmup, 11 + rank, rank == 0)
+    e2e["numa"] = ctx.numa
+    e2e_fp32 = e2e_f32(ctx, model, x_host, min(args.steps, 20), args.warmup)
+
+    # ------------------------------------------------------------------ per-kernel roofline, checks, baselines (rank 0)
+    roof = breakdown = cpu_base = verified = lib_base = None
+    if rank == 0:
+        r = roofline_of(ctx, prog, peaks)["conv"]
+        ai = r["algorithmic_flops"] / r["algorithmic_bytes"]
         ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-        gbs = conv_by / (conv_ms / 1e3) / 1e9
-        tfs = conv_fl / (conv_ms / 1e3) / 1e12
         bound = "hbm" if ai < ridge else "tensor"
-        # DRAM traffic of the same kernels from the committed ncu launch list (profiles/traffic_*.json)
         traffic, traffic_src = None, None
         try:
             import glob
@@ -399,32 +665,68 @@ def run_native(args):
             tb = sum(v["dram_bytes"] for k, v in tj.items() if k.startswith("conv"))
             tl = sum(v["launches"] for k, v in tj.items() if k.startswith("conv"))
             traffic, traffic_src = round(tb / tl), os.path.basename(tf)
-        except Exception:
+        except Exception:  # noqa: BLE001
             pass
         roof = {"kernel": "conv_gemm_kernel + conv3x3_kernel (all tcgen05 conv launches of a step)", "bound": bound,
-                "achieved": round(gbs if bound == "hbm" else tfs, 1),
+                "achieved": r["GBs"] if bound == "hbm" else r["TFLOPs"],
                 "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops_sustained"],
                 "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                "frac": round((gbs / peaks["hbm_gbs"]) if bound == "hbm" else (tfs / peaks["bf16_tflops_sustained"]), 4),
-                "traffic": traffic, "traffic_note": f"mean DRAM bytes per launch from {traffic_src} (ncu, same batch/config); algorithmic mean {round(conv_by / n_conv)}",
-                "peak_source": peaks["source"],
-                "launches_per_step": n_conv, "avg_launch_us": round(conv_ms / n_conv * 1e3, 2),
-                "algorithmic_bytes_per_step": conv_by, "algorithmic_flops_per_step": conv_fl,
-                "tflops": round(tfs, 1), "tensor_frac": round(tfs / peaks["bf16_tflops_sustained"], 4),
+                "frac": r["hbm_frac"] if bound == "hbm" else r["tensor_frac"],
+                "traffic": traffic, "traffic_note": f"mean DRAM bytes per launch from {traffic_src} (ncu, same batch/config); algorithmic mean {round(r['algorithmic_bytes'] / r['launches'])}",
+                "peak_source": peaks["source"], "launches_per_step": r["launches"], "avg_launch_us": round(r["ms"] / r["launches"] * 1e3, 2),
+                "algorithmic_bytes_per_step": r["algorithmic_bytes"], "algorithmic_flops_per_step": r["algorithmic_flops"],
+                "tflops": r["TFLOPs"], "tensor_frac": r["tensor_frac"], "hbm_GBs": r["GBs"], "hbm_frac": r["hbm_frac"],
                 "arithmetic_intensity": round(ai, 1),
-                "how": "CUDA events around 10 replays of a CUDA graph holding the step's conv launches back to back (device time, "
-                       "no host launch gaps); the eager per-launch events sum to conv_eager_ms"}
-        breakdown = {"conv_gemm_ms": round(conv_ms, 3), "conv_eager_ms": round(conv_eager_ms, 3),
-                     "other_program_ms": round(sum(per) - conv_eager_ms, 3),
-                     "stem_ms": round(per[0], 3), "nms_ms": round(nms_ms, 3),
-                     "decode": "fused into the epilogue of the head's final 1x1 convs (inside conv_gemm_ms)" if fused
-                               else "head_decode_v2_kernel, one launch per step",
-                     "standalone_decode_kernel_ms": round(dec_ms, 3),
-                     "standalone_decode_GBs": round(dec_bytes / (dec_ms / 1e3) / 1e9, 1),
-                     "standalone_decode_hbm_frac": round(dec_bytes / (dec_ms / 1e3) / 1e9 / peaks["hbm_gbs"], 4)}
-        if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(args.version, HW, args.cpu_images, 4, 1)
-            cpu_base = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+                "how": "CUDA events around 10 replays of a CUDA graph holding the step's conv launches back to back (device time, no host gaps)"}
+        # stem / nms alone (CUDA events, eager)
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        cb, cs, cl = prog.decoded["boxes"], prog.decoded["scores"], prog.decoded["labels"]
+        pb = ops.PostBuffers(B, cs.shape[1], dev)
+        stem_ms = nms_ms = 0.0
+        for it in range(7):
+            ea.record(); prog.steps[0](); eb.record()
+            ops.nms_batched(cb, cs, cl, CONF, IOU, model.head.nc_pad, out=pb)
+            ec.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                stem_ms += ea.elapsed_time(eb) / 5
+                nms_ms += eb.elapsed_time(ec) / 5
+        breakdown = {"step_ms": round(ms / args.steps, 4), "conv_ms": r["ms"], "stem_ms": round(stem_ms, 3), "nms_ms": round(nms_ms, 3),
+                     "decode": "fused into the epilogue of the head's final 1x1 convs (inside conv_ms)" if fused else "head_decode_v2_kernel"}
+        if world == 1:
+            verified = verify(ctx, model, x, model.detect(x, CONF, IOU))
+    del out
+    legs = {}
+    if not args.no_configs:
+        free(ctx)
+        # ---- BASELINE configs[2]: base model, batch 256 sharded over the GPUs (all ranks) ----
+        per = max(1, 256 // world)
+        for blk in ("c2f", "ms"):
+            legs[f"m_b256_{blk}"] = quick_leg(ctx, "m", blk, per, 640, 5, peaks, with_roofline=(blk == "c2f"))
+            legs[f"m_b256_{blk}"]["global_batch"] = per * world
+    if rank == 0 and world == 1:
+        if not args.no_configs:
+            del model, x
+            free(ctx)
+            # ---- the model north_star names: MS-Block backbone / neck (repo-local block definition, parity unpinned) ----
+            legs["s_ms_640_b32"] = quick_leg(ctx, "s", "ms", 32, 640, 20, peaks, with_e2e=True)
+            # ---- BASELINE configs[4]: high resolution ----
+            legs["s_c2f_1280_b16"] = quick_leg(ctx, "s", "c2f", 16, 1280, 10, peaks)
+            legs["s_ms_1280_b16"] = quick_leg(ctx, "s", "ms", 16, 1280, 10, peaks)
+            # ---- BASELINE configs[3]: operator stress ----
+            legs["decode_stress_64x144x8400"] = decode_stress(ctx, peaks)
+            legs["nms_stress_30k_x64"] = nms_stress(ctx)
+            free(ctx)
+        if not args.no_library_baseline:
+            try:
+                lib_base = gpu_library_baseline(ctx, args.version, B, HW)
+                lib_base["ours_over_library"] = round(value / lib_base["value"], 2)
+            except Exception as e:  # noqa: BLE001
+                lib_base = {"unavailable": repr(e)[:200]}
+            free(ctx)
+        if not args.no_cpu_baseline:
+            r2 = cpu_reference_run(args.version, HW, args.cpu_images, 10, 1)
+            cpu_base = {"value": round(r2["value"], 3), "unit": UNIT, "cores": r2["cores"], "kind": "port", "sample": r2["sample"]}
 
     if rank == 0:
         line = {
@@ -435,16 +737,17 @@ def run_native(args):
                                    f"forward+decode+NMS, batch {B} per GPU", "global_batch": B * world, "conf": CONF, "iou": IOU,
                        "parallelism": f"dp{world} (batch sharded by image, no collective)",
                        "l2": "per-step working set (~2.4 GB activations + 157 MB input) >> 126 MB L2, no explicit flush",
-                       "kept_detections_rank0": int(sum(kept))},
-            "clocks": clocks, "e2e": e2e, "e2e_fp32_interface": e2e_f32, "gpu_launches": launches_per_step * args.steps,
-            "gpu_launches_note": f"{launches_per_step} kernels per step ({prog.launches - 1} inside the CUDA graph, stem"
-                                 f"{'' if fused else ' + decode'} + NMS launched "
-                                 f"through the C ABI: {api_launches} ABI launches counted in the timed region)",
-            "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu_base,
+                       "kept_detections_rank0": kept},
+            "clocks": clocks, "e2e": e2e, "e2e_fp32_interface": e2e_fp32, "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_note": f"{launches_per_step} kernels per step, replayed as ONE CUDA graph per input buffer (stem"
+                                 f"{'' if fused else ' + decode'} + {prog.launches - 1} conv / glue launches + NMS); "
+                                 f"{api_launches} launches went through the C ABI eagerly inside the timed region",
+            "roofline": roof, "breakdown": breakdown, "verified": verified, "cpu_baseline": cpu_base,
+            "gpu_library_baseline": lib_base, "configs": legs or None,
         }
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 _REAL_STDOUT = None
@@ -475,8 +778,11 @@ def main():
     ap.add_argument("--block", default="c2f", choices=["c2f", "ms"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--hw", type=int, default=640)
+    ap.add_argument("--e2e-steps", type=int, default=200, help="minimum steps of the end-to-end leg (p50 / p95 need a few hundred)")
     ap.add_argument("--cpu-images", type=int, default=8, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs for the other BASELINE configs")
     ap.add_argument("--profile-step", action="store_true", help="run one step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

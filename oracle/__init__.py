@@ -1,10 +1,13 @@
 """CPU oracle for the YOLO-MS / YOLOv8 inference hot path.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the shipped
-product: only ``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline /
-``--impl reference`` legs of ``bench.py`` may import it, and only as the checker
-or as the thing timed *as the CPU baseline* -- never as a fallback for the CUDA
-path (``yolo_ms_b200`` raises if its CUDA library is missing).
+product: only ``tests/``, ``__graft_entry__.smoke()`` and the BASELINE legs of
+``bench.py`` (``cpu_baseline`` / ``--impl reference``: the port on the host cores;
+``gpu_library_baseline``: the same port's ATen ops run on the GPU through cuDNN +
+``torchvision.ops.nms``, i.e. what the unmodified reference reaches on a CUDA device;
+``verified``: the post-run self-check) may import it, and only as the checker or as
+the thing timed *as a baseline* -- never as a fallback for the CUDA path
+(``yolo_ms_b200`` raises if its CUDA library is missing).
 
 Contents
 --------

@@ -78,35 +78,7 @@ def dump_model(version, batch, h, w, seed):
     return pred
 
 
-def reference_postprocess(pred_single, conf_thresh, iou_thresh_nms):
-    """tools/test.py:166-218 executed with torch + the real torchvision nms; returns the
-    anchor indices the reference's final tensors correspond to."""
-    from torchvision.ops import nms
-    x_center, y_center, width, height = pred_single[:, :4].T
-    x1 = x_center - width / 2
-    y1 = y_center - height / 2
-    x2 = x_center + width / 2
-    y2 = y_center + height / 2
-    boxes = torch.stack((x1, y1, x2, y2), dim=1)
-    scores, class_indices = torch.max(pred_single[:, 4:], dim=1)
-    conf_mask = scores > conf_thresh
-    anchor_ids = torch.arange(pred_single.shape[0])[conf_mask]
-    b, s, c = boxes[conf_mask], scores[conf_mask], class_indices[conf_mask]
-    keep_ids, keep_boxes, keep_scores, keep_labels = [], [], [], []
-    for cls_idx in torch.unique(c):
-        cm = c == cls_idx
-        cb, cs = b[cm], s[cm]
-        if cb.shape[0] == 0:
-            continue
-        keep = nms(cb, cs, iou_thresh_nms)
-        keep_ids.append(anchor_ids[cm][keep])
-        keep_boxes.append(cb[keep])
-        keep_scores.append(cs[keep])
-        keep_labels.append(torch.full_like(cs[keep], fill_value=cls_idx.item(), dtype=torch.long))
-    if not keep_ids:
-        z = torch.zeros(0, dtype=torch.long)
-        return z, torch.zeros(0, 4), torch.zeros(0), z
-    return torch.cat(keep_ids), torch.cat(keep_boxes), torch.cat(keep_scores), torch.cat(keep_labels)
+from oracle.postprocess import torch_postprocess_image as reference_postprocess   # noqa: E402  (tools/test.py:166-218 with the real torchvision nms)
 
 
 @torch.no_grad()

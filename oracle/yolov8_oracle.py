@@ -176,18 +176,18 @@ def decode(raw, strides, reg_max=16):
     anchors, svec = [], []
     for r, s in zip(raw, strides):
         h, w = r.shape[2:]
-        sx = torch.arange(w, dtype=r.dtype) + 0.5
-        sy = torch.arange(h, dtype=r.dtype) + 0.5
+        sx = torch.arange(w, dtype=r.dtype, device=r.device) + 0.5
+        sy = torch.arange(h, dtype=r.dtype, device=r.device) + 0.5
         gy, gx = torch.meshgrid(sy, sx, indexing="ij")
         anchors.append(torch.stack((gx, gy), -1).view(-1, 2))
-        svec.append(torch.full((h * w, 1), float(s), dtype=r.dtype))
+        svec.append(torch.full((h * w, 1), float(s), dtype=r.dtype, device=r.device))
     anchors = torch.cat(anchors).t()           # [2, A]
     svec = torch.cat(svec).t()                 # [1, A]
     x = torch.cat([r.reshape(b, no, -1) for r in raw], 2)
     box, cls = x.split((4 * reg_max, no - 4 * reg_max), 1)
     a = box.shape[2]
     prob = box.view(b, 4, reg_max, a).transpose(1, 2).softmax(1)
-    proj = torch.arange(reg_max, dtype=x.dtype).view(1, reg_max, 1, 1)
+    proj = torch.arange(reg_max, dtype=x.dtype, device=x.device).view(1, reg_max, 1, 1)
     dist = F.conv2d(prob, proj.view(1, reg_max, 1, 1)).view(b, 4, a)
     lt, rb = dist.chunk(2, 1)
     x1y1 = anchors.unsqueeze(0) - lt

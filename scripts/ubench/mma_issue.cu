@@ -1,6 +1,6 @@
 // Micro-benchmark (B200): what does one k-block cost in the tcgen05 issue loop of the conv kernels?
 // One issuer warp per CTA, operands = garbage in shared memory (valid SW128 K-major descriptors), no producer.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I yolo_ms_b200/csrc scripts/ubench/mma_issue.cu -o build/mma_issue
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -I yolo_ms_b200/csrc scripts/ubench/mma_issue.cu -o build/mma_issue
 // Output: cycles per k-block for (N, MMAs per k-block, #independent accumulators, variant).
 #include "tc_ptx.cuh"
 #include <cstdio>

@@ -3,7 +3,7 @@
 //   style 0: whole warp loops, elect_one() inside per k-block, __syncwarp (current conv_gemm.cu)
 //   style 1: ONE elected thread runs the whole loop
 //   style 2: style 1 + the try_wait of the next stage is issued before the MMAs of the current one
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I yolo_ms_b200/csrc scripts/ubench/mma_ring.cu -o build/mma_ring
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -I yolo_ms_b200/csrc scripts/ubench/mma_ring.cu -o build/mma_ring
 #include "tc_ptx.cuh"
 #include <cstdio>
 #include <cstdlib>

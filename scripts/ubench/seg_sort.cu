@@ -5,7 +5,7 @@
 //   variant 0: nms.cu::segment_sort<false> (shared memory, one warp per segment, normalised bitonic network)
 //   variant 1: warp_sort_regs<E> (E = 1, 2, 4, 8 keys per lane; same network, strides >= E cross lanes by shuffle)
 // Both sort the same segments; the result is checked against std::sort; cycles are the CTA's clock64() span.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 scripts/ubench/seg_sort.cu -o build/seg_sort && build/seg_sort
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared scripts/ubench/seg_sort.cu -o build/seg_sort && build/seg_sort
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

@@ -46,14 +46,18 @@ def test_plan_modifiers_report_argument_errors_without_a_gpu():
 
 
 def test_host_side_fusion_switches():
-    """Which programs decode in the conv epilogue is host logic: class counts that are a multiple of 16 up to 128 (the fused
-    epilogue's limits, include/yms_b200.h); everything else keeps the stand-alone decode kernel.  The autotuner's cache key
-    separates layers that differ only in buffer strides (a channel slice of a concat buffer vs a dense tensor)."""
+    """Which programs decode in the conv epilogue is host logic: class counts up to 128 after the host has zero-padded the class
+    branch to a multiple of 16 (the fused epilogue's limits, include/yms_b200.h; the reference's own configs use 1 and 10
+    classes); everything else keeps the stand-alone decode kernel.  The autotuner's cache key separates layers that differ only
+    in buffer strides (a channel slice of a concat buffer vs a dense tensor)."""
     from yolo_ms_b200 import engine
     from yolo_ms_b200.model.yolov8_head import Head
     assert Head(version="n", num_classes=80).can_fuse_decode()
     assert Head(version="n", num_classes=16).can_fuse_decode()
-    assert not Head(version="n", num_classes=24).can_fuse_decode()
+    for nc, ncp in ((1, 16), (10, 16), (24, 32), (80, 80), (128, 128)):
+        h = Head(version="n", num_classes=nc)
+        assert h.nc_pad == ncp and h.no == 64 + nc and h.can_fuse_decode()
+        assert h.state_dict()["cls.0.2.weight"].shape[0] == nc            # the state_dict keeps the reference's shapes
     assert not Head(version="n", num_classes=144).can_fuse_decode()
     assert not Head(version="n", num_classes=80, ch=8).can_fuse_decode()
     dense = torch.empty(2, 8, 8, 32)

@@ -32,9 +32,13 @@ namespace yms {
 namespace {
 using namespace tc;
 
-constexpr int kTW = 16, kTH = 8;                 // output pixels per tile
-constexpr int kPitch = 24;                       // halo-row pitch in pixels
-constexpr int kRowPitchBytes = kPitch * 128;     // 3072
+// Tile geometry: output pixels per tile (TW x TH <= 128 = the M of the pw2 GEMM), and the pitch (pixels, a multiple of 8)
+// at which halo rows sit in shared memory.  GEOM 0 = 16 x 8 (pitch 24); GEOM 1 = 24 x 5 (pitch 32) for maps whose width is
+// a bad fit for 16-pixel tiles (a 20 x 20 map is 6 tiles at 52 % with GEOM 0, 4 tiles at 83 % with GEOM 1).
+template <int GEOM> struct Geom;
+template <> struct Geom<0> { static constexpr int TW = 16, TH = 8, PITCH = 24; };
+template <> struct Geom<1> { static constexpr int TW = 24, TH = 5, PITCH = 32; };
+
 constexpr int kMaxE = 4;                         // e-ring stages
 constexpr int kDTile = 128 * 128;                // one [128 x 64] bf16 tile
 constexpr int kGroupThreads = 256;               // threads of one depthwise group
@@ -42,7 +46,7 @@ constexpr int kFirstDwWarp = 6;                  // warp 0 producer, 1 MMA, 2-5 
 constexpr int kSmemLimit = 232448;
 
 struct MsParams {
-    int mode, ksize;
+    int mode, ksize, geom;
     int tiles_x, tiles_y, batch, total_tiles;
     uint32_t mg_tiles_x, mg_tiles_y;
     int e_ch, n_chunks, tail_ksteps;             // expanded channels, 64-channel chunks, k-steps of the last chunk
@@ -53,13 +57,14 @@ struct MsParams {
     int stage_bytes, off_dww, off_dwb, off_w2;   // layout of one e stage
     int so_x, so_e, so_d, so_w2, so_out, so_w1, so_bias;   // shared-memory carve-up (bytes from the 1024-aligned base)
     int x_kb_stride;                             // mode 2: bytes between the halo tiles of consecutive K blocks (hp * 128 rounded up to 1 KB)
+    int x_bufs, x_buf_bytes;                     // mode 2: 1 or 2 buffers for the input halo tile
     uint32_t stage_tx;                           // bytes TMA delivers per stage
     int bias_pad;
     const float* bias2;
     // mode 2
     int c_in1, c_in2, kb1, kb2;                  // pw1 sources (K-concatenated), 64-channel blocks of each
     int mt;                                      // M tiles (128 halo pixels each) of the pw1 GEMM
-    int hp;                                      // halo pixels = (16+k-1) * (8+k-1)
+    int hp;                                      // halo pixels = (TW+k-1) * (TH+k-1)
     int img_w, img_h;
     int w1_tile_bytes;                           // one [64 x 64] weight tile = 8192
     int g1_stride;                               // TMEM columns between the two pw1 accumulator stages
@@ -89,21 +94,23 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 }
 
 struct TileXY { int img, x0, y0; };
+template <int GEOM>
 __device__ __forceinline__ TileXY decode_tile(const MsParams& p, int t) {
     TileXY c;
     uint32_t q = fast_div((uint32_t)t, p.mg_tiles_x);
     const int tx = t - (int)q * p.tiles_x;
     const uint32_t q2 = fast_div(q, p.mg_tiles_y);
     const int ty = (int)(q - q2 * p.tiles_y);
-    c.img = (int)q2; c.x0 = tx * kTW; c.y0 = ty * kTH;
+    c.img = (int)q2; c.x0 = tx * Geom<GEOM>::TW; c.y0 = ty * Geom<GEOM>::TH;
     return c;
 }
 
-// Depthwise accumulation of one work item: 8 output pixels (row oy, x0 .. x0+7) x 4 channels, taps from the halo tile at e_base.
+// Depthwise accumulation of one work item: 8 output pixels (one row, x0 .. x0+7) x 4 channels.  eb[i] = address of this
+// thread's 8 bytes inside halo pixel (row oy, x0 + i) for i = 0..7 (the swizzle term depends on i & 7 only, so pixel x0 + j,
+// kernel row ky is eb[j & 7] + constant); w_base = this thread's 16 bytes of tap 0 in the [k*k][64] f32 weight block.
 // acc[o][0] = channels (4q, 4q+1), acc[o][1] = channels (4q+2, 4q+3) of output pixel o, as packed f32x2.
-template <int K>
-__device__ __forceinline__ void dw_accumulate(uint32_t e_base, uint32_t w_base, const uint32_t (&tbl)[8], int oy, int x0,
-                                              unsigned long long (&acc)[8][2]) {
+template <int K, int PITCH>
+__device__ __forceinline__ void dw_accumulate(const uint32_t (&eb)[8], uint32_t w_base, unsigned long long (&acc)[8][2]) {
     #pragma unroll
     for (int o = 0; o < 8; ++o) { acc[o][0] = 0ull; acc[o][1] = 0ull; }
     #pragma unroll
@@ -112,11 +119,10 @@ __device__ __forceinline__ void dw_accumulate(uint32_t e_base, uint32_t w_base, 
         #pragma unroll
         for (int kx = 0; kx < K; ++kx)
             asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w[kx][0]), "=l"(w[kx][1]) : "r"(w_base + (uint32_t)((ky * K + kx) * 256)));
-        const uint32_t rowbase = e_base + (uint32_t)(((oy + ky) * kPitch + x0) * 128);
         #pragma unroll
         for (int j = 0; j < 8 + K - 1; ++j) {
             uint32_t v0, v1;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(rowbase + tbl[j & 7] + (uint32_t)(j * 128)));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(eb[j & 7] + (uint32_t)((ky * PITCH + (j & ~7)) * 128)));
             const unsigned long long p0 = pack64(v0 << 16, v0 & 0xffff0000u);
             const unsigned long long p1 = pack64(v1 << 16, v1 & 0xffff0000u);
             #pragma unroll
@@ -131,32 +137,96 @@ __device__ __forceinline__ void dw_accumulate(uint32_t e_base, uint32_t w_base, 
     }
 }
 
-// bias + SiLU + bf16, written to row (oy*16 + x0 + o) of the [128 x 64] swizzled tile at d_base
-__device__ __forceinline__ void dw_store(uint32_t d_base, uint32_t b_addr, const uint32_t (&tbl)[8], int oy, int x0,
-                                         const unsigned long long (&acc)[8][2]) {
-    float4 b;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(b_addr));
-    b.x *= 0.5f; b.y *= 0.5f; b.z *= 0.5f; b.w *= 0.5f;
-    const uint32_t rowbase = d_base + (uint32_t)((oy * kTW + x0) * 128);
+// SiLU of two packed fp32 values given as acc (pre-activation without bias) and hb = 0.5 * bias:  h = 0.5 * acc + hb,
+// silu = h + h * tanh(h)  (conv_epilogue.cuh's one-MUFU form), both FMAs packed -> bf16x2
+__device__ __forceinline__ uint32_t silu2_bf16(unsigned long long acc, unsigned long long half2, unsigned long long hb) {
+    const unsigned long long h = fma2(acc, half2, hb);
+    float h0, h1, t0, t1;
+    unpack64(h, h0, h1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+    float r0, r1;
+    unpack64(fma2(h, pack64(__float_as_uint(t0), __float_as_uint(t1)), h), r0, r1);
+    return pack_bf16x2(r0, r1);
+}
+constexpr unsigned long long kHalf2 = 0x3f0000003f000000ull;     // (0.5f, 0.5f)
+
+// bias + SiLU + bf16, written to rows (r0 + o) of the [128 x 64] swizzled tile: db = d tile + r0 * 128 (r0 % 8 == 0), tbl[o] = swizzled
+// byte offset of this thread's 8 bytes inside a row with (row & 7) == o
+__device__ __forceinline__ void dw_store(uint32_t db, uint32_t b_addr, const uint32_t (&tbl)[8], const unsigned long long (&acc)[8][2]) {
+    unsigned long long b0, b1;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(b_addr));
+    b0 = fma2(b0, kHalf2, 0ull); b1 = fma2(b1, kHalf2, 0ull);
     #pragma unroll
     for (int o = 0; o < 8; ++o) {
-        float a0, a1, a2, a3;
-        unpack64(acc[o][0], a0, a1);
-        unpack64(acc[o][1], a2, a3);
-        const uint32_t o0 = pack_bf16x2(silu_from_half(fmaf(a0, 0.5f, b.x)), silu_from_half(fmaf(a1, 0.5f, b.y)));
-        const uint32_t o1 = pack_bf16x2(silu_from_half(fmaf(a2, 0.5f, b.z)), silu_from_half(fmaf(a3, 0.5f, b.w)));
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rowbase + tbl[o] + (uint32_t)(o * 128)), "r"(o0), "r"(o1) : "memory");
+        const uint32_t o0 = silu2_bf16(acc[o][0], kHalf2, b0);
+        const uint32_t o1 = silu2_bf16(acc[o][1], kHalf2, b1);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(db + tbl[o] + (uint32_t)(o * 128)), "r"(o0), "r"(o1) : "memory");
     }
 }
 
-template <int K>
+// k = 3, 16 x 8 tiles: register-blocked work item = 2 channels x a 4 x 4 block of output pixels.  Every input pixel of the
+// block's 6 x 6 halo is loaded (LDS.32: the 32 lanes of a warp are the 32 channel pairs of ONE pixel = its 128 contiguous
+// bytes) and converted ONCE and feeds up to 9 FFMA2; the 9 taps sit in registers.  ~390 instructions per 32 outputs against
+// ~740 for the row-strip item above (whose loads and conversions are repeated for every kernel row).
+//   e_blk = stage + ((by*4) * PITCH + bx*4) * 128, cp = channel pair (lane), xs = (bx*4) & 7 (0 or 4)
+template <int PITCH, int TW>
+__device__ __forceinline__ void dw_block_k3(uint32_t e_blk, uint32_t w_base, uint32_t b_addr, uint32_t d_blk, int cp, int xs) {
+    const uint32_t sub = (uint32_t)((cp & 3) * 4), chunk = (uint32_t)(cp >> 2);
+    uint32_t eb[6];
+    #pragma unroll
+    for (int j = 0; j < 6; ++j) eb[j] = e_blk + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)((xs + j) & 7)) << 4) + sub;
+    unsigned long long w[9];
+    #pragma unroll
+    for (int t = 0; t < 9; ++t) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(w[t]) : "r"(w_base + (uint32_t)(t * 256)));
+    unsigned long long acc[4][4];
+    #pragma unroll
+    for (int iy = 0; iy < 6; ++iy) {
+        unsigned long long v[6];
+        #pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            uint32_t u;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(eb[j] + (uint32_t)(iy * PITCH * 128)));
+            v[j] = pack64(u << 16, u & 0xffff0000u);
+        }
+        #pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int oy = iy - ky;
+            if (oy >= 0 && oy < 4) {
+                #pragma unroll
+                for (int ox = 0; ox < 4; ++ox) {
+                    #pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        acc[oy][ox] = (ky == 0 && kx == 0) ? fma2(v[ox], w[0], 0ull) : fma2(v[ox + kx], w[ky * 3 + kx], acc[oy][ox]);
+                }
+            }
+        }
+    }
+    unsigned long long hb;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(hb) : "r"(b_addr));
+    hb = fma2(hb, kHalf2, 0ull);
+    #pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+        const uint32_t db = d_blk + (uint32_t)(ox * 128) + ((chunk ^ (uint32_t)((xs + ox) & 7)) << 4) + sub;
+        #pragma unroll
+        for (int oy = 0; oy < 4; ++oy) {
+            const uint32_t o = silu2_bf16(acc[oy][ox], kHalf2, hb);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(db + (uint32_t)(oy * TW * 128)), "r"(o) : "memory");
+        }
+    }
+}
+
+template <int K, int GEOM>
 __global__ void __launch_bounds__(704, 1)
 ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_dww,
                 const __grid_constant__ CUtensorMap tm_dwb, const __grid_constant__ CUtensorMap tm_w2,
                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_w1,
                 const __grid_constant__ MsParams p) {
-    constexpr int HWX = kTW + K - 1, HWY = kTH + K - 1, PAD = K / 2;
+    constexpr int TW = Geom<GEOM>::TW, TH = Geom<GEOM>::TH, PITCH = Geom<GEOM>::PITCH;
+    constexpr int HWX = TW + K - 1, HWY = TH + K - 1, PAD = K / 2;
+    constexpr int kStripsX = TW / 8, kStrips = kStripsX * TH;
+    static_assert(HWX <= PITCH && TW * TH <= 128 && kStrips * 16 <= kGroupThreads, "tile geometry");
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
@@ -184,9 +254,9 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     const uint32_t w_bar = bar0 + 8u * (2 * kMaxE + 9);
     auto g1_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 10 + s); };      // mode 2: pw1 accumulator stage ready
     auto g1_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 12 + s); };
-    const uint32_t x_full = bar0 + 8u * (2 * kMaxE + 14);                        // mode 2: x halo tile landed / may be overwritten
-    const uint32_t x_empty = bar0 + 8u * (2 * kMaxE + 15);
-    constexpr int kNumBars = 2 * kMaxE + 16;
+    auto x_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 14 + s); };       // mode 2: x halo tile landed / may be overwritten
+    auto x_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 16 + s); };
+    constexpr int kNumBars = 2 * kMaxE + 18;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
     const int warp = threadIdx.x >> 5;
@@ -246,34 +316,39 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            uint32_t n = 0;                                    // chunk counter over the CTA's tiles
-            uint32_t xphase = 0;
+            int s = 0; uint32_t ph = 0;                        // e-ring stage / phase of the next chunk
+            int xb = 0; uint32_t xph = 0;                      // x buffer / phase of the next input halo tile
+            const int kbt = p.kb1 + p.kb2;
+            auto load_x = [&](int t) {
+                const TileXY tc = decode_tile<GEOM>(p, t);
+                mbar_wait_sleep(x_empty(xb), xph ^ 1u);
+                mbar_expect_tx(x_full(xb), (uint32_t)(kbt * HWX * HWY * 128));
+                for (int kb = 0; kb < kbt; ++kb)
+                    tma_load_4d(s_x + (uint32_t)(xb * p.x_buf_bytes + kb * p.x_kb_stride), kb < p.kb1 ? &tm_x : &tm_x2, x_full(xb),
+                                (kb < p.kb1 ? kb : kb - p.kb1) * 64, tc.x0 - PAD, tc.y0 - PAD, tc.img);
+                if (++xb == p.x_bufs) { xb = 0; xph ^= 1u; }
+            };
+            if (p.mode == 2 && (int)blockIdx.x < p.total_tiles) load_x(blockIdx.x);
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileXY tc = decode_tile(p, t);
-                if (p.mode == 2) {                             // the tile's input halo, all K blocks (single buffer, released by the last pw1 MMA)
-                    mbar_wait(x_empty, xphase ^ 1u);
-                    const int kbt = p.kb1 + p.kb2;
-                    mbar_expect_tx(x_full, (uint32_t)(kbt * HWX * HWY * 128));
-                    for (int kb = 0; kb < kbt; ++kb)
-                        tma_load_4d(s_x + (uint32_t)(kb * p.x_kb_stride), kb < p.kb1 ? &tm_x : &tm_x2, x_full,
-                                    (kb < p.kb1 ? kb : kb - p.kb1) * 64, tc.x0 - PAD, tc.y0 - PAD, tc.img);
-                    xphase ^= 1u;
-                }
-                for (int j = 0; j < p.n_chunks; ++j, ++n) {
-                    const int s = (int)(n % (uint32_t)p.e_stages);
-                    const uint32_t ph = (n / (uint32_t)p.e_stages) & 1u;
-                    mbar_wait(e_empty(s), ph ^ 1u);
+                const TileXY tc = decode_tile<GEOM>(p, t);
+                // the NEXT tile's input halo goes first: with two buffers it lands while this tile is processed; with one
+                // buffer it is issued after this tile's chunk loads (it has to wait for this tile's last pw1 MMA anyway)
+                if (p.mode == 2 && p.x_bufs == 2 && t + (int)gridDim.x < p.total_tiles) load_x(t + gridDim.x);
+                for (int j = 0; j < p.n_chunks; ++j) {
+                    mbar_wait_sleep(e_empty(s), ph ^ 1u);
                     const uint32_t st = s_e0 + (uint32_t)(s * p.stage_bytes);
                     mbar_expect_tx(e_full(s), p.stage_tx);
                     if (p.mode != 2) {
                         #pragma unroll 1
                         for (int hy = 0; hy < HWY; ++hy)
-                            tma_load_4d(st + (uint32_t)(hy * kRowPitchBytes), &tm_e, e_full(s), j * 64, tc.x0 - PAD, tc.y0 - PAD + hy, tc.img);
+                            tma_load_4d(st + (uint32_t)(hy * PITCH * 128), &tm_e, e_full(s), j * 64, tc.x0 - PAD, tc.y0 - PAD + hy, tc.img);
                     }
                     tma_load_2d(st + (uint32_t)p.off_dww, &tm_dww, e_full(s), j * 64, 0);
                     tma_load_2d(st + (uint32_t)p.off_dwb, &tm_dwb, e_full(s), j * 64, 0);
                     if (p.mode >= 1 && !p.w2_resident) tma_load_3d(st + (uint32_t)p.off_w2, &tm_w2, e_full(s), j * 64, 0, 0);
+                    if (++s == p.e_stages) { s = 0; ph ^= 1u; }
                 }
+                if (p.mode == 2 && p.x_bufs == 1 && t + (int)gridDim.x < p.total_tiles) load_x(t + gridDim.x);
             }
         }
     } else if (warp == 1) {
@@ -284,10 +359,13 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             const uint64_t hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             if (p.w2_resident || p.mode == 2) mbar_wait(w_bar, 0u);     // armed in the prologue only in these cases
             tc_fence_after();
-            uint32_t n = 0, ti = 0, xphase = 0;
+            uint32_t n = 0, ti = 0;
+            int s = 0; uint32_t ph = 0;                        // e-ring stage / phase of chunk n
+            int xb = 0; uint32_t xph = 0;                      // x buffer / phase of the next tile whose pw1 GEMM starts
             const int kbt = p.kb1 + p.kb2;
             const int tail1 = p.mode == 2 ? (((p.c_in1 - (p.kb1 - 1) * 64) + 15) >> 4) : 4;
             const int tail2 = (p.mode == 2 && p.kb2) ? (((p.c_in2 - (p.kb2 - 1) * 64) + 15) >> 4) : 4;
+            uint32_t sx_cur = s_x;                             // x buffer of the tile whose pw1 chunks are being issued
             auto issue_g1 = [&](uint32_t gn, int j) {
                 const int gs = (int)(gn & 1u);
                 mbar_wait(g1_empty(gs), ((gn >> 1) & 1u) ^ 1u);
@@ -295,7 +373,7 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                 for (int m = 0; m < p.mt; ++m) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
                     for (int kb = 0; kb < kbt; ++kb) {
-                        const uint32_t a16 = ((s_x + (uint32_t)(kb * p.x_kb_stride + m * kDTile)) & 0x3FFFFu) >> 4;
+                        const uint32_t a16 = ((sx_cur + (uint32_t)(kb * p.x_kb_stride + m * kDTile)) & 0x3FFFFu) >> 4;
                         const uint32_t b16 = ((s_w1 + (uint32_t)((j * kbt + kb) * p.w1_tile_bytes)) & 0x3FFFFu) >> 4;
                         const int ks = (kb == p.kb1 - 1) ? tail1 : ((kb == kbt - 1) ? tail2 : 4);
                         for (int k = 0; k < ks; ++k)
@@ -304,32 +382,39 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                 }
                 umma_commit(g1_full(gs));
             };
-            // mode 2: the pw1 GEMM runs one chunk AHEAD of the pw2 GEMM, also across tile boundaries (the x halo tile is a single
-            // buffer: it is released by the last pw1 MMA of its tile and refilled while the tile's remaining chunks are processed)
-            auto first_g1_of_tile = [&](uint32_t gn) {
-                mbar_wait(x_full, xphase); xphase ^= 1u;
-                tc_fence_after();
-                issue_g1(gn, 0);
-                if (p.n_chunks == 1) umma_commit(x_empty);
+            // mode 2: the pw1 GEMM runs TWO chunks ahead of the pw2 GEMM (both accumulator stages in flight), also across tile
+            // boundaries: pw1(n+2) is issued as soon as the pw1 epilogue of chunk n has drained its stage -- i.e. while the
+            // depthwise stage of chunk n is still running -- so that the group that finishes chunk n finds the accumulator of
+            // chunk n+2 ready.  (With a look-ahead of one, pw1(n+2) waited for pw2(n), i.e. for the END of the depthwise stage
+            // of chunk n, and every group idled for a pw1 GEMM latency per chunk.)  The x halo tile has one or two buffers; a
+            // buffer is released by the last pw1 MMA of its tile.
+            int g_t = blockIdx.x, g_j = 0; uint32_t g_n = 0;      // cursor of the next pw1 GEMM: tile, chunk, global chunk index
+            int xb_cur = 0;
+            auto issue_next_g1 = [&]() {
+                if (p.mode != 2 || g_t >= p.total_tiles) return;
+                if (g_j == 0) {
+                    mbar_wait(x_full(xb), xph);
+                    tc_fence_after();
+                    xb_cur = xb; sx_cur = s_x + (uint32_t)(xb * p.x_buf_bytes);
+                    if (++xb == p.x_bufs) { xb = 0; xph ^= 1u; }
+                }
+                issue_g1(g_n, g_j);
+                ++g_n;
+                if (++g_j == p.n_chunks) { umma_commit(x_empty(xb_cur)); g_j = 0; g_t += (int)gridDim.x; }
             };
-            if (p.mode == 2 && (int)blockIdx.x < p.total_tiles) first_g1_of_tile(0);
+            issue_next_g1();
+            issue_next_g1();
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
                 const int as = (int)(ti & 1u);
                 mbar_wait(acc_empty(as), ((ti >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
                 for (int j = 0; j < p.n_chunks; ++j, ++n) {
-                    if (p.mode == 2) {
-                        if (j + 1 < p.n_chunks) {
-                            issue_g1(n + 1, j + 1);
-                            if (j + 2 == p.n_chunks) umma_commit(x_empty);       // every pw1 MMA of this tile has been issued
-                        } else if (t + (int)gridDim.x < p.total_tiles) {
-                            first_g1_of_tile(n + 1);
-                        }
-                    }
+                    // pw1 of chunk n+2 first: its accumulator stage (n & 1) is free once the pw1 epilogue of chunk n is done,
+                    // which happens BEFORE the depthwise stage of chunk n that the pw2 MMAs below wait for
+                    issue_next_g1();
                     const int ds = (int)(n & 1u);
-                    const int s = (int)(n % (uint32_t)p.e_stages);
-                    if (!p.w2_resident) mbar_wait(e_full(s), (n / (uint32_t)p.e_stages) & 1u);
+                    if (!p.w2_resident) mbar_wait(e_full(s), ph);
                     mbar_wait(d_full(ds), (n >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t a16 = ((s_d0 + (uint32_t)ds * kDTile) & 0x3FFFFu) >> 4;
@@ -341,6 +426,7 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                     umma_commit(d_empty(ds));
                     if (!p.w2_resident) umma_commit(e_empty(s));
                     if (j == p.n_chunks - 1) umma_commit(acc_full(as));
+                    if (++s == p.e_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -362,9 +448,9 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             uint32_t res_phase = 0u, ti = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
                 const int as = (int)(ti & 1u);
-                const TileXY tc = decode_tile(p, t);
+                const TileXY tc = decode_tile<GEOM>(p, t);
                 EpiTile tl; tl.n0 = 0; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
-                mbar_wait(acc_full(as), (ti >> 1) & 1u);
+                mbar_wait_sleep(acc_full(as), (ti >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(as * p.acc_stride);
                 for (int ch = 0; ch < n_chunks_out; ++ch) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
@@ -379,38 +465,48 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         const int dwt = (int)threadIdx.x - kFirstDwWarp * 32;
         const int g = dwt >> 8, tg = dwt & 255;
         const int q = tg & 15, strip = tg >> 4;
-        const int oy = strip >> 1, x0 = (strip & 1) * 8;
+        const bool active = strip < kStrips;                                     // GEOM 1 has 15 strips for 16 slots
+        const int oy = active ? strip / kStripsX : 0, x0 = active ? (strip % kStripsX) * 8 : 0;
         uint32_t tbl[8];
         #pragma unroll
         for (int i = 0; i < 8; ++i) tbl[i] = ((uint32_t)((q >> 1) ^ i) << 4) + (uint32_t)((q & 1) * 8);
+        const uint32_t item_off = (uint32_t)((oy * PITCH + x0) * 128);          // this item's first halo pixel inside a stage
+        const uint32_t d_off = (uint32_t)((oy * TW + x0) * 128);                // and its first row inside the d tile
         const bool leader = tg == 0;
         const int bar_id = 2 + g;
+        const int wq = warp & 3;                                                 // TMEM lane quadrant this warp may read
+        const int wsub = (warp - kFirstDwWarp) & 7;                              // warp index inside the group
         uint32_t n = 0;
+        int s = 0; uint32_t ph = 0;
+        int gsel = 0;                                                            // group whose turn it is
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileXY tc = decode_tile(p, t);
+            TileXY tc; tc.img = 0; tc.x0 = 0; tc.y0 = 0;
+            if (p.mode != 1) tc = decode_tile<GEOM>(p, t);
             for (int j = 0; j < p.n_chunks; ++j, ++n) {
-                if ((int)(n % (uint32_t)p.dw_groups) != g) continue;
-                const int s = (int)(n % (uint32_t)p.e_stages);
-                const uint32_t st = s_e0 + (uint32_t)(s * p.stage_bytes);
+                const int s_cur = s; const uint32_t ph_cur = ph;
+                if (++s == p.e_stages) { s = 0; ph ^= 1u; }
+                const bool mine = gsel == g;
+                if (++gsel == p.dw_groups) gsel = 0;
+                if (!mine) continue;
+                const uint32_t st = s_e0 + (uint32_t)(s_cur * p.stage_bytes);
                 const int ds = (int)(n & 1u);
                 const uint32_t d_base = s_d0 + (uint32_t)ds * kDTile;
+                // the stage holds this chunk's depthwise weights (and, modes 0/1, its halo tile); in mode 2 this also says
+                // that the previous halo tile of the stage has been consumed, by whichever group used it
+                mbar_wait_sleep(e_full(s_cur), ph_cur);
                 if (p.mode == 2) {
                     // ---- pw1 epilogue: accumulator rows (halo pixels) -> bias / SiLU -> bf16 -> halo tile of this stage, zero outside the image
-                    // the stage is free (its previous halo tile has been consumed by whichever group used it) once the producer
-                    // could arm it for this chunk's depthwise weights
-                    mbar_wait(e_full(s), (n / (uint32_t)p.e_stages) & 1u);
                     const int gs = (int)(n & 1u);
-                    mbar_wait(g1_full(gs), (n >> 1) & 1u);
+                    mbar_wait_sleep(g1_full(gs), (n >> 1) & 1u);
                     tc_fence_after();
-                    const int wq = warp & 3;                                      // TMEM lane quadrant this warp may read
-                    const int wsub = (warp - kFirstDwWarp) & 7;                   // warp index inside the group
                     for (int m = wsub >> 2; m < p.mt; m += 2) {
                         const int hpix = m * 128 + wq * 32 + lane;                // halo pixel of this thread = accumulator row
+                        if (m * 128 + wq * 32 >= p.hp) break;                     // the whole warp is past the halo
                         const int hy = hpix / HWX, hx = hpix - hy * HWX;
                         const int gx = tc.x0 - PAD + hx, gy = tc.y0 - PAD + hy;
                         const bool inside = hpix < p.hp && gx >= 0 && gx < p.img_w && gy >= 0 && gy < p.img_h;
                         const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
-                        const uint32_t line = st + (uint32_t)((hy * kPitch + hx) * 128);
+                        const uint32_t line = st + (uint32_t)((hy * PITCH + hx) * 128);
                         #pragma unroll 1
                         for (int q16 = 0; q16 < 4; ++q16) {
                             uint32_t v[16];
@@ -422,12 +518,10 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                                 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     const float4 hb = bq[i];
-                                    const float f0 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 0]), 0.5f, hb.x));
-                                    const float f1 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, hb.y));
-                                    const float f2 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, hb.z));
-                                    const float f3 = silu_from_half(fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, hb.w));
-                                    o[2 * i] = inside ? pack_bf16x2(f0, f1) : 0u;
-                                    o[2 * i + 1] = inside ? pack_bf16x2(f2, f3) : 0u;
+                                    const uint32_t r0 = silu2_bf16(pack64(v[4 * i + 0], v[4 * i + 1]), kHalf2, pack64(__float_as_uint(hb.x), __float_as_uint(hb.y)));
+                                    const uint32_t r1 = silu2_bf16(pack64(v[4 * i + 2], v[4 * i + 3]), kHalf2, pack64(__float_as_uint(hb.z), __float_as_uint(hb.w)));
+                                    o[2 * i] = inside ? r0 : 0u;
+                                    o[2 * i + 1] = inside ? r1 : 0u;
                                 }
                                 #pragma unroll
                                 for (int h = 0; h < 2; ++h) {
@@ -441,28 +535,45 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(g1_empty(gs));
                     dwg_bar_sync(bar_id);                                         // the whole halo tile is written
-                } else {
-                    mbar_wait(e_full(s), (n / (uint32_t)p.e_stages) & 1u);
                 }
-                unsigned long long acc[8][2];
-                dw_accumulate<K>(st, st + (uint32_t)p.off_dww + (uint32_t)(q * 16), tbl, oy, x0, acc);
-                // the halo tile has been consumed (every load fed an FMA above); the stage may be refilled
-                if (p.mode == 0) {
-                    if (leader) { if (p.dw_groups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-                    dwg_bar_sync(bar_id);
+                // wait for the d buffer: mode 0 = its previous TMA store has read it; modes 1/2 = the MMAs that read it have retired
+                if constexpr (K == 3 && GEOM == 0) {
+                    // register-blocked item: the result is produced and stored block by block, so the buffer is needed up front
+                    if (p.mode == 0) {
+                        if (leader) { if (p.dw_groups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+                        dwg_bar_sync(bar_id);
+                    } else {
+                        mbar_wait_sleep(d_empty(ds), ((n >> 1) & 1u) ^ 1u);
+                    }
+                    const int cp = tg & 31, blk = tg >> 5, bx4 = (blk & 3) * 4, by4 = (blk >> 2) * 4;
+                    dw_block_k3<PITCH, TW>(st + (uint32_t)((by4 * PITCH + bx4) * 128), st + (uint32_t)p.off_dww + (uint32_t)(cp * 8),
+                                           st + (uint32_t)p.off_dwb + (uint32_t)(cp * 8), d_base + (uint32_t)((by4 * TW + bx4) * 128), cp, bx4 & 7);
                 } else {
-                    mbar_wait(d_empty(ds), ((n >> 1) & 1u) ^ 1u);
+                    unsigned long long acc[8][2];
+                    {
+                        uint32_t eb[8];
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) eb[i] = st + item_off + tbl[i] + (uint32_t)(i * 128);
+                        dw_accumulate<K, PITCH>(eb, st + (uint32_t)p.off_dww + (uint32_t)(q * 16), acc);
+                    }
+                    // the halo tile has been consumed (every load fed an FMA above); the stage may be refilled
+                    if (p.mode == 0) {
+                        if (leader) { if (p.dw_groups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+                        dwg_bar_sync(bar_id);
+                    } else {
+                        mbar_wait_sleep(d_empty(ds), ((n >> 1) & 1u) ^ 1u);
+                    }
+                    if (active) dw_store(d_base + d_off, st + (uint32_t)p.off_dwb + (uint32_t)(q * 16), tbl, acc);
                 }
-                dw_store(d_base, st + (uint32_t)p.off_dwb + (uint32_t)(q * 16), tbl, oy, x0, acc);
                 fence_proxy_async_smem();
                 if (p.mode == 0) {
                     dwg_bar_sync(bar_id);
                     if (leader) { tma_store_4d(&tm_y, d_base, j * 64, tc.x0, tc.y0, tc.img); tma_store_commit(); }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(e_empty(s));
+                    if (lane == 0) mbar_arrive(e_empty(s_cur));
                 } else {
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(d_full(ds)); mbar_arrive(e_empty(s)); }
+                    if (lane == 0) { mbar_arrive(d_full(ds)); mbar_arrive(e_empty(s_cur)); }
                 }
             }
         }
@@ -504,8 +615,9 @@ int encode_plain(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* a
     return 0;
 }
 
-template <int K> cudaError_t set_attr() {
-    return cudaFuncSetAttribute(ms_layer_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+template <int K> cudaError_t set_attr(int geom) {
+    return geom ? cudaFuncSetAttribute(ms_layer_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)
+                : cudaFuncSetAttribute(ms_layer_kernel<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
 }
 
 }  // namespace
@@ -534,11 +646,19 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     yms_ms_plan* pl = new (std::nothrow) yms_ms_plan();
     if (!pl) return fail(YMS_E_ARG, "ms: out of host memory");
     MsParams& kp = pl->kp;
+    // tile geometry: the one that wastes fewer pixels (ties: 16 x 8); the other one when the preferred one does not fit
+    const double u0 = (double)q->w * q->h / ((double)ceil_div(q->w, 16) * ceil_div(q->h, 8) * 128.0);
+    const double u1 = (double)q->w * q->h / ((double)ceil_div(q->w, 24) * ceil_div(q->h, 5) * 120.0);
+    const int preferred = u1 > u0 * 1.1 ? 1 : 0;
+    int kTW = 16, kTH = 8, hwx = 0, hwy = 0;
+    auto layout = [&](int geom) -> int {
     memset(&kp, 0, sizeof(kp));
-    kp.mode = q->mode; kp.ksize = k;
+    kp.mode = q->mode; kp.ksize = k; kp.geom = geom;
+    kTW = geom ? 24 : 16; kTH = geom ? 5 : 8;
+    const int kPitchB = (geom ? 32 : 24) * 128;
     kp.tiles_x = ceil_div(q->w, kTW); kp.tiles_y = ceil_div(q->h, kTH); kp.batch = q->batch;
     const long long total = (long long)kp.tiles_x * kp.tiles_y * q->batch;
-    if (total > 0x3fffffffLL) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: too many tiles"); }
+    if (total > 0x3fffffffLL) return fail(YMS_E_UNSUPPORTED, "ms: too many tiles");
     kp.total_tiles = (int)total;
     kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
     kp.e_ch = q->e_ch; kp.n_chunks = ceil_div(q->e_ch, 64);
@@ -546,14 +666,14 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     kp.c_out = q->mode >= 1 ? q->c_out : 0; kp.block_n = kp.c_out; kp.act2 = q->act2 ? 1 : 0;
     kp.bias2 = q->bias2; kp.bias1 = q->bias1;
     kp.img_w = q->w; kp.img_h = q->h;
-    const int hwx = kTW + k - 1, hwy = kTH + k - 1;
+    hwx = kTW + k - 1; hwy = kTH + k - 1;
     kp.hp = hwx * hwy; kp.mt = ceil_div(kp.hp, 128);
     kp.c_in1 = q->c_in; kp.c_in2 = q->c_in2;
     kp.kb1 = q->mode == 2 ? ceil_div(q->c_in, 64) : 0; kp.kb2 = q->mode == 2 ? ceil_div(q->c_in2, 64) : 0;
     kp.w1_tile_bytes = 64 * 128;
     kp.w2_tile_bytes = kp.block_n * 128;
     // one e stage: halo rows | depthwise weights [k*k][64] f32 | bias [64] f32 | (streamed pw2 weight chunk)
-    const int e_rows = hwy * kRowPitchBytes;
+    const int e_rows = hwy * kPitchB;
     kp.off_dww = e_rows; kp.off_dwb = e_rows + k * k * 256;
     int stage = kp.off_dwb + 256;
     stage = (stage + 1023) & ~1023;
@@ -564,19 +684,24 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
         kp.acc_stride = kp.block_n <= 32 ? 32 : (kp.block_n <= 64 ? 64 : (kp.block_n <= 128 ? 128 : 256));
         cols = 2 * kp.acc_stride;
         if (q->mode == 2) { kp.g1_base = cols; kp.g1_stride = kp.mt * 64; cols += 2 * kp.g1_stride; }
-        if (cols > 512) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: accumulators exceed the 512 TMEM columns"); }
+        if (cols > 512) return fail(YMS_E_UNSUPPORTED, "ms: accumulators exceed the 512 TMEM columns");
         int pow2 = 32; while (pow2 < cols) pow2 <<= 1;
         kp.tmem_cols = pow2;
     }
     kp.bias_pad = q->mode == 2 ? 256 + kp.n_chunks * 64 : 256;
     const int kbt = kp.kb1 + kp.kb2;
     kp.x_kb_stride = (kp.hp * 128 + 1023) & ~1023;
-    const int x_bytes = q->mode == 2 ? kbt * kp.x_kb_stride : 0;
+    kp.x_buf_bytes = kbt * kp.x_kb_stride;
+    kp.x_bufs = q->mode == 2 ? 2 : 0;
+    int x_bytes = kp.x_bufs * kp.x_buf_bytes;
     const int w1_bytes = q->mode == 2 ? kp.n_chunks * kbt * kp.w1_tile_bytes : 0;
     const int out_bytes = q->mode >= 1 ? kDTile : 0;
     const int tail_bytes = kp.bias_pad * 4 + (2 * kMaxE + 16) * 8 + 16;
-    const int fixed = x_bytes + 2 * kDTile + out_bytes + w1_bytes + tail_bytes + 1024 /* alignment slack */;
+    int fixed = x_bytes + 2 * kDTile + out_bytes + w1_bytes + tail_bytes + 1024 /* alignment slack */;
     const int w2_all = kp.n_chunks * kp.w2_tile_bytes;
+    // mode 2: a second input-halo buffer lets the next tile's input land while this tile is processed; dropped when the
+    // layer does not leave two e stages (+ resident pw2 weights) beside it
+    if (q->mode == 2 && kSmemLimit - fixed - w2_all < 2 * stage) { kp.x_bufs = 1; x_bytes = kp.x_buf_bytes; fixed -= kp.x_buf_bytes; }
     int budget = kSmemLimit - fixed;
     kp.w2_resident = 0;
     if (q->mode >= 1) {
@@ -588,7 +713,7 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     kp.stage_bytes = stage;
     int stages = budget / stage;
     if (stages > kMaxE) stages = kMaxE;
-    if (stages < 2) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: the layer does not fit in shared memory (use the unfused kernels)"); }
+    if (stages < 2) return fail(YMS_E_UNSUPPORTED, "ms: the layer does not fit in shared memory (use a lower fusion mode)");
     kp.e_stages = stages;
     kp.dw_groups = 2;
     kp.stage_tx = (uint32_t)((q->mode != 2 ? hwx * hwy * 128 : 0) + k * k * 256 + 256 + ((q->mode >= 1 && !kp.w2_resident) ? kp.w2_tile_bytes : 0));
@@ -600,7 +725,12 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     kp.so_w1 = kp.so_out + out_bytes;
     kp.so_bias = kp.so_w1 + w1_bytes;
     pl->smem = (size_t)kp.so_bias + tail_bytes + 1024;
-    if (pl->smem > (size_t)kSmemLimit) { delete pl; return fail(YMS_E_UNSUPPORTED, "ms: shared-memory budget exceeded"); }
+    if (pl->smem > (size_t)kSmemLimit) return fail(YMS_E_UNSUPPORTED, "ms: shared-memory budget exceeded");
+    return 0;
+    };
+    int lrc = layout(preferred);
+    if (lrc == YMS_E_UNSUPPORTED) lrc = layout(1 - preferred);
+    if (lrc) { delete pl; return lrc; }
     pl->grid = kp.total_tiles < kNumSMs ? kp.total_tiles : kNumSMs;
     pl->threads = 64 + 128 + kp.dw_groups * kGroupThreads;
 
@@ -664,10 +794,10 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
 
     cudaError_t e = cudaSuccess;        // per call: the attribute is per device, and plan creation is not a hot path
     switch (k) {
-        case 3: e = set_attr<3>(); break;
-        case 5: e = set_attr<5>(); break;
-        case 7: e = set_attr<7>(); break;
-        default: e = set_attr<9>(); break;
+        case 3: e = set_attr<3>(kp.geom); break;
+        case 5: e = set_attr<5>(kp.geom); break;
+        case 7: e = set_attr<7>(kp.geom); break;
+        default: e = set_attr<9>(kp.geom); break;
     }
     if (e != cudaSuccess) { delete pl; return fail((int)e, "ms: smem attribute: %s", cudaGetErrorString(e)); }
     *out = pl;
@@ -678,8 +808,10 @@ extern "C" int yms_ms_plan_run(const yms_ms_plan* pl, void* stream) {
     if (!pl) return fail(YMS_E_ARG, "ms: null plan");
     cudaError_t le;
     cudaStream_t st = (cudaStream_t)stream;
-#define YMS_MS_LAUNCH(K) le = launch_pdl(ms_layer_kernel<K>, pl->grid, pl->threads, pl->smem, st, pl->tm_e, pl->tm_dww, pl->tm_dwb, pl->tm_w2, \
-                                         pl->tm_y, pl->tm_x, pl->tm_x2, pl->tm_w1, pl->kp)
+#define YMS_MS_LAUNCH(K) le = pl->kp.geom ? launch_pdl(ms_layer_kernel<K, 1>, pl->grid, pl->threads, pl->smem, st, pl->tm_e, pl->tm_dww, pl->tm_dwb, \
+                                                      pl->tm_w2, pl->tm_y, pl->tm_x, pl->tm_x2, pl->tm_w1, pl->kp) \
+                                         : launch_pdl(ms_layer_kernel<K, 0>, pl->grid, pl->threads, pl->smem, st, pl->tm_e, pl->tm_dww, pl->tm_dwb, \
+                                                      pl->tm_w2, pl->tm_y, pl->tm_x, pl->tm_x2, pl->tm_w1, pl->kp)
     switch (pl->kp.ksize) {
         case 3: YMS_MS_LAUNCH(3); break;
         case 5: YMS_MS_LAUNCH(5); break;

@@ -34,6 +34,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` elapse, instead of
+// spinning through the issue slots other warps of the SM need (long waits of whole warp groups, e.g. csrc/ms_fused.cu).
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok;
+}
+// Bounded wait for warps that may wait long: sleeping try_wait, the trap clock is only read between sleeps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_hint(bar, parity, 4000u)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 #ifdef YMS_PROF
 static __device__ unsigned long long* g_trap_buf = nullptr;   // per translation unit; set by yms_debug_*_trap_buf
 #endif

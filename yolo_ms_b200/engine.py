@@ -70,6 +70,10 @@ class Program:
         self.bytes = 0.0
         self.raw_tail: List[ops.ConvPlan] = []   # decode-fused programs: the plans that store the raw head logits instead
         self.decoded: Optional[dict] = None      # decode-fused programs: static pred / candidate buffers + the stride tensor
+        self.post: dict = {}                     # max_det -> ops.PostBuffers (static NMS / gather outputs of YOLOv8.detect)
+        self.full_graphs: dict = {}              # (input address, conf, iou, max_det) -> (graph of the WHOLE step, outputs)
+        self.full_keep: list = []
+        self.seen: dict = {}
 
     # ---- buffers -------------------------------------------------------------------------
     def buf(self, b: int, h: int, w: int, c: int, dtype=torch.bfloat16) -> torch.Tensor:
@@ -186,12 +190,44 @@ class Program:
         best.desc = default_plan.desc + (f" [v{best.variant}]" if best.variant else "")
         return best
 
-    def ms_layer(self, plan: "ops.MsLayerPlan"):
-        """A fused MS-Block layer (ops.MsLayerPlan): one launch, costed like a convolution plan."""
+    def ms_layer(self, plan):
+        """A ready-made plan (ops.MsLayerPlan / ops.ConvPlan): one launch, costed by the plan itself."""
         self.plans.append(plan)
+        self.hold(*[t for t in plan._keep if t is not None])
         self._push(plan.run, plan.desc)
         self.flops += plan.flops
         self.bytes += plan.bytes
+
+    def pick_fastest(self, key, candidates):
+        """candidates: [(tag, [plans])], most fused first.  With the autotuner on, every candidate sequence is timed on the
+        layer's real buffers (decision cached per process under `key`); otherwise the first one is taken."""
+        if not AUTOTUNE or len(candidates) == 1:
+            return candidates[0]
+        known = _TUNE_CACHE.get(key)
+        if known is not None:
+            for c in candidates:
+                if c[0] == known:
+                    return c
+        def timed(plans):
+            for _ in range(2):
+                for pl in plans:
+                    pl.run()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                for pl in plans:
+                    pl.run()
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b)
+        best, best_t = candidates[0], timed(candidates[0][1])
+        for c in candidates[1:]:
+            t = timed(c[1])
+            if t < 0.97 * best_t:
+                best, best_t = c, t
+        _TUNE_CACHE[key] = best[0]
+        self.tuned.append((key, best[0]))
+        return best
 
     def add(self, fn: Callable[[], None], nbytes: float = 0.0, flops: float = 0.0, name: str = "op"):
         self._push(fn, name)

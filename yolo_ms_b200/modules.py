@@ -47,18 +47,27 @@ def yolo_params(version):
     return _VERSIONS[version]
 
 
+_WEIGHTS_EPOCH = [0]     # bumped whenever ANY compiled module's parameters may have been replaced (load_state_dict / .to() / ...)
+
+
 class _Compiled(nn.Module):
-    """Mixin: per-shape program cache that is dropped whenever parameters may have changed."""
+    """Mixin: per-shape program cache.  Programs bake in folded-BN bf16 weights, so they are dropped whenever parameters may
+    have changed: `load_state_dict` / `_apply` (.to, .half, ...) on this module OR on any other compiled module -- a parent's
+    program holds its children's weights, and `model.head.load_state_dict(...)` must invalidate `model`'s program too, hence
+    one process-wide epoch instead of per-module flags.  In-place edits that bypass those calls (`p.data.copy_`, an optimizer
+    step) cannot be seen from here: call `refresh()` after them."""
 
     def _programs(self) -> Dict:
         cache = self.__dict__.get("_yms_cache")
-        if cache is None:
+        if cache is None or self.__dict__.get("_yms_epoch") != _WEIGHTS_EPOCH[0]:
             cache = {}
             self.__dict__["_yms_cache"] = cache
+            self.__dict__["_yms_epoch"] = _WEIGHTS_EPOCH[0]
         return cache
 
     def refresh(self):
         """Drop compiled programs (call after modifying parameters in place)."""
+        _WEIGHTS_EPOCH[0] += 1
         for m in self.modules():
             m.__dict__.pop("_yms_cache", None)
         return self
@@ -70,9 +79,6 @@ class _Compiled(nn.Module):
     def load_state_dict(self, *a, **k):
         self.refresh()
         return super().load_state_dict(*a, **k)
-
-    def train(self, mode: bool = True):
-        return super().train(mode)
 
 
 def _device_of(m: nn.Module) -> torch.device:
@@ -215,61 +221,65 @@ class MSBlock(_Compiled):
         self.branches = nn.ModuleList(branches)
         self.out_conv = Conv(3 * c, out_channels, kernel_size=1, stride=1, padding=0)
 
-    def _emit_layer(self, P, layer, src, src2, dst):
-        """One branch layer pw1 -> dw -> pw2 over src (+ src2: conv(src + src2) as a K-concatenated GEMM with repeated
-        weights).  Fused as far as the layer fits the kernel's budgets (csrc/ms_fused.cu): whole layer, dw -> pw2, or unfused."""
+    def _emit_layer(self, P, layer, src, dup, dst):
+        """One branch layer pw1 -> dw -> pw2 over src.  dup: src is the 2c-wide slice [a | b] of the two tensors whose SUM the
+        layer takes -- conv(a + b) = K-concatenated GEMM with the pw1 weights repeated along K (exact in fp32 accumulation).
+        Three implementations (csrc/ms_fused.cu): the whole layer in one kernel (when it fits the shared-memory / TMEM
+        budgets), pw1 + (dw -> pw2), or three launches; the fastest one on this layer's buffers is kept (engine.pick_fastest;
+        YMS_AUTOTUNE=0: the most fused one that fits).  They differ in fp32 summation order only."""
         k = self.kernel_size
-        b, hh, ww, c = src.shape
+        b, hh, ww, _ = src.shape
+        if not (layer.pw1.has_act and layer.dw.has_act and layer.pw1.conv.groups == 1 and layer.pw2.conv.groups == 1):
+            e = layer.pw1.emit(P, src, dup_k=dup)
+            return layer.pw2.emit(P, layer.dw.emit(P, e), out=dst)
         wd, bd = layer.dw.dw_folded()
+        w1f, b1 = layer.pw1.folded()
         w2f, b2 = layer.pw2.folded()
-        w2 = w2f.reshape(w2f.shape[0], -1).contiguous().to(torch.bfloat16)
-        b2 = b2.contiguous()
+        if dup:
+            w1f = torch.cat([w1f, w1f], 1)
+        w1 = w1f.reshape(w1f.shape[0], -1).contiguous().to(torch.bfloat16)        # [E, K]
+        w2 = w2f.reshape(w2f.shape[0], -1).contiguous().to(torch.bfloat16)        # [c, E]
+        b1, b2 = b1.contiguous(), b2.contiguous()
+        e_ch = w1.shape[0]
         if dst is None:
             dst = P.buf(b, hh, ww, w2.shape[0])
-        plain = layer.pw1.has_act and layer.dw.has_act and layer.dw.conv.stride[0] == 1
-        if MS_FUSE >= 2 and plain:
-            w1f, b1 = layer.pw1.folded()
-            w1 = w1f.reshape(w1f.shape[0], -1)
-            if src2 is not None:
-                w1 = torch.cat([w1, w1], 1)
-            w1 = w1.contiguous().to(torch.bfloat16)
-            b1 = b1.contiguous()
+        act2 = layer.pw2.has_act
+        cands = []
+        if MS_FUSE >= 2:
             try:
-                plan = ops.MsLayerPlan(2, dst, k, wd, bd, x=src, x2=src2, w1=w1, bias1=b1, w2=w2, bias2=b2, act2=layer.pw2.has_act)
-                P.hold(wd, bd, w1, b1, w2, b2)
-                P.ms_layer(plan)
-                return dst
+                cands.append(("fused", [ops.MsLayerPlan(2, dst, k, wd, bd, x=src, w1=w1, bias1=b1, w2=w2, bias2=b2, act2=act2)]))
             except YmsError:
                 pass
-        e = layer.pw1.emit(P, src, x2=src2, dup_k=src2 is not None)
-        if MS_FUSE >= 1 and plain:
+        e = torch.empty((b, hh, ww, e_ch), dtype=torch.bfloat16, device=src.device)
+        pw1 = ops.ConvPlan(src, w1.unsqueeze(0), b1, e, ksize=1, stride=1, act=True)
+        if MS_FUSE >= 1:
             try:
-                plan = ops.MsLayerPlan(1, dst, k, wd, bd, e=e, w2=w2, bias2=b2, act2=layer.pw2.has_act)
-                P.hold(wd, bd, w2, b2)
-                P.ms_layer(plan)
-                return dst
+                cands.append(("dw+pw2", [pw1, ops.MsLayerPlan(1, dst, k, wd, bd, e=e, w2=w2, bias2=b2, act2=act2)]))
             except YmsError:
                 pass
-        d = layer.dw.emit(P, e)
-        return layer.pw2.emit(P, d, out=dst)
+        d = torch.empty_like(e)
+        cands.append(("unfused", [pw1, ops.MsLayerPlan(0, d, k, wd, bd, e=e), ops.ConvPlan(d, w2.unsqueeze(0), b2, dst, ksize=1, stride=1, act=act2)]))
+        key = ("ms-layer", str(src.device), tuple(src.shape), src.stride(-2), dst.stride(-2), e_ch, k, tuple(c[0] for c in cands))
+        tag, plans = P.pick_fastest(key, cands)
+        del cands, e, d                                     # the losing candidates' scratch tensors die with their plans
+        for pl in plans:
+            P.ms_layer(pl)
+        return dst
 
     def emit(self, P, x, out=None):
+        """One buffer [x0 | x1 | x2 | y1 | y2] (5c channels): in_conv fills the first three slots, the branches the last two.
+        The branch inputs x1 + x0 and x2 + y1 are then ADJACENT slices ([x0|x1], [x2|y1]): one 2c-wide source each, and
+        out_conv reads cat[x0, y1, y2] as x0 plus the adjacent pair [y1|y2]."""
         c = self.mid_channels
         b, hh, ww, _ = x.shape
-        y = self.in_conv.emit(P, x)                         # [x0 | x1 | x2]
-        tail = P.buf(b, hh, ww, 2 * c)                      # [y1 | y2]
-        prev = y[..., :c]
+        y = P.buf(b, hh, ww, 5 * c)
+        self.in_conv.emit(P, x, out=y[..., :3 * c])
         for bi, layers in enumerate(self.branches):
-            xi = y[..., (bi + 1) * c:(bi + 2) * c]
-            t = None
+            t = y[..., 0:2 * c] if bi == 0 else y[..., 2 * c:4 * c]
             for li, layer in enumerate(layers):
-                dst = tail[..., bi * c:(bi + 1) * c] if li == len(layers) - 1 else None
-                if li == 0:   # conv(x_i + y_{i-1}) = K-concatenated GEMM with repeated weights
-                    t = self._emit_layer(P, layer, xi, prev, dst)
-                else:
-                    t = self._emit_layer(P, layer, t, None, dst)
-            prev = t
-        return self.out_conv.emit(P, y[..., :c], out=out, x2=tail)
+                dst = y[..., (3 + bi) * c:(4 + bi) * c] if li == len(layers) - 1 else None
+                t = self._emit_layer(P, layer, t, li == 0, dst)
+        return self.out_conv.emit(P, y[..., :c], out=out, x2=y[..., 3 * c:5 * c])
 
     def forward(self, x):
         return _run_standalone(self, (x,), lambda P, xs: (self.emit(P, xs[0]),))[0]
@@ -480,9 +490,31 @@ class Head(_Compiled):
         self.cls = nn.ModuleList([branch(c, num_classes) for c in chans])
         self.dfl = DFL()                                  # the reference ignores `ch` here too (:113)
 
+    @property
+    def nc_pad(self) -> int:
+        """Class channels as the kernels see them: the class branch is zero-padded to a multiple of 16 when the weights are
+        packed (state_dict keys and shapes stay the reference's).  Padded channels carry logit -1e4 -> score exactly 0, so
+        they never win the arg-max; predictions and raw outputs are sliced back to num_classes."""
+        return (self.num_classes + 15) // 16 * 16
+
     def can_fuse_decode(self) -> bool:
-        """The decode-fused epilogue handles class counts that are a multiple of 16 up to 128 (include/yms_b200.h)."""
-        return FUSE_DECODE and self.ch == 16 and self.num_classes % 16 == 0 and 0 < self.num_classes <= 128
+        """The decode-fused epilogue handles (padded) class counts up to 128 (include/yms_b200.h)."""
+        return FUSE_DECODE and self.ch == 16 and 0 < self.nc_pad <= 128
+
+    def _cls_padded(self, i):
+        """Folded weights of cls[i] with every class dimension zero-padded from num_classes to nc_pad."""
+        nc, ncp = self.num_classes, self.nc_pad
+        w0, b0 = self.cls[i][0].folded()
+        w1, b1 = self.cls[i][1].folded()
+        w2, b2 = self.cls[i][2].weight.detach().float(), self.cls[i][2].bias.detach().float()
+        if ncp != nc:
+            pad_o = lambda t: torch.cat([t, t.new_zeros((ncp - nc,) + tuple(t.shape[1:]))], 0)
+            pad_i = lambda t: torch.cat([t, t.new_zeros((t.shape[0], ncp - nc) + tuple(t.shape[2:]))], 1)
+            w0, b0 = pad_o(w0), pad_o(b0)
+            w1, b1 = pad_i(pad_o(w1)), pad_o(b1)
+            w2 = pad_i(pad_o(w2))
+            b2 = torch.cat([b2, b2.new_full((ncp - nc,), -1.0e4)])
+        return (w0, b0), (w1, b1), (w2, b2)
 
     def emit(self, P, feats: Sequence[torch.Tensor], fuse_decode: bool = False) -> List[torch.Tensor]:
         """-> 3 fp32 raw tensors [B,H,W,64+nc] (box | cls), yolov8_head.py:119-122.
@@ -493,11 +525,13 @@ class Head(_Compiled):
         if self.ch != 16:
             raise RuntimeError("DFL is fixed to 16 bins (the reference builds DFL() with its default ch)")
         raws = []
+        nc, ncp = self.num_classes, self.nc_pad
+        nop = self.coordinates + ncp
         if fuse_decode:
             b = feats[0].shape[0]
             anchors = sum(f.shape[1] * f.shape[2] for f in feats)
             dev = feats[0].device
-            dec = {"pred": torch.empty((b, anchors, 4 + self.num_classes), dtype=torch.float32, device=dev),
+            dec = {"pred": torch.empty((b, anchors, 4 + ncp), dtype=torch.float32, device=dev),
                    "boxes": torch.empty((b, anchors, 4), dtype=torch.float32, device=dev),
                    "scores": torch.empty((b, anchors), dtype=torch.float32, device=dev),
                    "labels": torch.empty((b, anchors), dtype=torch.int32, device=dev),
@@ -509,20 +543,23 @@ class Head(_Compiled):
         for i, f in enumerate(feats):
             P.branch(i)
             b, h, w, _ = f.shape
-            raw = P.buf(b, h, w, self.no, dtype=torch.float32)
+            raw = P.buf(b, h, w, nop, dtype=torch.float32)
             # box[i][0] and cls[i][0] read the same feature map: ONE 3x3 conv with the two weight sets
             # stacked along c_out (64 + nc) reads it once; the second convs take channel slices.
             wb, bb = self.box[i][0].folded()
-            wc, bc = self.cls[i][0].folded()
-            first = P.buf(b, h, w, self.no)
+            (wc, bc), (wc1, bc1), (wc2, bc2) = self._cls_padded(i)
+            first = P.buf(b, h, w, nop)
             P.conv(pack_weight(torch.cat([wb, wc], 0)), torch.cat([bb, bc]).contiguous(), f, first, ksize=3, stride=1, act=True)
-            for seq, lo, hi in ((self.box[i], 0, self.coordinates), (self.cls[i], self.coordinates, self.no)):
-                t = seq[1].emit(P, first[..., lo:hi])
-                last = seq[2]
-                wl = pack_weight(last.weight.detach().float())
-                bl = last.bias.detach().float().contiguous()
+            for kind, lo, hi in (("box", 0, self.coordinates), ("cls", self.coordinates, nop)):
+                if kind == "box":
+                    t = self.box[i][1].emit(P, first[..., lo:hi])
+                    last = self.box[i][2]
+                    wl, bl = pack_weight(last.weight.detach().float()), last.bias.detach().float().contiguous()
+                else:
+                    t = P.buf(b, h, w, ncp)
+                    P.conv(pack_weight(wc1), bc1.contiguous(), first[..., lo:hi], t, ksize=3, stride=1, act=self.cls[i][1].has_act)
+                    wl, bl = pack_weight(wc2), bc2.contiguous()
                 if fuse_decode:
-                    kind = "box" if lo == 0 else "cls"
                     cand = {"cand_boxes": dec["boxes"]} if lo == 0 else {"cand_scores": dec["scores"], "cand_labels": dec["labels"]}
                     P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False,
                            decode=dict(branch=kind, stride=dec["stride"][i:i + 1], pred=dec["pred"], anchor_base=base, **cand))
@@ -546,12 +583,13 @@ class Head(_Compiled):
         return cached[1]
 
     def decode(self, raws):
-        return ops.head_decode(raws, self._stride_list(), self.num_classes)
+        """raws: the program's [B,H,W,64+nc_pad] logits -> [B,A,4+num_classes] (a view when classes were padded)."""
+        return ops.head_decode(raws, self._stride_list(), self.nc_pad)[..., :4 + self.num_classes]
 
     def forward(self, x):
         raws = _run_standalone(self, tuple(x), lambda P, xs: tuple(self.emit(P, xs)), raw_out=True)
         if self.training:
-            return [r.permute(0, 3, 1, 2) for r in raws]
+            return [r.permute(0, 3, 1, 2)[:, :self.no] for r in raws]
         return self.decode([r.contiguous() for r in raws])
 
 
@@ -578,6 +616,12 @@ class YOLOv8(_Compiled):
         live in device memory and follow head.stride (a plain attribute in the reference) from call to call."""
         prog, io = _get_program(self, (x,), self._build, image_input=True)
         io["inputs"][0].bind(x)
+        self._sync_stride(prog)
+        prog.run()
+        return prog, io
+
+    def _sync_stride(self, prog):
+        """head.stride is a plain attribute in the reference: the program reads it from device memory, refreshed when it changes."""
         dec = prog.decoded
         if dec is not None:
             vals = self.head._stride_list()
@@ -586,11 +630,9 @@ class YOLOv8(_Compiled):
                     raise YmsError("head.stride must hold 3 values")
                 dec["stride"][:3].copy_(torch.tensor(vals, dtype=torch.float32))
                 dec["stride_vals"] = list(vals)
-        prog.run()
-        return prog, io
 
     def forward_raw(self, x):
-        """Run the network; returns the program's static fp32 raw head buffers [B,H,W,64+nc]."""
+        """Run the network; returns the program's static fp32 raw head buffers [B,H,W,64+nc_pad] (nc_pad = classes rounded up to 16)."""
         prog, io = self._run(x)
         for plan in prog.raw_tail:        # decode-fused program: the logits are only stored on request
             plan.run()
@@ -598,25 +640,68 @@ class YOLOv8(_Compiled):
 
     def forward(self, x):
         if self.head.training:
-            return [r.permute(0, 3, 1, 2).clone() for r in self.forward_raw(x)]
+            return [r.permute(0, 3, 1, 2)[:, :self.head.no].clone() for r in self.forward_raw(x)]
         prog, io = self._run(x)
-        if prog.decoded is not None:
-            return prog.decoded["pred"].clone()            # the program's buffer is overwritten by the next call
+        if prog.decoded is not None:                       # the program's buffer is overwritten by the next call
+            return prog.decoded["pred"][..., :4 + self.head.num_classes].clone()
         return self.head.decode(io["outputs"])
 
     @torch.no_grad()
-    def detect(self, x, conf_thresh: float = 0.25, iou_thresh: float = 0.45):
-        """Fused forward + decode + class-aware NMS (the reference's tools/test.py:160-218 per
-        batch).  Returns (boxes [B,A,4], scores [B,A], labels [B,A], keep [B,A], count [B]); boxes / scores / labels
-        are the program's static candidate buffers (valid until the next call on this model with the same shape)."""
-        prog, io = self._run(x)
-        if prog.decoded is not None:
-            boxes, scores, labels = prog.decoded["boxes"], prog.decoded["scores"], prog.decoded["labels"]
-        else:
-            _, (boxes, scores, labels) = ops.head_decode(io["outputs"], self.head._stride_list(), self.head.num_classes,
-                                                         with_candidates=True)
-        keep, count = ops.nms_batched(boxes, scores, labels, conf_thresh, iou_thresh, self.head.num_classes)
-        return boxes, scores, labels, keep, count
+    def detect(self, x, conf_thresh: float = 0.25, iou_thresh: float = 0.45, max_det: Optional[int] = None):
+        """Fused forward + decode + class-aware NMS (the reference's tools/test.py:160-218 per batch).
+        Returns (boxes [B,A,4], scores [B,A], labels [B,A], keep [B,A], count [B]) -- plus dets [B,max_det,6] rows
+        (x1,y1,x2,y2,score,label; label -1 = unused) when max_det is given.  All of them are the program's STATIC buffers
+        (valid until the next call on this model with the same input shape): nothing is allocated per call.
+
+        Steady state: when the same input tensor storage shows up again (a caller recycling its input buffers, as a
+        pipelined inference loop does), the WHOLE step -- stem, every conv / glue launch, decode, NMS, gather -- is replayed
+        as ONE CUDA graph captured for that input address: one host call per step.  Other calls run the stem and the
+        post-process as separate launches around the program's graph."""
+        prog, io = _get_program(self, (x,), self._build, image_input=True)
+        slot = io["inputs"][0]
+        slot.bind(x)
+        self._sync_stride(prog)
+        nc = self.head.nc_pad
+        key = (slot.tensor.data_ptr(), float(conf_thresh), float(iou_thresh), max_det)
+        full = prog.full_graphs.get(key)
+        if full is not None:
+            full[0].replay()
+            return full[1]
+        b = slot.shape[0]
+        anchors = sum(t.shape[1] * t.shape[2] for t in io["outputs"])
+        post = prog.post.get(max_det)
+        if post is None:
+            post = prog.post[max_det] = ops.PostBuffers(b, anchors, prog.device, max_det)
+
+        def step(run_program, pb):
+            run_program()
+            if prog.decoded is not None:
+                boxes, scores, labels = prog.decoded["boxes"], prog.decoded["scores"], prog.decoded["labels"]
+            else:
+                _, (boxes, scores, labels) = ops.head_decode(io["outputs"], self.head._stride_list(), nc, with_candidates=True)
+            keep, count = ops.nms_batched(boxes, scores, labels, conf_thresh, iou_thresh, nc, out=pb)
+            outs = (boxes, scores, labels, keep, count)
+            if max_det is not None:
+                outs = outs + (ops.gather_detections(boxes, scores, labels, keep, count, max_det, out=pb.dets),)
+            return outs
+
+        if len(prog.seen) > 64:                               # a caller that never recycles its input buffers
+            prog.seen.clear()
+        seen = prog.seen.get(key, 0) + 1
+        prog.seen[key] = seen
+        if seen >= 2 and prog.decoded is not None and len(prog.full_graphs) < 8:
+            # every captured input address gets its OWN keep / count / dets buffers: a pipelined caller reads the results of
+            # buffer A (device -> host copy on another stream) while the step on buffer B is already running
+            pb = ops.PostBuffers(b, anchors, prog.device, max_det)
+            torch.cuda.synchronize(prog.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = step(prog.run_eager, pb)
+            prog.full_graphs[key] = (g, outs)
+            prog.full_keep.append((slot.tensor, pb))          # the captured addresses must stay alive
+            g.replay()
+            return outs
+        return step(prog.run, post)
 
 
 # =============================================================================================

@@ -31,13 +31,15 @@ def extract_state_dict(checkpoint):
     return sd
 
 
-def load_checkpoint(model, checkpoint_path, strict=True, map_location="cpu"):
+def load_checkpoint(model, checkpoint_path, strict=True, map_location="cpu", trusted=False):
     """Load a reference ``.pt`` checkpoint into a yolo_ms_b200 model (same state_dict keys as the reference's modules).
     The compiled launch programs (folded BN, packed bf16 weights) are rebuilt lazily on the next forward.
+    Checkpoints are un-pickled with ``weights_only=True`` (what the reference's plain ``torch.load`` does on current torch):
+    only tensors and plain containers are accepted; ``trusted=True`` allows arbitrary pickled objects for files you made.
     Returns (missing_keys, unexpected_keys) like ``nn.Module.load_state_dict``."""
     if not os.path.exists(checkpoint_path):
         raise FileNotFoundError(f"Checkpoint file not found: {checkpoint_path}")
-    sd = extract_state_dict(torch.load(checkpoint_path, map_location=map_location, weights_only=False))
+    sd = extract_state_dict(torch.load(checkpoint_path, map_location=map_location, weights_only=not trusted))
     res = model.load_state_dict(sd, strict=strict)
     return list(res.missing_keys), list(res.unexpected_keys)
 
