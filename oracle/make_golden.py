@@ -11,6 +11,7 @@ Outputs (all small, committed):
   post_n.npz                   reference post-process (tools/test.py:166-218 with the real
                                torchvision.ops.nms) on a reference prediction
   nms_cases.npz                torchvision.ops.nms keep lists on adversarial box sets
+  tools_test_sample.json       the detection records written by the reference's inference app test() (tools/test.py:63-276)
   dwconv_ref.npz               the reference's own Conv unit run as a depthwise layer, Conv(c, c, k, 1, k//2, groups=c)
                                (components.py:69-77; the reference never instantiates it that way, but the class supports it),
                                k = 3/5/7/9, and the MS-Block branch layer pw1 -> dw -> pw2 composed of three reference Conv units
@@ -193,6 +194,46 @@ def dump_dwconv():
     print("dwconv_ref", {k: v.shape for k, v in out.items() if k.endswith("_y")})
 
 
+def dump_tools_test():
+    """The REAL inference app of the reference, yolov8.tools.test.test() (tools/test.py:63-276), run on the reference's own
+    fixture image yolov8/test/sample.png (137x138 RGBA) with a seeded checkpoint: commits the JSON records it writes
+    (tests/golden/tools_test_sample.json) plus the decoded RGB pixels of the fixture (the GPU box has no /root/reference)."""
+    import tempfile
+    import yaml
+    from PIL import Image
+    from yolov8.tools.test import test as ref_test          # the real reference app
+    src = os.path.join(REF, "yolov8", "test", "sample.png")
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "best.pt")
+        # seeded weights whose BN statistics are calibrated ON this image (+ one synthetic one): logits stay O(1) and scores
+        # spread over (0, 1) instead of saturating at 1.0
+        import torchvision.transforms as T
+        tf = T.Compose([T.Resize((160, 192)), T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+        xs = tf(Image.open(src).convert("RGB")).unsqueeze(0)
+        sd = W.make_state_dict(W.load_manifest("n"), seed=5)
+        with torch.no_grad():
+            O.calibrate_bn(sd, torch.cat([xs, W.make_images(1, 160, 192, seed=55)]))
+        torch.save(sd, ck)
+        np.savez_compressed(os.path.join(GOLD, "tools_test_sample_bn.npz"),
+                            **{k: v.numpy() for k, v in sd.items() if k.endswith(("running_mean", "running_var"))})
+        cfg = os.path.join(td, "cfg.yaml")
+        names = [f"thing{i}" for i in range(80)]
+        with open(cfg, "w") as f:
+            yaml.safe_dump({"device": "cpu", "model": {"architecture": "n", "input_size": [160, 192]},
+                            "dataset": {"num_classes": 80, "class_names": names}}, f)
+        out = os.path.join(td, "out")
+        ref_test(cfg, ck, src, out, conf_thresh=0.25, iou_thresh_nms=0.45)
+        with open(os.path.join(out, "sample_detections.json")) as f:
+            recs = json.load(f)
+    with open(os.path.join(GOLD, "tools_test_sample.json"), "w") as f:
+        json.dump({"config": {"architecture": "n", "input_size": [160, 192], "num_classes": 80, "weights": "make_state_dict(manifest n, seed 5) + BN running stats of tools_test_sample_bn.npz",
+                              "conf_thresh": 0.25, "iou_thresh_nms": 0.45},
+                   "produced_by": "yolov8.tools.test.test() of the reference on yolov8/test/sample.png (oracle/make_golden.py::dump_tools_test)",
+                   "records": recs}, f)
+    np.savez_compressed(os.path.join(GOLD, "tools_test_sample_image.npz"), rgb=np.asarray(Image.open(src).convert("RGB")))
+    print("tools_test", len(recs), "records; first", recs[0] if recs else None)
+
+
 def dump_bn_fixtures():
     """BN running statistics of the calibrated synthetic weights (seed 1) for bench.py / smoke():
     yolo_ms_b200/synth_bn/bn_{version}_{block}_seed1.npz."""
@@ -216,3 +257,4 @@ if __name__ == "__main__":
     dump_post()
     dump_nms()
     dump_dwconv()
+    dump_tools_test()

@@ -125,7 +125,7 @@ def test_head_teacher_forced_logits_boxes_and_matches():
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("version,block,hw,gate", [("n", "c2f", (64, 96), 0.04), ("n", "c2f", (320, 320), 0.12),
                                                     ("s", "c2f", (256, 256), 0.12), ("m", "c2f", (128, 128), 0.12),
-                                                    ("n", "ms", (64, 64), 0.4)])
+                                                    ("n", "ms", (64, 64), 0.045)])     # ms: 1.5 x the measured 0.024-0.029
 def test_end_to_end_vs_oracle(version, block, hw, gate):
     """Whole forward vs (i) the oracle under the product's numeric contract (bf16 storage, fp32
     accumulate): raw logits rel-L2 <= gate (bf16 roundings flip under a different fp32 summation
@@ -441,7 +441,9 @@ def test_batch32_at_the_benchmarked_shape(version, block):
     x = W.make_images(32, 640, 640, seed=7)
     xd = x.to(DEV)
     raws = [r.clone() for r in m.forward_raw(xd)]
-    gate = 0.15 if block == "c2f" else 0.2
+    # c2f: gate of test_full_resolution_configs.  ms: 1.5 x the measured bf16 floor of this variant at this shape
+    # (scripts/ms_gate_probe.py: 0.16 / 0.19 / 0.17 for the three scales; the CPU contract-vs-fp32 floor itself is 0.24-0.28)
+    gate = 0.15 if block == "c2f" else 0.3
     with torch.no_grad():
         for i in (0, 31):
             emu = O.forward_bf16_contract(sd, x[i:i + 1], return_parts=True)
@@ -462,7 +464,7 @@ def test_batch32_at_the_benchmarked_shape(version, block):
     raw2 = m.forward_raw(pair)
     for s in range(3):
         for j, i in enumerate((0, 31)):
-            assert rel_l2(raw2[s][j], raws[s][i]) < 2e-2, (s, i)        # different tile schedules / tuned variants: fp32 order only
+            assert rel_l2(raw2[s][j], raws[s][i]) < (0.05 if block == "c2f" else 0.15), (s, i)   # other tile schedules / tuned variants: fp32 order -> bf16 flips, amplified by depth
     b2 = m.detect(pair, 0.25, 0.45)
     p2 = m(pair).cpu().numpy()
     for j in range(2):
