@@ -1,9 +1,13 @@
-"""Class-size statistics of the bench workload's NMS input and the kernel time (env knobs: YMS_NMS_GROUPS, YMS_NMS_MASK_TILES)."""
+"""Class-size statistics of the bench workload's NMS input and the kernel time.
+    python scripts/nms_probe.py [--stats] [name=value ...]     # library options, e.g. nms_groups=8 nms_mask_tiles=100 nms_sort_bitonic=1"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from yolo_ms_b200 import YOLOv8, synth, ops
+from yolo_ms_b200 import YOLOv8, synth, ops, _lib
+for a in sys.argv[1:]:
+    if "=" in a:
+        _lib.set_debug_option(a.split("=")[0], int(a.split("=")[1]))
 dev = torch.device("cuda", 0)
 model = YOLOv8(version="s", num_classes=80)
 model.load_state_dict(synth.synthetic_state_dict(model, "s", "c2f", seed=1))
@@ -27,4 +31,4 @@ a.record()
 for _ in range(20):
     ops.nms_batched(boxes, scores, labels, 0.25, 0.45, 80)
 b.record(); torch.cuda.synchronize()
-print("nms ms:", round(a.elapsed_time(b) / 20, 4), "groups env:", os.environ.get("YMS_NMS_GROUPS"), "mask tiles env:", os.environ.get("YMS_NMS_MASK_TILES"))
+print("nms ms:", round(a.elapsed_time(b) / 20, 4), "options:", [a for a in sys.argv[1:] if "=" in a])

@@ -25,9 +25,12 @@ prof post 'nms_kernel|head_decode|stem_t' 0 3
 prof dec conv_gemm_kernel 26 9           # the LAST conv_gemm launches of the step: the six decode-fused final head convs (75 registers)
                                          # + the head's 20x20 3x3 layers the autotuner gave to the generic kernel
 du -sh $OUT; ls $OUT | grep $TAG
-# 3. MS-Block variant: the depthwise kernels (launch list + --set full of four of them)
+# 3. MS-Block variant: launch list of one step + --set full of the fused layer kernel (160x160 pw1->dw->pw2, 80x80, 40x40 dw->pw2 / dw, 20x20)
 CMDMS="python bench.py --block ms --profile-step --warmup 3"
 $CMDMS > /dev/null 2>&1 && \
-ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:dwconv" -s 0 -c 4 -o $OUT/prof_dw_$TAG $CMDMS > $OUT/ncu_dw_$TAG.log 2>&1
+ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    --csv --log-file $OUT/launches_ms_$TAG.csv $CMDMS > $OUT/ncu_launches_ms_$TAG.log 2>&1
+$CMDMS > /dev/null 2>&1 && \
+ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:ms_layer_kernel" -s 0 -c 20 -o $OUT/prof_dw_$TAG $CMDMS > $OUT/ncu_dw_$TAG.log 2>&1
 ncu -i $OUT/prof_dw_$TAG.ncu-rep --page raw --csv > $OUT/prof_dw_${TAG}_raw.csv 2>/dev/null
 rm -f $OUT/prof_dw_$TAG.ncu-rep

@@ -114,12 +114,12 @@ def test_conv1x1_over_upsampled_concat(ops, B, H, W, c_low, c_skip, cout):
 
 
 def test_half_cta_mode_in_a_subprocess():
-    """YMS_CONV_HALF=1 (opt-in): conv_gemm_kernel with 2 epilogue groups / 320 threads / 256 TMEM columns /
-    <= 113 KB so that two CTAs share an SM.  The switch is read once per process, so the generic-kernel parity cases and the
-    decode-fused program are re-run in a child interpreter with the variable set."""
+    """Library option conv_half=1 (opt-in): conv_gemm_kernel with 2 epilogue groups / 320 threads / 256 TMEM
+    columns / <= 113 KB so that two CTAs share an SM.  The option is process-wide, so the generic-kernel parity cases and the
+    decode-fused program are re-run in a child interpreter that sets it at session start (tests/conftest.py)."""
     import subprocess
     import sys
-    env = dict(os.environ, YMS_CONV_HALF="1")
+    env = dict(os.environ, YMS_TEST_OPTIONS="conv_half=1")
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
                         os.path.join(here, "test_gpu_ops.py"), os.path.join(here, "test_gpu_model.py"),
@@ -219,7 +219,7 @@ def test_stem_conv(ops, cout):
 @pytest.mark.parametrize("B,H,W,cout", [(2, 64, 256, 32), (1, 96, 320, 48), (2, 32, 640, 32), (1, 64, 260, 16)])
 def test_stem_tma_variant_fp32_and_u8(ops, B, H, W, cout, monkeypatch):
     """Image widths >= 256 take the TMA-fed stem (raw rows through a TMA ring, row-aligned tiles, partial last tile when
-    W/2 is not a multiple of 128): vs plain PyTorch, fp32 and uint8 inputs, and vs the gather kernel (YMS_STEM_GATHER)."""
+    W/2 is not a multiple of 128): vs plain PyTorch, fp32 and uint8 inputs, and vs the gather kernel (library option stem_gather)."""
     g = torch.Generator().manual_seed(W + cout)
     img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
     mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
@@ -231,10 +231,14 @@ def test_stem_tma_variant_fp32_and_u8(ops, B, H, W, cout, monkeypatch):
     ops.stem_conv_u8(img.to(DEV), w, b, yu)
     assert rel_l2(yf, ref) < 1e-2 and rel_l2(yu, ref) < 1e-2
     assert rel_l2(yu, yf.float()) < 2e-3
-    monkeypatch.setenv("YMS_STEM_GATHER", "1")          # same arithmetic, different data path: bit-identical outputs
-    yg = torch.empty_like(yf); ygu = torch.empty_like(yf)
-    ops.stem_conv(x.to(DEV), w, b, yg)
-    ops.stem_conv_u8(img.to(DEV), w, b, ygu)
+    from yolo_ms_b200 import _lib
+    _lib.set_debug_option("stem_gather", 1)             # same arithmetic, different data path: bit-identical outputs
+    try:
+        yg = torch.empty_like(yf); ygu = torch.empty_like(yf)
+        ops.stem_conv(x.to(DEV), w, b, yg)
+        ops.stem_conv_u8(img.to(DEV), w, b, ygu)
+    finally:
+        _lib.set_debug_option("stem_gather", 0)
     assert torch.equal(yg, yf) and torch.equal(ygu, yu)
 
 

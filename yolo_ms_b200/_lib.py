@@ -123,5 +123,14 @@ def check(rc: int, what: str) -> None:
         raise YmsError(f"{what} failed (code {rc}): {msg}")
 
 
+def set_debug_option(name: str, value: int) -> None:
+    """Experiment switches of the library (csrc/common.cuh::DebugOptions): 'pdl_off', 'conv_half', 'stem_gather', 'nms_groups',
+    'nms_mask_tiles', 'nms_poll_ns', 'nms_sort_bitonic'.  Not part of the reference-facing ABI; affects plans created and
+    kernels launched after the call.  (The library never reads environment variables.)"""
+    lib = load()
+    lib.yms_debug_set_option.argtypes = [C.c_char_p, C.c_int]
+    check(lib.yms_debug_set_option(name.encode(), int(value)), "yms_debug_set_option")
+
+
 def launch_count() -> int:
     return int(load().yms_launch_count())

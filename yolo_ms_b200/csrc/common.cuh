@@ -10,6 +10,19 @@
 
 namespace yms {
 
+// Debug / experiment switches of the library, set through yms_debug_set_option (capi.cu) -- never read from the environment,
+// never consulted per launch beyond a plain load.
+struct DebugOptions {
+    int pdl_off;            // 1: launch without programmatic stream serialization
+    int conv_half;          // 1: "half" CTAs for N <= 128 plans of the generic conv kernel (two CTAs per SM)
+    int stem_gather;        // 1: force the gather stem kernel (bit-identical to the TMA-fed one)
+    int nms_groups;         // > 0: CTAs per image of the NMS kernel
+    int nms_mask_tiles;     // IoU-bitmask path limit (default 8)
+    int nms_poll_ns;        // back-off of the pipelined greedy path (default 256)
+    int nms_sort_bitonic;   // 1: single bitonic sort instead of per-segment sorts
+};
+extern DebugOptions g_opt;
+
 extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
 
@@ -20,6 +33,15 @@ inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
     return 0;
+}
+
+// cudaFuncSetAttribute is per DEVICE: returns true the first time it is called on the current device for this flag word
+// (one word per call site), so a second GPU driven from the same process gets its dynamic shared-memory opt-in too.
+inline bool first_use_on_device(std::atomic<unsigned long long>& seen) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    return !(seen.fetch_or(bit) & bit);
 }
 
 constexpr int kNumSMs = 148;  // B200

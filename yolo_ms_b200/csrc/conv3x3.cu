@@ -337,28 +337,25 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.bias_pad = k.n_tiles * k.block_n + 64;
     k.bias = q->bias;
     k.halo_bytes = (uint32_t)(kHaloPitch * (k.th + 2) * 128);
-    const char* dm = getenv("YMS_CONV3_DESC");
-    k.desc_mode = dm ? atoi(dm) : 0;
+    k.desc_mode = 0;
 
     const int b_tile = (k.block_n * 128 + 1023) & ~1023;
     const int halo_stage = (int)k.halo_bytes;
     k.halo_stage = halo_stage;
     const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16;
     const int resident_bytes = 9 * k.kb * b_tile;
-    const char* force_stream = getenv("YMS_CONV3_STREAM");
     // largest ring depth (in items of `sub` halos) that fits next to `other` bytes of weights
     auto max_a_stages = [&](int sub, int other) {
         int n = 0;
         while (n < kRing && ((((n + 1) * sub * halo_stage + 1023) & ~1023) + other + fixed <= kSmemLimit3)) ++n;
         return n;
     };
-    k.resident = (k.n_tiles == 1 && !force_stream && max_a_stages(1, resident_bytes) >= 2) ? 1 : 0;
+    k.resident = (k.n_tiles == 1 && max_a_stages(1, resident_bytes) >= 2) ? 1 : 0;
     if (k.resident) {
         // two sub-tiles per item when they fit: their MMAs use independent accumulators and are
         // interleaved, which hides part of the ~100-cycle per-instruction tcgen05.mma latency
-        const char* fs = getenv("YMS_CONV3_SUB");
         const long long sub_tiles = (long long)k.tiles_x * k.tiles_y * k.batch;
-        k.sub = fs ? atoi(fs) : ((k.tiles_x >= 2 && sub_tiles >= 4096) ? 2 : 1);    // pairing only pays with many tiles per CTA
+        k.sub = (k.tiles_x >= 2 && sub_tiles >= 4096) ? 2 : 1;                       // pairing only pays with many tiles per CTA
         if (q->variant == 2) k.sub = 1; else if (q->variant == 3 && k.tiles_x >= 2) k.sub = 2;
         k.b_stages = 0;
         if ((k.sub != 1 && k.sub != 2 && k.sub != 4) || k.sub * k.block_n > 512) k.sub = 1;
@@ -407,13 +404,12 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     pl->flops = 2.0 * m * q->c_out * (double)q->c_in * 9.0;
     pl->bytes = 2.0 * m * q->c_in + 2.0 * m * q->c_out + 2.0 * 9.0 * q->c_out * q->c_in + (q->residual ? 2.0 * m * q->c_out : 0.0);
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_seen{0};
+    if (first_use_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e != cudaSuccess) return fail((int)e, "conv3x3: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
     }
     return 0;
 }

@@ -450,7 +450,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
         *out = pl;
         return 0;
     }
-    if (q->ksize == 3 && q->stride == 1 && q->out_dtype == YMS_DTYPE_BF16 && q->c_in2 == 0 && q->variant != 1 && !getenv("YMS_CONV3_LEGACY")) {
+    if (q->ksize == 3 && q->stride == 1 && q->out_dtype == YMS_DTYPE_BF16 && q->c_in2 == 0 && q->variant != 1) {
         int rc3 = conv3_plan_init(pl, q);
         if (rc3) { delete pl; return rc3; }
         *out = pl;
@@ -502,9 +502,9 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 
     const int b_bytes = (kp.block_n * 128 + 1023) & ~1023;
     const int res_bytes = kp.taps * (kp.kb1 + kp.kb2) * b_bytes;
-    // "half" CTAs (YMS_CONV_HALF=1, experimental): 2 epilogue groups, 2 x 128 TMEM columns, <= 113 KB -> two CTAs per SM.  Only for
+    // "half" CTAs (yms_debug_set_option("conv_half", 1), experimental): 2 epilogue groups, 2 x 128 TMEM columns, <= 113 KB -> two CTAs per SM.  Only for
     // N <= 128 (two accumulator stages must remain) and when at least 3 ring stages fit beside resident / streamed weights.
-    static const bool want_half = [] { const char* e = getenv("YMS_CONV_HALF"); return e && e[0] == '1'; }();
+    const bool want_half = g_opt.conv_half != 0;
     int groups = kEpiGroups, limit = kSmemLimit;
     if (want_half && kp.block_n <= 128) {
         const int fixed_h = 2 * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 16) * 8 + 1024;
@@ -516,7 +516,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     kp.acc_stages = groups == 2 ? 2 : (kp.block_n <= 128 ? 4 : 2);
     kp.mg_n_tiles = fast_div_magic(kp.n_tiles); kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
     // small weight sets stay resident for the whole persistent CTA (no per-tile re-fetch from L2)
-    kp.resident = (kp.n_tiles == 1 && !getenv("YMS_CONV_STREAM") && limit - fixed - res_bytes >= (groups == 2 ? 3 : 4) * kATileBytes) ? 1 : 0;
+    kp.resident = (kp.n_tiles == 1 && limit - fixed - res_bytes >= (groups == 2 ? 3 : 4) * kATileBytes) ? 1 : 0;
     const int stage_bytes = kATileBytes + (kp.resident ? 0 : b_bytes);
     int stages = (limit - fixed - (kp.resident ? res_bytes : 0)) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -530,7 +530,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     int rc;
     const int K_total = q->c_in + q->c_in2;
     const int bx = kp.tw * q->stride, by = kp.th * q->stride;
-    kp.s2_dense = (q->stride == 2 && q->x_pixel_stride == q->c_in && q->c_in2 == 0 && !getenv("YMS_CONV_S2_STRIDED")) ? 1 : 0;
+    kp.s2_dense = (q->stride == 2 && q->x_pixel_stride == q->c_in && q->c_in2 == 0) ? 1 : 0;
     if (kp.s2_dense) {
         const uint64_t C = (uint64_t)q->c_in, W = (uint64_t)q->in_w, H = (uint64_t)q->in_h;
         uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, (uint64_t)q->batch};
@@ -560,12 +560,11 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     pl->bytes = 2.0 * (double)q->batch * q->in_h * q->in_w * K_total + (kp.out_f32 ? 4.0 : 2.0) * m * q->c_out +
                 2.0 * (double)kp.taps * q->c_out * K_total + (q->residual ? 2.0 * m * q->c_out : 0.0);
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_seen{0};
+    if (first_use_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) { delete pl; return fail((int)e, "conv: smem attribute: %s", cudaGetErrorString(e)); }
-        attr_set = true;
     }
     *out = pl;
     return 0;

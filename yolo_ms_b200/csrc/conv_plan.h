@@ -84,7 +84,7 @@ inline uint32_t fast_div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x
 // global data).  YMS_PDL=0 disables it.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
-    static const bool enabled = [] { const char* e = getenv("YMS_PDL"); return !(e && e[0] == '0'); }();
+    const bool enabled = !g_opt.pdl_off;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -156,11 +156,10 @@ extern "C" int yms_sppf_pool(void* buf, int64_t ps, int batch, int h, int w, int
     if (h * w <= kPoolMaxHW) {
         dim3 grid(c / 8, batch);
         const size_t smem = (size_t)2 * h * w * sizeof(uint4);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned long long> attr_seen{0};
+        if (first_use_on_device(attr_seen)) {
             cudaError_t e = cudaFuncSetAttribute(sppf_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPoolMaxHW * (int)sizeof(uint4));
             if (e != cudaSuccess) return fail((int)e, "sppf: smem attribute");
-            attr_set = true;
         }
         sppf_pool_smem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(buf), ps, h, w, c);
         return check_launch("sppf_pool_smem_kernel");

@@ -301,7 +301,7 @@ extern "C" int yms_head_decode(const void* raw0, const void* raw1, const void* r
     const long long grid = (long long)batch * tiles;
     if (grid > 0x7fffffffLL) return fail(YMS_E_UNSUPPORTED, "decode: grid too large");
     cudaError_t e;
-    if ((num_classes % 16) == 0 && num_classes <= 256 && !getenv("YMS_DECODE_V1")) {      // v2: one thread per 16-channel chunk
+    if ((num_classes % 16) == 0 && num_classes <= 256) {      // v2: one thread per 16-channel chunk
         const int ngroups = a.no / 16, ncg = ngroups - 4;
         const size_t smem2 = (size_t)kTileAnchors * ((4 + num_classes) + 4 + 2 * ncg) * 4;
         const int threads = kTileAnchors * ngroups;

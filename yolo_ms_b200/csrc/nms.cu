@@ -791,7 +791,7 @@ __global__ void gather_dets_kernel(const float4* boxes, const float* scores, con
 int next_pow2(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
 int pick_groups(int batch, int num_classes, int n) {
-    static const int forced = [] { const char* e = getenv("YMS_NMS_GROUPS"); return e ? atoi(e) : 0; }();
+    const int forced = g_opt.nms_groups;
     int g = forced > 0 ? forced : kNumSMs / batch;
     const int by_size = (n + 4095) / 4096;          // keep the expected candidates per CTA well inside the shared-memory fast path
     if (forced <= 0 && g < by_size) g = by_size;
@@ -860,21 +860,23 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.ws_count = reinterpret_cast<int32_t*>(ws + w.count);
     a.ws_ticket = reinterpret_cast<unsigned int*>(ws + w.ticket);
     a.prof = g_prof_buf;
-    { static const int dbg = [] { const char* e = getenv("YMS_NMS_DBG"); return e ? atoi(e) : 1; }(); a.dbg = dbg; }
-    { static const int lim = [] { const char* e = getenv("YMS_NMS_MASK_TILES"); return e ? atoi(e) : 8; }(); a.mask_tile_limit = lim; }
-    { static const int poll = [] { const char* e = getenv("YMS_NMS_POLL"); return e ? atoi(e) : 256; }(); a.poll_ns = poll < 16 ? 16 : poll; }
-    { static const int seg = [] { const char* e = getenv("YMS_NMS_SORT"); return (e && e[0] == 'b') ? 0 : 1; }(); a.seg_sort = seg; }
+    a.dbg = 1;
+    a.mask_tile_limit = g_opt.nms_mask_tiles;
+    a.poll_ns = g_opt.nms_poll_ns < 16 ? 16 : g_opt.nms_poll_ns;
+    a.seg_sort = g_opt.nms_sort_bitonic ? 0 : 1;
     if (groups > 1) {
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
         if (e != cudaSuccess) return fail((int)e, "nms: ticket memset failed");
     }
     const size_t smem = kKeyRegionBytes + (size_t)(num_classes + 2) * 4 * 4 + (size_t)(kFastCap / 32 + num_classes + 4) * 4 + 16;   // class tables + removed words
     if (smem > 232448) return fail(YMS_E_UNSUPPORTED, "nms: %d classes need %zu bytes of shared memory (limit 232448)", num_classes, smem);
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) {
+    static std::atomic<size_t> attr_bytes[64];           // per device: cudaFuncSetAttribute is a per-device setting
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    if (smem > attr_bytes[dev_id & 63].load()) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "nms: smem attribute: %s", cudaGetErrorString(e));
-        attr_bytes = smem;
+        attr_bytes[dev_id & 63].store(smem);
     }
     nms_kernel<<<batch * groups, kNmsThreads, smem, st>>>(a);
     return check_launch("nms_kernel");

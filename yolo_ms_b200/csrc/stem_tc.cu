@@ -509,7 +509,7 @@ using namespace yms;
 int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* mean, const float* stdv, int batch, int in_h, int in_w,
                        int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream) {
     const int out_h = in_h / 2, out_w = in_w / 2;
-    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && !getenv("YMS_STEM_GATHER")) {
+    if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && !g_opt.stem_gather) {
         // ---- TMA-fed variant: raw rows through a TMA ring, row-aligned tiles ----
         static thread_local struct Cache2 { const void* in; const void* y; int64_t ps; int b, h, w, c, u8; CUtensorMap min, my; bool ok; } c2 = {};
         const void* in = xu8 ? (const void*)xu8 : (const void*)x;
@@ -575,12 +575,11 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
     if (p.m_total + 128 >= (1LL << 31)) return fail(YMS_E_UNSUPPORTED, "stem: more than 2^31 output pixels");
     p.weight = weight; p.bias = bias;
     const size_t smem = 1024 + kStages * kATile + 8192 + kStemEpiGroups * kStageOutBytes + 192 * 4 + (2 * kStages + 2 * kStemEpiGroups) * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_seen{0};
+    if (first_use_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail((int)e, "stem: smem attribute: %s", cudaGetErrorString(e));
-        attr_set = true;
     }
     const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     if (xu8) stem_tc_kernel<true><<<grid, kStemThreads, smem, stream>>>(cache.map, p);

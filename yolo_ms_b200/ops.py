@@ -21,8 +21,20 @@ __all__ = ["ConvPlan", "MsLayerPlan", "stem_conv", "stem_conv_u8", "dwconv", "sp
            "select_candidates", "nms_batched", "gather_detections", "PostBuffers", "YmsError"]
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+import contextlib
+
+_NULL = contextlib.nullcontext()
+
+
+def _stream(t: Optional[torch.Tensor] = None) -> int:
+    """The current stream of the DEVICE the tensors live on (not of whatever device happens to be current)."""
+    return torch.cuda.current_stream(None if t is None else t.device).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Context that makes t's device current for a launch (kernels launch on the current device; a stream of another
+    device is an error).  No-op in the usual one-process-per-GPU setting."""
+    return _NULL if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
 
 
 def _need_cuda(*tensors: torch.Tensor) -> None:
@@ -76,7 +88,8 @@ class ConvPlan:
         self._keep = (x, weight, bias, y, residual, x2)      # keep the storages alive
         self._h = C.c_void_p()
         self._lib = _lib.load()
-        check(self._lib.yms_conv_plan_create(C.byref(p), C.byref(self._h)), "yms_conv_plan_create")
+        with _on(y):
+            check(self._lib.yms_conv_plan_create(C.byref(p), C.byref(self._h)), "yms_conv_plan_create")
         fl, by = C.c_double(), C.c_double()
         self._lib.yms_conv_plan_cost(self._h, C.byref(fl), C.byref(by))
         self.flops, self.bytes = fl.value, by.value
@@ -129,7 +142,9 @@ class ConvPlan:
         self.desc += " +up(f32)"
 
     def run(self) -> None:
-        check(self._lib.yms_conv_plan_run(self._h, _stream()), "yms_conv_plan_run")
+        y = self._keep[3]
+        with _on(y):
+            check(self._lib.yms_conv_plan_run(self._h, _stream(y)), "yms_conv_plan_run")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -194,7 +209,8 @@ class MsLayerPlan:
         self.mode = int(mode)
         self._h = C.c_void_p()
         self._lib = _lib.load()
-        check(self._lib.yms_ms_plan_create(C.byref(p), C.byref(self._h)), "yms_ms_plan_create")
+        with _on(y):
+            check(self._lib.yms_ms_plan_create(C.byref(p), C.byref(self._h)), "yms_ms_plan_create")
         fl, by = C.c_double(), C.c_double()
         self._lib.yms_ms_plan_cost(self._h, C.byref(fl), C.byref(by))
         self.flops, self.bytes = fl.value, by.value
@@ -203,7 +219,9 @@ class MsLayerPlan:
         self.desc = f"{what[self.mode]} @{h}x{w}"
 
     def run(self) -> None:
-        check(self._lib.yms_ms_plan_run(self._h, _stream()), "yms_ms_plan_run")
+        y = self._keep[0]
+        with _on(y):
+            check(self._lib.yms_ms_plan_run(self._h, _stream(y)), "yms_ms_plan_run")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -221,8 +239,9 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torc
     if x.dtype != torch.float32 or not x.is_contiguous() or x.shape[1] != 3:
         raise YmsError("stem: x must be contiguous f32 [B,3,H,W]")
     b, _, h, w = x.shape
-    check(_lib.load().yms_stem_conv(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(),
-                                    y.data_ptr(), _pixel_stride(y), _stream()), "yms_stem_conv")
+    with _on(y):
+        check(_lib.load().yms_stem_conv(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(),
+                                        y.data_ptr(), _pixel_stride(y), _stream(y)), "yms_stem_conv")
 
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
@@ -238,30 +257,34 @@ def stem_conv_u8(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: t
     b, h, w, _ = x.shape
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[float(v) for v in std])
-    check(_lib.load().yms_stem_conv_u8(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(), m, s,
-                                       y.data_ptr(), _pixel_stride(y), _stream()), "yms_stem_conv_u8")
+    with _on(y):
+        check(_lib.load().yms_stem_conv_u8(x.data_ptr(), b, h, w, y.shape[-1], weight.data_ptr(), bias.data_ptr(), m, s,
+                                           y.data_ptr(), _pixel_stride(y), _stream(y)), "yms_stem_conv_u8")
 
 
 def dwconv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, y: torch.Tensor, ksize: int) -> None:
     """Depthwise kxk + bias + SiLU.  x,y bf16 [B,H,W,C]; weight f32 [k*k, C]; bias f32 [C]."""
     _need_cuda(x, weight, bias, y)
     b, h, w, c = x.shape
-    check(_lib.load().yms_dwconv(x.data_ptr(), _pixel_stride(x), b, h, w, c, ksize, weight.data_ptr(), bias.data_ptr(),
-                                 y.data_ptr(), _pixel_stride(y), _stream()), "yms_dwconv")
+    with _on(y):
+        check(_lib.load().yms_dwconv(x.data_ptr(), _pixel_stride(x), b, h, w, c, ksize, weight.data_ptr(), bias.data_ptr(),
+                                     y.data_ptr(), _pixel_stride(y), _stream(y)), "yms_dwconv")
 
 
 def sppf_pool(buf: torch.Tensor, c: int) -> None:
     """buf bf16 [B,H,W,>=4c]: slot 0 holds x; writes the 5/9/13 max pools into slots 1..3."""
     _need_cuda(buf)
     b, h, w, _ = buf.shape
-    check(_lib.load().yms_sppf_pool(buf.data_ptr(), _pixel_stride(buf), b, h, w, c, _stream()), "yms_sppf_pool")
+    with _on(buf):
+        check(_lib.load().yms_sppf_pool(buf.data_ptr(), _pixel_stride(buf), b, h, w, c, _stream(buf)), "yms_sppf_pool")
 
 
 def upsample2x(x: torch.Tensor, y: torch.Tensor) -> None:
     _need_cuda(x, y)
     b, h, w, c = x.shape
-    check(_lib.load().yms_upsample2x(x.data_ptr(), _pixel_stride(x), b, h, w, c, y.data_ptr(), _pixel_stride(y),
-                                     _stream()), "yms_upsample2x")
+    with _on(y):
+        check(_lib.load().yms_upsample2x(x.data_ptr(), _pixel_stride(x), b, h, w, c, y.data_ptr(), _pixel_stride(y),
+                                         _stream(y)), "yms_upsample2x")
 
 
 def head_decode(raw: Sequence[torch.Tensor], strides: Sequence[float], num_classes: int,
@@ -294,9 +317,10 @@ def head_decode(raw: Sequence[torch.Tensor], strides: Sequence[float], num_class
     else:
         boxes = scores = labels = None
         ptrs = (None, None, None)
-    check(_lib.load().yms_head_decode(raw[0].data_ptr(), raw[1].data_ptr(), raw[2].data_ptr(),
-                                      _lib.DTYPE_F32 if dt == torch.float32 else _lib.DTYPE_BF16, b, hw, num_classes, st,
-                                      pred.data_ptr(), *ptrs, _stream()), "yms_head_decode")
+    with _on(pred):
+        check(_lib.load().yms_head_decode(raw[0].data_ptr(), raw[1].data_ptr(), raw[2].data_ptr(),
+                                          _lib.DTYPE_F32 if dt == torch.float32 else _lib.DTYPE_BF16, b, hw, num_classes, st,
+                                          pred.data_ptr(), *ptrs, _stream(pred)), "yms_head_decode")
     return (pred, (boxes, scores, labels)) if with_candidates else pred
 
 
@@ -310,8 +334,9 @@ def select_candidates(pred: torch.Tensor):
     boxes = torch.empty((b, a, 4), dtype=torch.float32, device=pred.device)
     scores = torch.empty((b, a), dtype=torch.float32, device=pred.device)
     labels = torch.empty((b, a), dtype=torch.int32, device=pred.device)
-    check(_lib.load().yms_select_candidates(pred.data_ptr(), b, a, no - 4, boxes.data_ptr(), scores.data_ptr(),
-                                            labels.data_ptr(), _stream()), "yms_select_candidates")
+    with _on(pred):
+        check(_lib.load().yms_select_candidates(pred.data_ptr(), b, a, no - 4, boxes.data_ptr(), scores.data_ptr(),
+                                                labels.data_ptr(), _stream(pred)), "yms_select_candidates")
     return boxes, scores, labels
 
 
@@ -351,10 +376,11 @@ def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor,
     nv = None
     if n_valid is not None:
         nv = n_valid.to(torch.int32).contiguous()
-    check(_lib.load().yms_nms_batched(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(),
-                                      None if nv is None else nv.data_ptr(), b, n, num_classes, _f32(conf_thr), float(iou_thr),
-                                      out.keep.data_ptr(), out.count.data_ptr(), out.ws.data_ptr(), out.ws_bytes, _stream()),
-          "yms_nms_batched")
+    with _on(boxes):
+        check(_lib.load().yms_nms_batched(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(),
+                                          None if nv is None else nv.data_ptr(), b, n, num_classes, _f32(conf_thr), float(iou_thr),
+                                          out.keep.data_ptr(), out.count.data_ptr(), out.ws.data_ptr(), out.ws_bytes, _stream(boxes)),
+              "yms_nms_batched")
     return out.keep, out.count
 
 
@@ -365,9 +391,10 @@ def gather_detections(boxes, scores, labels, keep, count, max_det: int, out: Opt
     dets = out if out is not None else torch.empty((b, max_det, 6), dtype=torch.float32, device=boxes.device)
     if tuple(dets.shape) != (b, max_det, 6) or dets.dtype != torch.float32 or not dets.is_contiguous():
         raise YmsError("gather_detections: `out` must be contiguous f32 [B, max_det, 6]")
-    check(_lib.load().yms_gather_detections(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr(),
-                                            count.data_ptr(), b, n, max_det, dets.data_ptr(), _stream()),
-          "yms_gather_detections")
+    with _on(dets):
+        check(_lib.load().yms_gather_detections(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), keep.data_ptr(),
+                                                count.data_ptr(), b, n, max_det, dets.data_ptr(), _stream(dets)),
+              "yms_gather_detections")
     return dets
 
 

@@ -73,11 +73,16 @@ def resize_u8(img: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     h0, w0, c = img.shape
     h1, w1, _ = out.shape
     lib = _lib.load()
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream(img.device).cuda_stream
     if (h0, w0) == (h1, w1):
         out.copy_(img)
         return out
     cur, cur_h, cur_w = img, h0, w0
+    with torch.cuda.device(img.device):
+        return _resize_passes(lib, stream, img, out, cur, cur_h, cur_w, h0, w0, h1, w1, c)
+
+
+def _resize_passes(lib, stream, img, out, cur, cur_h, cur_w, h0, w0, h1, w1, c):
     if w0 != w1:
         ks, b, k = _device_coeffs(w0, w1, img.device)
         dst = out if h0 == h1 else torch.empty((h0, w1, c), dtype=torch.uint8, device=img.device)
