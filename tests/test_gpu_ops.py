@@ -378,7 +378,8 @@ def test_postprocess_matches_reference_golden(ops):
 @pytest.mark.parametrize("B,N,nc,mode", [(4, 1000, 80, "uni"), (3, 8400, 80, "clu"), (2, 30000, 80, "ties"),
                                           (2, 3000, 1, "clu"), (2, 20000, 3, "clu"), (1, 1, 80, "uni"),
                                           (2, 33, 5, "uni"), (2, 16385, 80, "uni"),
-                                          (2, 33600, 80, "skew"), (3, 8400, 80, "skewbig"), (40, 2000, 80, "skew"), (2, 6000, 300, "uni")])
+                                          (2, 33600, 80, "skew"), (3, 8400, 80, "skewbig"), (40, 2000, 80, "skew"), (2, 6000, 300, "uni"),
+                                          (2, 33600, 80, "one9k"), (2, 33600, 80, "one13k"), (2, 33600, 80, "one20k"), (1, 40000, 2, "one30k")])
 def test_nms_random_ragged_matches_c_oracle(ops, B, N, nc, mode):
     from oracle import postprocess as P
     rng = np.random.default_rng(N + nc)
@@ -396,6 +397,11 @@ def test_nms_random_ragged_matches_c_oracle(ops, B, N, nc, mode):
     if mode.startswith("skew"):       # a few dominant classes (what a random-weight head produces): exercises the cost- and
         p = 1.0 / np.arange(1, nc + 1) ** 1.3   # count-balanced class ranges and classes of thousands of boxes
         labels = rng.choice(nc, size=(B, N), p=p / p.sum()).astype(np.int32)
+    if mode.startswith("one"):        # ONE dominant class of 9k / 13k / 20k / 30k boxes next to uniform ones (MS-Block legs of bench.py at
+        big = int(mode[3:-1]) * 1000  # 1280 x 1280): boxes beyond shared memory (> 8192), keys beyond shared memory (> 16384)
+        labels[:, :big] = 0
+        wh = rng.uniform(30, 120, (B, N, 2))
+        boxes = np.concatenate([xy, xy + wh], -1).astype(np.float32)
     if mode == "skewbig":             # large, heavily overlapping boxes (15 x stride wide), like the bench workload
         wh = rng.uniform(100, 480, (B, N, 2))
         boxes = np.concatenate([xy - wh / 2, xy + wh / 2], -1).astype(np.float32)

@@ -162,6 +162,64 @@ __device__ __forceinline__ bool apply_kept(BoxAt box_at, int from, int to, const
     return removed;
 }
 
+// Register + shuffle flavour of the same normalised bitonic network for ONE warp and segments of at most 32 * E keys
+// (scripts/ubench/seg_sort.cu, measured on the B200: 10.2 kcycles against 28.8 kcycles for the shared-memory network on the
+// bench workload's 24 segments per CTA -- the shared-memory version is bound by its 2 x 8-byte accesses per compare-exchange).
+// Element index = lane * E + r.  Partners below E stay in the lane; a half-cleaner of stride j >= E pairs lane with
+// lane ^ (j / E); the mirror step of merge size k > E pairs (lane, r) with (lane ^ (k / E - 1), E - 1 - r).  Positions >= len
+// hold +inf and never move.
+__device__ __forceinline__ void cmpx64(unsigned long long& x, unsigned long long& y) { if (x > y) { const unsigned long long t = x; x = y; y = t; } }
+
+template <int E>
+__device__ __forceinline__ void warp_sort_regs(unsigned long long* s, int len, int lane) {
+    unsigned long long v[E];
+    #pragma unroll
+    for (int r = 0; r < E; ++r) { const int i = lane * E + r; v[r] = (i < len) ? s[i] : ~0ull; }
+    constexpr int P = 32 * E;
+    #pragma unroll
+    for (int k = 2; k <= P; k <<= 1) {
+        if (k <= E) {
+            #pragma unroll
+            for (int r = 0; r < E; ++r) { const int q = r ^ (k - 1); if (q > r) cmpx64(v[r], v[q]); }
+        } else {
+            const int mm = k / E - 1;
+            const bool lower = (lane & ((mm + 1) >> 1)) == 0;
+            unsigned long long o[E];
+            #pragma unroll
+            for (int r = 0; r < E; ++r) o[r] = __shfl_xor_sync(0xffffffffu, v[E - 1 - r], mm);
+            #pragma unroll
+            for (int r = 0; r < E; ++r) v[r] = lower ? (v[r] < o[r] ? v[r] : o[r]) : (v[r] > o[r] ? v[r] : o[r]);
+        }
+        #pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            if (j < E) {
+                #pragma unroll
+                for (int r = 0; r < E; ++r) if ((r & j) == 0) cmpx64(v[r], v[r | j]);
+            } else {
+                const int m = j / E;
+                const bool lower = (lane & m) == 0;
+                #pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], m);
+                    v[r] = lower ? (v[r] < o ? v[r] : o) : (v[r] > o ? v[r] : o);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    #pragma unroll
+    for (int r = 0; r < E; ++r) { const int i = lane * E + r; if (i < len) s[i] = v[r]; }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_sort_segment(unsigned long long* s, int len, int lane) {     // len <= kWarpSortMax
+    if (len < 2) return;
+    if (len <= 32) warp_sort_regs<1>(s, len, lane);
+    else if (len <= 64) warp_sort_regs<2>(s, len, lane);
+    else if (len <= 128) warp_sort_regs<4>(s, len, lane);
+    else warp_sort_regs<8>(s, len, lane);
+}
+
 // Resolve one chunk (32 boxes in score order held by the lanes); returns the survivor mask.
 __device__ __forceinline__ unsigned resolve_chunk(const float4& bj, float aj, bool& removed, float thr_f, int lane) {
     unsigned alive = ~__ballot_sync(0xffffffffu, removed);
@@ -305,27 +363,6 @@ __device__ __forceinline__ bool apply_kept_smem(const float4* kb, int from, int 
     return removed;
 }
 
-// Resolve one chunk (32 boxes in score order, box of lane l = chunk[l]): the 32 x 32 pair tests are independent (each lane
-// tests its box against the broadcast box jj), the greedy order is then replayed on the mask words.  Returns the survivors.
-template <bool kFinite>
-__device__ __forceinline__ unsigned resolve_chunk_smem(const float4* chunk, int cnt, const float4& bj, float aj, bool& removed, float thr_f, int lane) {
-    unsigned word = 0u;
-    #pragma unroll 4
-    for (int jj = 1; jj < cnt; ++jj) {
-        const float4 bc = chunk[jj];
-        const bool hit = (lane < jj) && pair_hit<kFinite>(bj, aj, bc, box_area(bc), thr_f);
-        word |= hit ? (1u << jj) : 0u;
-    }
-    unsigned rem = __ballot_sync(0xffffffffu, removed);
-    #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const unsigned mi = __shfl_sync(0xffffffffu, word, i);
-        rem |= ((rem >> i) & 1u) ? 0u : mi;
-    }
-    removed = (rem >> lane) & 1u;
-    return ~rem;
-}
-
 struct NmsArgs {
     const float4* boxes; const float* scores; const int32_t* labels; const int32_t* n_valid;
     int n, num_classes, groups; float conf; float thr_f;
@@ -337,10 +374,8 @@ struct NmsArgs {
     int n_pad_full;                // pow2(n)
     long long* prof;               // -DYMS_PROF builds: [grid][16] phase time stamps
     int mask_tile_limit;           // bitmask path only when the largest class of the CTA has at most this many 32-box blocks
-    int poll_ns;                   // back-off unit of the pipelined greedy path's progress polling (YMS_NMS_POLL, default 256 ns per chunk ahead)
-    int seg_sort;                  // 1 (default): counting scatter by class + per-segment sorts; 0 (YMS_NMS_SORT=bitonic): one bitonic sort of all keys
-    int dbg;                       // YMS_NMS_DBG switches: 1 = broadcast/4-way apply of kept boxes (default), 2 = mask-based chunk
-                                   // resolve (measured slower: the phase is issue-bound and it executes more instructions)
+    int poll_ns;                   // back-off unit of the pipelined greedy path's progress polling (library option nms_poll_ns, default 256 ns per chunk ahead)
+    int seg_sort;                  // 1 (default): counting scatter by class + per-segment sorts; 0 (library option nms_sort_bitonic): one bitonic sort of all keys
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
@@ -482,7 +517,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         }
         for (int c = warp; c < ncl; c += kNmsWarps) {
             const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
-            if (len <= kWarpSortMax) segment_sort<false>(skeys + s0, len, lane, 32);
+            if (len <= kWarpSortMax) warp_sort_segment(skeys + s0, len, lane);
         }
         __syncthreads();
     } else if (in_smem) {
@@ -612,8 +647,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
             const int kept = nseg ? nms_mask_compact(skeys + s0, remw_all + (s0 >> 5) + c, nseg, lane) : 0;
             if (lane == 0) cls_count[c] = kept;
         }
-    } else if (fast) {
-        // ---- D (fast): pipelined chunks -------------------------------------------------------
+    } else {
+        // ---- D (pipelined chunks), any size.  fast (m <= 8192): keys and boxes in shared memory.  Otherwise the boxes are
+        // re-gathered from the read-only input by index (L1 / L2 hits) and, beyond 16384 candidates, the keys live in the
+        // CTA's global workspace (written and read by this CTA only: __threadfence_block orders them like shared memory).
+        // A skewed class distribution -- one class holding most of 33 600 anchors -- therefore still runs on all 32 warps
+        // (the first version had a one-warp-per-class path there: 104 ms for a 17 000-box class, 35 ms on the 1280x1280
+        // MS-Block leg of bench.py) ----
         // Chunks are enumerated class by class in DESCENDING class size (perm, kept in cls_count until the end): the chain of
         // a class's chunks is sequential, so the longest chains must start first and overlap with everything else.
         int* perm = cls_count;
@@ -653,8 +693,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                 const int s0 = cls_start[c], s1 = cls_start[c + 1];
                 const int pos = s0 + 32 * j + lane;
                 const bool have = pos < s1;
-                const unsigned long long key = have ? skeys[pos] : kInvalidKey;
-                const float4 bj = have ? sbox[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const unsigned long long key = have ? keys[pos] : kInvalidKey;
+                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (have) bj = fast ? sbox[pos] : __ldg(boxes + (int)(key & kIdxMask));
                 const float aj = box_area(bj);
                 bool removed = !have;
                 int applied = 0, kept = 0;
@@ -664,8 +705,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                     st = __shfl_sync(0xffffffffu, st, 0);
                     __threadfence_block();
                     kept = (int)(st & 0xffffu);
-                    if (a.dbg & 1) removed = apply_kept_smem<kFinite>(sbox + s0, applied, kept, bj, aj, removed, a.thr_f);
-                    else removed = apply_kept([&](int q) { return sbox[s0 + q]; }, applied, kept, bj, aj, removed, a.thr_f, lane);
+                    if (fast) removed = apply_kept_smem<kFinite>(sbox + s0, applied, kept, bj, aj, removed, a.thr_f);
+                    else removed = apply_kept([&](int q) { return __ldg(boxes + (int)(keys[s0 + q] & kIdxMask)); }, applied, kept, bj, aj, removed, a.thr_f, lane);
                     applied = kept;
                     const int ahead = j - (int)(st >> 16);     // chunks of this class that are not final yet
                     if (ahead == 0) break;                     // every earlier chunk of this class is final
@@ -674,47 +715,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                     // saturated the issue ports and starved the one warp per class that is on the critical chain.
                     __nanosleep(ahead <= 1 ? 32u : (unsigned)min(a.poll_ns * ahead, 4096));
                 }
-                const unsigned surv = (a.dbg & 2) ? resolve_chunk_smem<kFinite>(sbox + s0 + 32 * j, min(32, s1 - s0 - 32 * j), bj, aj, removed, a.thr_f, lane)
-                                                  : resolve_chunk(bj, aj, removed, a.thr_f, lane);
+                const unsigned surv = resolve_chunk(bj, aj, removed, a.thr_f, lane);
                 __syncwarp();                                  // every lane has read its chunk box before the in-place compaction
                 if (!removed) {
                     const int dst = s0 + kept + __popc(surv & ((1u << lane) - 1u));   // in place: dst < s0 + 32*(j+1)
-                    skeys[dst] = key;
-                    sbox[dst] = bj;
+                    keys[dst] = key;
+                    if (fast) sbox[dst] = bj;
                 }
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) state[c] = ((unsigned)(j + 1) << 16) | (unsigned)(kept + __popc(surv));
             }
         };
-        if (nonfinite) run_chunks(std::false_type{}); else run_chunks(std::true_type{});
+        if (nonfinite || !fast) run_chunks(std::false_type{}); else run_chunks(std::true_type{});
         __syncthreads();
         for (int c = tid; c < ncl; c += kNmsThreads) cls_count[c] = (int)(state[c] & 0xffffu);
-    } else {
-        // ---- D (general): one warp per class segment, boxes gathered from global memory -----------
-        for (;;) {
-            int c = 0;
-            if (lane == 0) c = atomicAdd(&s_next, 1);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            if (c >= ncl) break;
-            const int s0 = cls_start[c], s1 = cls_start[c + 1];
-            int kept = 0;
-            for (int d = s0; d < s1; d += 32) {
-                const int pos = d + lane;
-                const bool have = pos < s1;
-                const unsigned long long key = have ? keys[pos] : kInvalidKey;
-                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (have) bj = boxes[(int)(key & kIdxMask)];
-                const float aj = box_area(bj);
-                bool removed = !have;
-                removed = apply_kept([&](int q) { return boxes[(int)(keys[s0 + q] & kIdxMask)]; }, 0, kept, bj, aj, removed, a.thr_f, lane);
-                const unsigned surv = resolve_chunk(bj, aj, removed, a.thr_f, lane);
-                if (!removed) keys[s0 + kept + __popc(surv & ((1u << lane) - 1u))] = key;
-                kept += __popc(surv);
-                __syncwarp();
-            }
-            if (lane == 0) cls_count[c] = kept;
-        }
     }
     __syncthreads();
 
@@ -860,7 +875,6 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
     a.ws_count = reinterpret_cast<int32_t*>(ws + w.count);
     a.ws_ticket = reinterpret_cast<unsigned int*>(ws + w.ticket);
     a.prof = g_prof_buf;
-    a.dbg = 1;
     a.mask_tile_limit = g_opt.nms_mask_tiles;
     a.poll_ns = g_opt.nms_poll_ns < 16 ? 16 : g_opt.nms_poll_ns;
     a.seg_sort = g_opt.nms_sort_bitonic ? 0 : 1;

@@ -246,6 +246,11 @@ class Program:
         self.schedule.append(("fork", n_branches, 0))
         self._n_side = max(self._n_side, n_branches - 1)
 
+    def fork_one(self, k: int):
+        """Side branch k (> 0) starts here: its stream waits for everything the main branch has issued so far."""
+        self.schedule.append(("fork_one", k, 0))
+        self._n_side = max(self._n_side, k)
+
     def branch(self, i: int):
         self._branch = i
 
@@ -278,6 +283,11 @@ class Program:
                     ev.record(main)
                     for k in range(arg - 1):
                         self._side[k].wait_event(ev)
+            elif kind == "fork_one":
+                if op_idx >= start:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self._side[arg - 1].wait_event(ev)
             elif kind == "join":
                 for k in sorted(used):
                     ev = torch.cuda.Event()

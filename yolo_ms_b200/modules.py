@@ -33,6 +33,8 @@ FUSE_DECODE = os.environ.get("YMS_FUSE_DECODE", "1") != "0"    # decode in the e
 MS_FUSE = int(os.environ.get("YMS_MS_FUSE", "2"))               # MS-Block layers: 2 = pw1 -> depthwise -> pw2 in one kernel where it
                                                                 # fits, 1 = depthwise -> pw2, 0 = three launches
 
+OVERLAP_HEAD = os.environ.get("YMS_OVERLAP_HEAD", "1") != "0"    # head scales 0 / 1 on graph branches next to the rest of the neck
+
 FUSE_UPSAMPLE = os.environ.get("YMS_FUSE_UPSAMPLE", "1") != "0"  # neck: upsample + concat inside the consumer C2f's first 1x1 conv
 
 _VERSIONS = {  # depth, width, ratio  (components.py:193-209)
@@ -79,6 +81,10 @@ class _Compiled(nn.Module):
     def load_state_dict(self, *a, **k):
         self.refresh()
         return super().load_state_dict(*a, **k)
+
+
+def img_device(image) -> torch.device:
+    return image.tensor.device
 
 
 def _device_of(m: nn.Module) -> torch.device:
@@ -437,9 +443,12 @@ class Neck(_Compiled):
         self.__dict__["_cats"] = (cat1, cat2, cat3, cat4)
         return cat2[..., c4:], cat1[..., c5:], cat4[..., c4:]
 
-    def emit(self, P):
+    def emit(self, P, on_output=None):
+        """on_output(i, tensor): called as soon as output i (N3, N4, N5 in this order) has been emitted -- the model starts the
+        head of that scale there, on its own graph branch, while the rest of the neck runs."""
         c3, c4, c5 = self.channels
         cat1, cat2, cat3, cat4 = self.__dict__.pop("_cats")
+        on_output = on_output or (lambda i, t: None)
         # C2f consumers take the upsample + concat inside their first 1x1 conv (C2f.emit, up_src); other blocks read the
         # concat buffer that upsample2x_kernel fills
         def foldable(block, c_out):       # limits of yms_conv_plan_add_upsampled
@@ -454,10 +463,13 @@ class Neck(_Compiled):
         else:
             self.up.emit(P, res2, cat2[..., :c4])
             out1 = self.c2f_2.emit(P, cat2)
+        on_output(0, out1)
         self.conv1.emit(P, out1, out=cat3[..., :c3])
         out2 = self.c2f_3.emit(P, cat3)
+        on_output(1, out2)
         self.conv2.emit(P, out2, out=cat4[..., :c4])
         out3 = self.c2f_4.emit(P, cat4)
+        on_output(2, out3)
         return out1, out2, out3
 
     def forward(self, x_res_1, x_res_2, x):
@@ -516,59 +528,71 @@ class Head(_Compiled):
             b2 = torch.cat([b2, b2.new_full((ncp - nc,), -1.0e4)])
         return (w0, b0), (w1, b1), (w2, b2)
 
-    def emit(self, P, feats: Sequence[torch.Tensor], fuse_decode: bool = False) -> List[torch.Tensor]:
-        """-> 3 fp32 raw tensors [B,H,W,64+nc] (box | cls), yolov8_head.py:119-122.
+    def begin(self, P, shapes, device, fuse_decode: bool = False):
+        """Set up one head emission over feature maps of the given [(B, H, W)] shapes; returns the context for emit_scale.
 
         fuse_decode: the program's final 1x1 convs decode in their epilogue (pred [B,A,4+nc] + candidates, `P.decoded`)
         instead of storing the logits; the logit-storing plans are kept in `P.raw_tail` and only run when the raw
         tensors are asked for (training-mode output, forward_raw)."""
         if self.ch != 16:
             raise RuntimeError("DFL is fixed to 16 bins (the reference builds DFL() with its default ch)")
-        raws = []
-        nc, ncp = self.num_classes, self.nc_pad
-        nop = self.coordinates + ncp
+        ctx = {"fuse": fuse_decode, "bases": [], "dec": None}
+        base = 0
+        for (_, h, w) in shapes:
+            ctx["bases"].append(base)
+            base += h * w
         if fuse_decode:
-            b = feats[0].shape[0]
-            anchors = sum(f.shape[1] * f.shape[2] for f in feats)
-            dev = feats[0].device
-            dec = {"pred": torch.empty((b, anchors, 4 + ncp), dtype=torch.float32, device=dev),
-                   "boxes": torch.empty((b, anchors, 4), dtype=torch.float32, device=dev),
-                   "scores": torch.empty((b, anchors), dtype=torch.float32, device=dev),
-                   "labels": torch.empty((b, anchors), dtype=torch.int32, device=dev),
-                   "stride": torch.zeros(4, dtype=torch.float32, device=dev), "stride_vals": None}
+            b = shapes[0][0]
+            dec = {"pred": torch.empty((b, base, 4 + self.nc_pad), dtype=torch.float32, device=device),
+                   "boxes": torch.empty((b, base, 4), dtype=torch.float32, device=device),
+                   "scores": torch.empty((b, base), dtype=torch.float32, device=device),
+                   "labels": torch.empty((b, base), dtype=torch.int32, device=device),
+                   "stride": torch.zeros(4, dtype=torch.float32, device=device), "stride_vals": None}
             P.hold(*[v for v in dec.values() if torch.is_tensor(v)])
             P.decoded = dec
-            base = 0
+            ctx["dec"] = dec
+        return ctx
+
+    def emit_scale(self, P, ctx, i: int, f: torch.Tensor) -> torch.Tensor:
+        """Head branches of scale i over feature map f -> the fp32 raw tensor [B,H,W,64+nc_pad] (box | cls),
+        yolov8_head.py:119-122 for one i."""
+        ncp = self.nc_pad
+        nop = self.coordinates + ncp
+        dec, fuse_decode = ctx["dec"], ctx["fuse"]
+        b, h, w, _ = f.shape
+        raw = P.buf(b, h, w, nop, dtype=torch.float32)
+        # box[i][0] and cls[i][0] read the same feature map: ONE 3x3 conv with the two weight sets
+        # stacked along c_out (64 + nc) reads it once; the second convs take channel slices.
+        wb, bb = self.box[i][0].folded()
+        (wc, bc), (wc1, bc1), (wc2, bc2) = self._cls_padded(i)
+        first = P.buf(b, h, w, nop)
+        P.conv(pack_weight(torch.cat([wb, wc], 0)), torch.cat([bb, bc]).contiguous(), f, first, ksize=3, stride=1, act=True)
+        for kind, lo, hi in (("box", 0, self.coordinates), ("cls", self.coordinates, nop)):
+            if kind == "box":
+                t = self.box[i][1].emit(P, first[..., lo:hi])
+                last = self.box[i][2]
+                wl, bl = pack_weight(last.weight.detach().float()), last.bias.detach().float().contiguous()
+            else:
+                t = P.buf(b, h, w, ncp)
+                P.conv(pack_weight(wc1), bc1.contiguous(), first[..., lo:hi], t, ksize=3, stride=1, act=self.cls[i][1].has_act)
+                wl, bl = pack_weight(wc2), bc2.contiguous()
+            if fuse_decode:
+                cand = {"cand_boxes": dec["boxes"]} if lo == 0 else {"cand_scores": dec["scores"], "cand_labels": dec["labels"]}
+                P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False,
+                       decode=dict(branch=kind, stride=dec["stride"][i:i + 1], pred=dec["pred"], anchor_base=ctx["bases"][i], **cand))
+                P.raw_tail.append(P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False, scheduled=False))
+            else:
+                P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False)
+        return raw
+
+    def emit(self, P, feats: Sequence[torch.Tensor], fuse_decode: bool = False) -> List[torch.Tensor]:
+        """-> 3 fp32 raw tensors [B,H,W,64+nc_pad] (box | cls), yolov8_head.py:119-122: the three scales as parallel branches."""
+        ctx = self.begin(P, [(f.shape[0], f.shape[1], f.shape[2]) for f in feats], feats[0].device, fuse_decode)
+        raws = []
         P.fork(len(feats))                                   # the scales are independent: parallel graph branches
         for i, f in enumerate(feats):
             P.branch(i)
-            b, h, w, _ = f.shape
-            raw = P.buf(b, h, w, nop, dtype=torch.float32)
-            # box[i][0] and cls[i][0] read the same feature map: ONE 3x3 conv with the two weight sets
-            # stacked along c_out (64 + nc) reads it once; the second convs take channel slices.
-            wb, bb = self.box[i][0].folded()
-            (wc, bc), (wc1, bc1), (wc2, bc2) = self._cls_padded(i)
-            first = P.buf(b, h, w, nop)
-            P.conv(pack_weight(torch.cat([wb, wc], 0)), torch.cat([bb, bc]).contiguous(), f, first, ksize=3, stride=1, act=True)
-            for kind, lo, hi in (("box", 0, self.coordinates), ("cls", self.coordinates, nop)):
-                if kind == "box":
-                    t = self.box[i][1].emit(P, first[..., lo:hi])
-                    last = self.box[i][2]
-                    wl, bl = pack_weight(last.weight.detach().float()), last.bias.detach().float().contiguous()
-                else:
-                    t = P.buf(b, h, w, ncp)
-                    P.conv(pack_weight(wc1), bc1.contiguous(), first[..., lo:hi], t, ksize=3, stride=1, act=self.cls[i][1].has_act)
-                    wl, bl = pack_weight(wc2), bc2.contiguous()
-                if fuse_decode:
-                    cand = {"cand_boxes": dec["boxes"]} if lo == 0 else {"cand_scores": dec["scores"], "cand_labels": dec["labels"]}
-                    P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False,
-                           decode=dict(branch=kind, stride=dec["stride"][i:i + 1], pred=dec["pred"], anchor_base=base, **cand))
-                    P.raw_tail.append(P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False, scheduled=False))
-                else:
-                    P.conv(wl, bl, t, raw[..., lo:hi], ksize=1, stride=1, act=False)
-            if fuse_decode:
-                base += h * w
-            raws.append(raw)
+            raws.append(self.emit_scale(P, ctx, i, f))
         P.join()
         return raws
 
@@ -607,9 +631,25 @@ class YOLOv8(_Compiled):
         b, _, h, w = img.shape
         outs = self.neck.alloc(P, b, h // 8, w // 8)
         ps = self.backbone.emit(P, img, outs=outs)
-        feats = self.neck.emit(P)
+        # The head of a scale only needs that scale's neck output: scales 0 and 1 start on their own graph branches as soon as
+        # N3 / N4 exist and run next to the rest of the neck (their launches fill the drain / launch gaps of the neck's chain
+        # and the SMs its small-map layers leave idle); scale 2 continues the main chain.
+        ctx = self.head.begin(P, [(b, h // s, w // s) for s in (8, 16, 32)], img_device(img), fuse_decode=self.head.can_fuse_decode())
+        raws = [None, None, None]
+
+        def start_head(i, t):
+            if i < 2 and OVERLAP_HEAD:
+                P.fork_one(i + 1)
+                P.branch(i + 1)
+                raws[i] = self.head.emit_scale(P, ctx, i, t)
+                P.branch(0)
+            else:
+                raws[i] = self.head.emit_scale(P, ctx, i, t)
+
+        feats = self.neck.emit(P, start_head)
+        P.join()
         self.__dict__["_taps"] = {"p": ps, "n": feats}      # NHWC bf16 views, for the parity tests
-        return tuple(self.head.emit(P, feats, fuse_decode=self.head.can_fuse_decode()))
+        return tuple(raws)
 
     def _run(self, x):
         """Replay the program on x.  Decode-fused programs leave pred / candidates in `prog.decoded`; the stride values
