@@ -7,8 +7,9 @@ import torch
 from yolo_ms_b200 import YOLOv8, synth, _lib, ops
 dev = torch.device("cuda", 0)
 lib = _lib.load(); lib.yms_debug_set_prof.argtypes = [C.c_void_p]
-model = YOLOv8(version="s", num_classes=80)
-model.load_state_dict(synth.synthetic_state_dict(model, "s", "c2f", seed=1))
+block = "ms" if "--ms" in sys.argv else "c2f"
+model = YOLOv8(version="s", num_classes=80, block=block)
+model.load_state_dict(synth.synthetic_state_dict(model, "s", block, seed=1))
 model = model.to(dev).eval(); model.head.stride = torch.tensor([8.0, 16.0, 32.0])
 x = synth.make_images(32, 640, 640, seed=7).to(dev)
 raws = model.forward_raw(x)
@@ -26,4 +27,4 @@ print("kept per image (first 4):", cnt[:4].tolist())
 for i, nm in enumerate(names):
     col = d[:, i][b[:, i + 1] > 0]
     if nm != "-" and len(col): print(f"{nm:24s} mean {col.mean()/1e3:8.1f} kcyc  max {col.max()/1e3:8.1f} kcyc")
-tot = (b[:, 7] - b[:, 0]); print("total to stamp7: mean %.1f max %.1f kcyc" % (tot.mean()/1e3, tot.max()/1e3))
+tot = (b[:, 7] - b[:, 0]); print("per-CTA total kcyc (first 16 CTAs = 4 images):", [round(float(v) / 1e3) for v in tot[:16]]); print("total to stamp7: mean %.1f max %.1f kcyc" % (tot.mean()/1e3, tot.max()/1e3))

@@ -10,17 +10,28 @@
 //   mode 1  depthwise -> pw2          e (TMA halo tiles) -> d (smem, UMMA A operand) -> tcgen05.mma -> epilogue -> y
 //   mode 2  pw1 -> depthwise -> pw2   x halo tile (TMA) -> tcgen05.mma -> e (TMEM -> bias/SiLU -> smem, zero outside the image)
 //                                     -> d -> tcgen05.mma -> epilogue -> y        (3c elements per pixel)
-// Work decomposition: output tile = 16 x 8 pixels of one image (M = 128 rows of the pw2 GEMM); the expanded channels are walked
-// in chunks of 64 (one 128-byte swizzle row); chunk j of pw2's K dimension is produced by the depthwise stage while the
-// tensor core consumes chunk j-1.
+// Work decomposition: output tile = 16 x 8 (or 24 x 5) pixels of one image (M = 128 rows of the pw2 GEMM); the expanded channels
+// are walked in chunks of 64 (one 128-byte swizzle row); chunk n of pw2's K dimension is produced by the depthwise stage while the
+// tensor core consumes chunk n-1.  Mode 0 has no GEMM: its work unit is ONE (tile, chunk) pair, so that a 20 x 20 map with 512
+// channels spreads over all SMs.
 //
-// Depthwise stage (the CUDA-core part; HBM-bound for k = 3, FMA-bound for k >= 5):
-//   * halo rows live in shared memory at a pitch of 24 pixels (a multiple of 8), 128 B per pixel, 16-byte chunks XOR-swizzled
-//     by (pixel & 7) -- exactly what TMA SWIZZLE_128B writes when every halo row is its own box at a 3072-byte pitch.  With
-//     strips that start at x = 0 or 8 the swizzle term of every tap is a compile-time constant: one IADD per load.
-//   * thread = 4 channels x 8 consecutive output pixels of one row: per kernel row it loads 8+k-1 pixels (LDS.64), converts
-//     bf16 -> fp32 with a shift / mask, and issues k FFMA2 (fma.rn.f32x2) per pixel per channel pair against the k weights
-//     of that row held in registers; fp32 accumulation throughout (the repo's numeric contract).
+// Roles (704 threads, one CTA per SM): warp 0 TMA producer | warp 1 MMA issuer (mode 0: issues the TMA stores) | warps 2-5 pw2
+// epilogue | warps 6-21 compute warps.  The depthwise stage is the CUDA-core bound of the layer, and it is latency-bound, not
+// throughput-bound, when whole warp groups march through a chunk in lock step (round 2, first version: two groups of 8 warps with
+// named barriers; ncu: the depthwise instructions were 28 % of the groups' samples, the rest waits).  So the unit of work is a
+// WARP ITEM -- a pixel block of one chunk, lane = channel pair -- and items of consecutive chunks are dealt round-robin to the
+// depthwise warps, each of which runs its own sequence against the chunk mbarriers (e_full / d_empty in, d_full / e_empty out; no
+// named barrier anywhere).  In mode 2 compute warps 0-7 are the pw1 epilogue (two per TMEM lane quadrant) and run one e stage
+// ahead of the 8 depthwise warps.
+//
+// Depthwise items (fp32 accumulation throughout -- the repo's numeric contract; FFMA2 = fma.rn.f32x2 on a channel pair):
+//   * halo rows live in shared memory at a pitch of 24 / 32 pixels (a multiple of 8), 128 B per pixel, 16-byte chunks XOR-swizzled
+//     by (pixel & 7) -- exactly what TMA SWIZZLE_128B writes when every halo row is its own box at a 3072-byte pitch.  A warp
+//     reads ONE pixel per LDS.32 (its 32 lanes are the 32 channel pairs = the pixel's 128 contiguous bytes: conflict-free).
+//   * k = 3, 16 x 8 tiles: item = 4 x 4 output pixels; the 6 x 6 halo is loaded and converted once, the 9 taps sit in registers.
+//   * other k / tiles: item = 2 rows x 8 pixels; every input row is loaded and converted once and feeds both output rows
+//     (2k FFMA2 per loaded pixel); the weights of two kernel rows sit in registers (a ring over the input rows).  Shared-memory
+//     traffic per chunk drops from k x to (k+1)/2 x the halo tile against one-row strips -- the strips were bandwidth-bound.
 //   * the result (bias, SiLU, bf16) is written as a [128 x 64] K-major SWIZZLE_128B tile = the A operand of pw2's MMAs
 //     (or the source of a TMA store in mode 0).
 #include "conv_plan.h"
@@ -36,22 +47,41 @@ using namespace tc;
 // at which halo rows sit in shared memory.  GEOM 0 = 16 x 8 (pitch 24); GEOM 1 = 24 x 5 (pitch 32) for maps whose width is
 // a bad fit for 16-pixel tiles (a 20 x 20 map is 6 tiles at 52 % with GEOM 0, 4 tiles at 83 % with GEOM 1).
 template <int GEOM> struct Geom;
-template <> struct Geom<0> { static constexpr int TW = 16, TH = 8, PITCH = 24; };
-template <> struct Geom<1> { static constexpr int TW = 24, TH = 5, PITCH = 32; };
+template <> struct Geom<0> { static constexpr int TW = 16, TH = 8; };
+template <> struct Geom<1> { static constexpr int TW = 24, TH = 5; };
+// Halo-row pitch in pixels: TW + k - 1 rounded up to a multiple of 8, except k = 5 (20 / 28 pixels: a multiple of 4 -- the swizzle
+// phase of a pixel is then (row * pitch + x) & 7, still a compile-time constant per tap for items that start on even rows; the
+// 17 % smaller stage is what lets the dw -> pw2 mode of the 256-channel layers keep three stages beside its resident weights)
+__host__ __device__ constexpr int halo_pitch(int k, int geom) {
+    return k == 5 ? (geom ? 28 : 20) : (((geom ? 24 : 16) + k - 1 + 7) & ~7);
+}
 
 constexpr int kMaxE = 4;                         // e-ring stages
 constexpr int kDTile = 128 * 128;                // one [128 x 64] bf16 tile
-constexpr int kGroupThreads = 256;               // threads of one depthwise group
-constexpr int kFirstDwWarp = 6;                  // warp 0 producer, 1 MMA, 2-5 epilogue, 6.. depthwise groups
+constexpr int kFirstCw = 6;                      // warp 0 producer, 1 MMA / storer, 2-5 pw2 epilogue, 6.. compute warps
+constexpr int kCwCount = 16;                     // compute warps
+constexpr int kPWarps = 8;                       // mode 2: compute warps 0..7 = pw1 epilogue, the rest depthwise
+constexpr int kG1Warp = kFirstCw + kCwCount;     // mode 2: issuer of the pw1 MMAs (its own warp: never blocked behind the pw2 chain)
+constexpr int kThreads = (kG1Warp + 1) * 32;
+constexpr int kMaxD = 4;                         // d-ring buffers
 constexpr int kSmemLimit = 232448;
+
+// Depthwise warp items of one chunk (host and device must agree: the chunk barriers count item arrivals)
+__host__ __device__ constexpr bool item_is_block(int k, int geom) { return k == 3 && geom == 0; }
+__host__ __device__ constexpr int item_rows(int k) { return k <= 7 ? 2 : 1; }
+__host__ __device__ constexpr int items_per_chunk(int k, int geom) {
+    return item_is_block(k, geom) ? 8
+         : (geom ? (24 / 8) * ((5 + item_rows(k) - 1) / item_rows(k)) : (16 / 8) * ((8 + item_rows(k) - 1) / item_rows(k)));
+}
 
 struct MsParams {
     int mode, ksize, geom;
     int tiles_x, tiles_y, batch, total_tiles;
+    int units, cpu;                              // work units of the grid and chunks per unit (mode 0: tiles * chunks, 1; else tiles, chunks)
     uint32_t mg_tiles_x, mg_tiles_y;
     int e_ch, n_chunks, tail_ksteps;             // expanded channels, 64-channel chunks, k-steps of the last chunk
     int c_out, block_n, act2;
-    int e_stages, dw_groups;
+    int e_stages, n_items, d_bufs, g1_stages;
     int w2_resident, w2_tile_bytes;
     int acc_stride, tmem_cols;
     int stage_bytes, off_dww, off_dwb, off_w2;   // layout of one e stage
@@ -76,7 +106,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void dwg_bar_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ unsigned long long pack64(uint32_t lo, uint32_t hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
@@ -92,6 +121,13 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+// bf16x2 word -> packed (f32, f32): the low half through PRMT (ALU pipe; a shift would be emitted as an IMAD on the FMA pipe,
+// which is the pipe the depthwise stage is bound by), the high half through a mask
+__device__ __forceinline__ unsigned long long bf16x2_to_f32x2(uint32_t u) {
+    uint32_t lo;
+    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(u));
+    return pack64(lo, u & 0xffff0000u);
+}
 
 struct TileXY { int img, x0, y0; };
 template <int GEOM>
@@ -103,38 +139,6 @@ __device__ __forceinline__ TileXY decode_tile(const MsParams& p, int t) {
     const int ty = (int)(q - q2 * p.tiles_y);
     c.img = (int)q2; c.x0 = tx * Geom<GEOM>::TW; c.y0 = ty * Geom<GEOM>::TH;
     return c;
-}
-
-// Depthwise accumulation of one work item: 8 output pixels (one row, x0 .. x0+7) x 4 channels.  eb[i] = address of this
-// thread's 8 bytes inside halo pixel (row oy, x0 + i) for i = 0..7 (the swizzle term depends on i & 7 only, so pixel x0 + j,
-// kernel row ky is eb[j & 7] + constant); w_base = this thread's 16 bytes of tap 0 in the [k*k][64] f32 weight block.
-// acc[o][0] = channels (4q, 4q+1), acc[o][1] = channels (4q+2, 4q+3) of output pixel o, as packed f32x2.
-template <int K, int PITCH>
-__device__ __forceinline__ void dw_accumulate(const uint32_t (&eb)[8], uint32_t w_base, unsigned long long (&acc)[8][2]) {
-    #pragma unroll
-    for (int o = 0; o < 8; ++o) { acc[o][0] = 0ull; acc[o][1] = 0ull; }
-    #pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-        unsigned long long w[K][2];
-        #pragma unroll
-        for (int kx = 0; kx < K; ++kx)
-            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w[kx][0]), "=l"(w[kx][1]) : "r"(w_base + (uint32_t)((ky * K + kx) * 256)));
-        #pragma unroll
-        for (int j = 0; j < 8 + K - 1; ++j) {
-            uint32_t v0, v1;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(eb[j & 7] + (uint32_t)((ky * PITCH + (j & ~7)) * 128)));
-            const unsigned long long p0 = pack64(v0 << 16, v0 & 0xffff0000u);
-            const unsigned long long p1 = pack64(v1 << 16, v1 & 0xffff0000u);
-            #pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const int o = j - kx;
-                if (o >= 0 && o < 8) {
-                    acc[o][0] = fma2(p0, w[kx][0], acc[o][0]);
-                    acc[o][1] = fma2(p1, w[kx][1], acc[o][1]);
-                }
-            }
-        }
-    }
 }
 
 // SiLU of two packed fp32 values given as acc (pre-activation without bias) and hb = 0.5 * bias:  h = 0.5 * acc + hb,
@@ -151,24 +155,9 @@ __device__ __forceinline__ uint32_t silu2_bf16(unsigned long long acc, unsigned 
 }
 constexpr unsigned long long kHalf2 = 0x3f0000003f000000ull;     // (0.5f, 0.5f)
 
-// bias + SiLU + bf16, written to rows (r0 + o) of the [128 x 64] swizzled tile: db = d tile + r0 * 128 (r0 % 8 == 0), tbl[o] = swizzled
-// byte offset of this thread's 8 bytes inside a row with (row & 7) == o
-__device__ __forceinline__ void dw_store(uint32_t db, uint32_t b_addr, const uint32_t (&tbl)[8], const unsigned long long (&acc)[8][2]) {
-    unsigned long long b0, b1;
-    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(b_addr));
-    b0 = fma2(b0, kHalf2, 0ull); b1 = fma2(b1, kHalf2, 0ull);
-    #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        const uint32_t o0 = silu2_bf16(acc[o][0], kHalf2, b0);
-        const uint32_t o1 = silu2_bf16(acc[o][1], kHalf2, b1);
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(db + tbl[o] + (uint32_t)(o * 128)), "r"(o0), "r"(o1) : "memory");
-    }
-}
-
-// k = 3, 16 x 8 tiles: register-blocked work item = 2 channels x a 4 x 4 block of output pixels.  Every input pixel of the
-// block's 6 x 6 halo is loaded (LDS.32: the 32 lanes of a warp are the 32 channel pairs of ONE pixel = its 128 contiguous
-// bytes) and converted ONCE and feeds up to 9 FFMA2; the 9 taps sit in registers.  ~390 instructions per 32 outputs against
-// ~740 for the row-strip item above (whose loads and conversions are repeated for every kernel row).
+// k = 3, 16 x 8 tiles: warp item = a 4 x 4 block of output pixels, lane = channel pair.  Every input pixel of the block's 6 x 6
+// halo is loaded (LDS.32: the 32 lanes of a warp are the 32 channel pairs of ONE pixel = its 128 contiguous bytes) and converted
+// ONCE and feeds up to 9 FFMA2; the 9 taps sit in registers.
 //   e_blk = stage + ((by*4) * PITCH + bx*4) * 128, cp = channel pair (lane), xs = (bx*4) & 7 (0 or 4)
 template <int PITCH, int TW>
 __device__ __forceinline__ void dw_block_k3(uint32_t e_blk, uint32_t w_base, uint32_t b_addr, uint32_t d_blk, int cp, int xs) {
@@ -187,7 +176,7 @@ __device__ __forceinline__ void dw_block_k3(uint32_t e_blk, uint32_t w_base, uin
         for (int j = 0; j < 6; ++j) {
             uint32_t u;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(eb[j] + (uint32_t)(iy * PITCH * 128)));
-            v[j] = pack64(u << 16, u & 0xffff0000u);
+            v[j] = bf16x2_to_f32x2(u);
         }
         #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -216,17 +205,73 @@ __device__ __forceinline__ void dw_block_k3(uint32_t e_blk, uint32_t w_base, uin
     }
 }
 
+// General warp item: NR output rows x 8 pixels (x0 a multiple of 8), lane = channel pair.  Input row iy of the item's halo
+// (NR + K - 1 rows of 8 + K - 1 pixels) is loaded and converted once; it is kernel row ky = iy - r of output row r, so the weights
+// of kernel rows iy and iy - 1 are live (a two-slot ring, K LDS.64 per input row).
+//   e_item = stage + (oy0 * PITCH + x0) * 128 with (oy0 * PITCH + x0) % 8 == 0;  d_item = d tile + (oy0 * TW + x0) * 128;
+//   w_lane / b_lane = this lane's 8 bytes of tap 0 / of the bias.
+template <int K, int PITCH, int TW, int NR>
+__device__ __forceinline__ void dw_rows(uint32_t e_item, uint32_t w_lane, uint32_t b_lane, uint32_t d_item, int cp) {
+    static_assert(NR == 1 || NR == 2, "row ring holds two kernel rows");
+    const uint32_t sub = (uint32_t)((cp & 3) * 4), chunk = (uint32_t)(cp >> 2);
+    uint32_t sw[8];                                   // lane part of the swizzled address of a pixel with (pixel & 7) == i
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) sw[i] = ((chunk ^ (uint32_t)i) << 4) + sub;
+    unsigned long long acc[NR][8];
+    unsigned long long w[2][K];
+    #pragma unroll
+    for (int iy = 0; iy < NR + K - 1; ++iy) {
+        if (iy < K) {
+            #pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(w[iy & 1][kx]) : "r"(w_lane + (uint32_t)((iy * K + kx) * 256)));
+        }
+        #pragma unroll
+        for (int j = 0; j < 8 + K - 1; ++j) {
+            uint32_t u;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(e_item + sw[(iy * PITCH + j) & 7] + (uint32_t)((iy * PITCH + j) * 128)));
+            const unsigned long long v = bf16x2_to_f32x2(u);
+            #pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int ky = iy - r;
+                if (ky >= 0 && ky < K) {
+                    #pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        const int o = j - kx;
+                        if (o >= 0 && o < 8)
+                            acc[r][o] = (ky == 0 && kx == 0) ? fma2(v, w[0][0], 0ull) : fma2(v, w[ky & 1][kx], acc[r][o]);
+                    }
+                }
+            }
+        }
+    }
+    unsigned long long hb;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(hb) : "r"(b_lane));
+    hb = fma2(hb, kHalf2, 0ull);
+    #pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        #pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const uint32_t v = silu2_bf16(acc[r][o], kHalf2, hb);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(d_item + sw[o] + (uint32_t)((r * TW + o) * 128)), "r"(v) : "memory");
+        }
+    }
+}
+
 template <int K, int GEOM>
-__global__ void __launch_bounds__(704, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_dww,
                 const __grid_constant__ CUtensorMap tm_dwb, const __grid_constant__ CUtensorMap tm_w2,
                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_w1,
                 const __grid_constant__ MsParams p) {
-    constexpr int TW = Geom<GEOM>::TW, TH = Geom<GEOM>::TH, PITCH = Geom<GEOM>::PITCH;
+    constexpr int TW = Geom<GEOM>::TW, TH = Geom<GEOM>::TH, PITCH = halo_pitch(K, GEOM);
     constexpr int HWX = TW + K - 1, HWY = TH + K - 1, PAD = K / 2;
-    constexpr int kStripsX = TW / 8, kStrips = kStripsX * TH;
-    static_assert(HWX <= PITCH && TW * TH <= 128 && kStrips * 16 <= kGroupThreads, "tile geometry");
+    constexpr bool kBlock = item_is_block(K, GEOM);
+    constexpr int NR = item_rows(K);
+    constexpr int kStripsX = TW / 8;
+    constexpr int kItems = items_per_chunk(K, GEOM);
+    static_assert(HWX <= PITCH && TW * TH <= 128 && TW % 8 == 0 && (PITCH % 8 == 0 || (PITCH % 4 == 0 && !kBlock)), "tile geometry");
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
@@ -244,24 +289,24 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     float* s_bias = reinterpret_cast<float*>(gbase + (s_biasu - base));          // pw2 bias (0.5 x when act), then pw1 bias (mode 2)
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
     const uint32_t bar0 = smem_u32(bars);
-    auto e_full = [&](int s) { return bar0 + 8u * s; };
-    auto e_empty = [&](int s) { return bar0 + 8u * (kMaxE + s); };
-    auto d_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + s); };
-    auto d_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 2 + s); };
-    auto acc_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 4 + s); };
-    auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 6 + s); };
-    const uint32_t res_bar = bar0 + 8u * (2 * kMaxE + 8);
-    const uint32_t w_bar = bar0 + 8u * (2 * kMaxE + 9);
-    auto g1_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 10 + s); };      // mode 2: pw1 accumulator stage ready
-    auto g1_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 12 + s); };
-    auto x_full = [&](int s) { return bar0 + 8u * (2 * kMaxE + 14 + s); };       // mode 2: x halo tile landed / may be overwritten
-    auto x_empty = [&](int s) { return bar0 + 8u * (2 * kMaxE + 16 + s); };
-    constexpr int kNumBars = 2 * kMaxE + 18;
+    auto e_full = [&](int s) { return bar0 + 8u * s; };                          // chunk inputs of stage s complete (TMA + pw1 epilogue warps)
+    auto e_empty = [&](int s) { return bar0 + 8u * (kMaxE + s); };               // every depthwise item of the stage's chunk has been computed
+    auto d_full = [&](int s) { return bar0 + 8u * (8 + s); };                    // every item of the chunk has been written to d buffer s
+    auto d_empty = [&](int s) { return bar0 + 8u * (12 + s); };                  // the MMAs (mode 0: the TMA store) that read d buffer s are done
+    auto acc_full = [&](int s) { return bar0 + 8u * (16 + s); };
+    auto acc_empty = [&](int s) { return bar0 + 8u * (18 + s); };
+    const uint32_t res_bar = bar0 + 8u * 20;
+    const uint32_t w_bar = bar0 + 8u * 21;
+    auto g1_full = [&](int s) { return bar0 + 8u * (22 + s); };                  // mode 2: pw1 accumulator stage ready (up to 3 stages)
+    auto g1_empty = [&](int s) { return bar0 + 8u * (25 + s); };
+    auto x_full = [&](int s) { return bar0 + 8u * (28 + s); };                   // mode 2: x halo tile landed / may be overwritten
+    auto x_empty = [&](int s) { return bar0 + 8u * (30 + s); };
+    constexpr int kNumBars = 32;
+    static_assert(kMaxE == 4 && kMaxD == 4, "barrier map");
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int dw_warps = p.dw_groups * 8;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -272,10 +317,11 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         }
         if (lane < kNumBars) {
             uint32_t cnt = 1;
-            if (lane >= kMaxE && lane < 2 * kMaxE) cnt = 8u + ((p.mode >= 1 && !p.w2_resident) ? 1u : 0u);   // e_empty: the 8 warps of a group (+ MMA commit)
-            else if (lane >= 2 * kMaxE && lane < 2 * kMaxE + 2) cnt = 8u;                                     // d_full: the 8 warps of a group
-            else if (lane >= 2 * kMaxE + 6 && lane < 2 * kMaxE + 8) cnt = 4u;                                 // acc_empty: 4 epilogue warps
-            else if (lane >= 2 * kMaxE + 12 && lane < 2 * kMaxE + 14) cnt = 8u;                               // g1_empty: the 8 warps of a group
+            if (lane < kMaxE) cnt = 1u + (p.mode == 2 ? (uint32_t)kPWarps : 0u);                              // e_full: producer (+ pw1 epilogue warps)
+            else if (lane < 2 * kMaxE) cnt = (uint32_t)kItems + ((p.mode >= 1 && !p.w2_resident) ? 1u : 0u);  // e_empty: items (+ MMA commit)
+            else if (lane < 12) cnt = (uint32_t)kItems;                                                       // d_full: items
+            else if (lane >= 18 && lane < 20) cnt = 4u;                                                       // acc_empty: 4 epilogue warps
+            else if (lane >= 25 && lane < 28) cnt = (uint32_t)kPWarps;                                        // g1_empty: pw1 epilogue warps
             mbar_init(bar0 + 8u * lane, cnt);
         }
         fence_barrier_init();
@@ -313,6 +359,10 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
     pdl_launch_dependents();
     pdl_wait();
 
+    const int grid = (int)gridDim.x;
+    // unit u of the grid: mode 0 = chunk (u % n_chunks) of tile (u / n_chunks); else all chunks of tile u
+    auto unit_tile = [&](int u, int& j0) { int t = u; j0 = 0; if (p.mode == 0) { t = u / p.n_chunks; j0 = u - t * p.n_chunks; } return t; };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
@@ -328,94 +378,70 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                                 (kb < p.kb1 ? kb : kb - p.kb1) * 64, tc.x0 - PAD, tc.y0 - PAD, tc.img);
                 if (++xb == p.x_bufs) { xb = 0; xph ^= 1u; }
             };
-            if (p.mode == 2 && (int)blockIdx.x < p.total_tiles) load_x(blockIdx.x);
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            if (p.mode == 2 && (int)blockIdx.x < p.units) load_x(blockIdx.x);
+            for (int u = blockIdx.x; u < p.units; u += grid) {
+                int j0;
+                const int t = unit_tile(u, j0);
                 const TileXY tc = decode_tile<GEOM>(p, t);
                 // the NEXT tile's input halo goes first: with two buffers it lands while this tile is processed; with one
                 // buffer it is issued after this tile's chunk loads (it has to wait for this tile's last pw1 MMA anyway)
-                if (p.mode == 2 && p.x_bufs == 2 && t + (int)gridDim.x < p.total_tiles) load_x(t + gridDim.x);
-                for (int j = 0; j < p.n_chunks; ++j) {
+                if (p.mode == 2 && p.x_bufs == 2 && u + grid < p.units) load_x(u + grid);
+                for (int jj = 0; jj < p.cpu; ++jj) {
+                    const int j = j0 + jj;
                     mbar_wait_sleep(e_empty(s), ph ^ 1u);
                     const uint32_t st = s_e0 + (uint32_t)(s * p.stage_bytes);
                     mbar_expect_tx(e_full(s), p.stage_tx);
                     if (p.mode != 2) {
-                        #pragma unroll 1
-                        for (int hy = 0; hy < HWY; ++hy)
-                            tma_load_4d(st + (uint32_t)(hy * PITCH * 128), &tm_e, e_full(s), j * 64, tc.x0 - PAD, tc.y0 - PAD + hy, tc.img);
+                        if constexpr (PITCH == HWX) {          // rows are contiguous: the whole halo is one box (host: box height HWY)
+                            tma_load_4d(st, &tm_e, e_full(s), j * 64, tc.x0 - PAD, tc.y0 - PAD, tc.img);
+                        } else {
+                            #pragma unroll 1
+                            for (int hy = 0; hy < HWY; ++hy)
+                                tma_load_4d(st + (uint32_t)(hy * PITCH * 128), &tm_e, e_full(s), j * 64, tc.x0 - PAD, tc.y0 - PAD + hy, tc.img);
+                        }
                     }
                     tma_load_2d(st + (uint32_t)p.off_dww, &tm_dww, e_full(s), j * 64, 0);
                     tma_load_2d(st + (uint32_t)p.off_dwb, &tm_dwb, e_full(s), j * 64, 0);
                     if (p.mode >= 1 && !p.w2_resident) tma_load_3d(st + (uint32_t)p.off_w2, &tm_w2, e_full(s), j * 64, 0, 0);
                     if (++s == p.e_stages) { s = 0; ph ^= 1u; }
                 }
-                if (p.mode == 2 && p.x_bufs == 1 && t + (int)gridDim.x < p.total_tiles) load_x(t + gridDim.x);
+                if (p.mode == 2 && p.x_bufs == 1 && u + grid < p.units) load_x(u + grid);
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one elected thread) =================
-        if (p.mode >= 1 && elect_one()) {
+        if (p.mode == 0) {
+            // ================= mode 0: TMA store of every finished d tile (one elected thread) =================
+            if (elect_one()) {
+                int ds = 0; uint32_t dph = 0;
+                for (int u = blockIdx.x; u < p.units; u += grid) {
+                    int j0;
+                    const int t = unit_tile(u, j0);
+                    const TileXY tc = decode_tile<GEOM>(p, t);
+                    mbar_wait_sleep(d_full(ds), dph);                        // the writers fenced (generic -> async proxy) before arriving
+                    tma_store_4d(&tm_y, s_d0 + (uint32_t)ds * kDTile, j0 * 64, tc.x0, tc.y0, tc.img);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                    mbar_arrive(d_empty(ds));
+                    if (++ds == p.d_bufs) { ds = 0; dph ^= 1u; }
+                }
+            }
+        } else if (elect_one()) {
+            // ================= MMA issuer (one elected thread) =================
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint64_t hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-            if (p.w2_resident || p.mode == 2) mbar_wait(w_bar, 0u);     // armed in the prologue only in these cases
+            if (p.w2_resident) mbar_wait_sleep(w_bar, 0u);          // armed in the prologue
             tc_fence_after();
-            uint32_t n = 0, ti = 0;
-            int s = 0; uint32_t ph = 0;                        // e-ring stage / phase of chunk n
-            int xb = 0; uint32_t xph = 0;                      // x buffer / phase of the next tile whose pw1 GEMM starts
-            const int kbt = p.kb1 + p.kb2;
-            const int tail1 = p.mode == 2 ? (((p.c_in1 - (p.kb1 - 1) * 64) + 15) >> 4) : 4;
-            const int tail2 = (p.mode == 2 && p.kb2) ? (((p.c_in2 - (p.kb2 - 1) * 64) + 15) >> 4) : 4;
-            uint32_t sx_cur = s_x;                             // x buffer of the tile whose pw1 chunks are being issued
-            auto issue_g1 = [&](uint32_t gn, int j) {
-                const int gs = (int)(gn & 1u);
-                mbar_wait(g1_empty(gs), ((gn >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                for (int m = 0; m < p.mt; ++m) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
-                    for (int kb = 0; kb < kbt; ++kb) {
-                        const uint32_t a16 = ((sx_cur + (uint32_t)(kb * p.x_kb_stride + m * kDTile)) & 0x3FFFFu) >> 4;
-                        const uint32_t b16 = ((s_w1 + (uint32_t)((j * kbt + kb) * p.w1_tile_bytes)) & 0x3FFFFu) >> 4;
-                        const int ks = (kb == p.kb1 - 1) ? tail1 : ((kb == kbt - 1) ? tail2 : 4);
-                        for (int k = 0; k < ks; ++k)
-                            umma_bf16(d_tmem, hi | (uint64_t)(a16 + 2 * k), hi | (uint64_t)(b16 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
-                    }
-                }
-                umma_commit(g1_full(gs));
-            };
-            // mode 2: the pw1 GEMM runs TWO chunks ahead of the pw2 GEMM (both accumulator stages in flight), also across tile
-            // boundaries: pw1(n+2) is issued as soon as the pw1 epilogue of chunk n has drained its stage -- i.e. while the
-            // depthwise stage of chunk n is still running -- so that the group that finishes chunk n finds the accumulator of
-            // chunk n+2 ready.  (With a look-ahead of one, pw1(n+2) waited for pw2(n), i.e. for the END of the depthwise stage
-            // of chunk n, and every group idled for a pw1 GEMM latency per chunk.)  The x halo tile has one or two buffers; a
-            // buffer is released by the last pw1 MMA of its tile.
-            int g_t = blockIdx.x, g_j = 0; uint32_t g_n = 0;      // cursor of the next pw1 GEMM: tile, chunk, global chunk index
-            int xb_cur = 0;
-            auto issue_next_g1 = [&]() {
-                if (p.mode != 2 || g_t >= p.total_tiles) return;
-                if (g_j == 0) {
-                    mbar_wait(x_full(xb), xph);
-                    tc_fence_after();
-                    xb_cur = xb; sx_cur = s_x + (uint32_t)(xb * p.x_buf_bytes);
-                    if (++xb == p.x_bufs) { xb = 0; xph ^= 1u; }
-                }
-                issue_g1(g_n, g_j);
-                ++g_n;
-                if (++g_j == p.n_chunks) { umma_commit(x_empty(xb_cur)); g_j = 0; g_t += (int)gridDim.x; }
-            };
-            issue_next_g1();
-            issue_next_g1();
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+            uint32_t ti = 0;
+            int s = 0; uint32_t ph = 0;                        // e-ring stage / phase of the next chunk
+            int ds = 0; uint32_t dph = 0;                      // d-ring buffer / phase of the next chunk
+            for (int t = blockIdx.x; t < p.total_tiles; t += grid, ++ti) {
                 const int as = (int)(ti & 1u);
-                mbar_wait(acc_empty(as), ((ti >> 1) & 1u) ^ 1u);
+                mbar_wait_sleep(acc_empty(as), ((ti >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
-                for (int j = 0; j < p.n_chunks; ++j, ++n) {
-                    // pw1 of chunk n+2 first: its accumulator stage (n & 1) is free once the pw1 epilogue of chunk n is done,
-                    // which happens BEFORE the depthwise stage of chunk n that the pw2 MMAs below wait for
-                    issue_next_g1();
-                    const int ds = (int)(n & 1u);
-                    if (!p.w2_resident) mbar_wait(e_full(s), ph);
-                    mbar_wait(d_full(ds), (n >> 1) & 1u);
+                for (int j = 0; j < p.n_chunks; ++j) {
+                    if (!p.w2_resident) mbar_wait_sleep(e_full(s), ph);
+                    mbar_wait_sleep(d_full(ds), dph);
                     tc_fence_after();
                     const uint32_t a16 = ((s_d0 + (uint32_t)ds * kDTile) & 0x3FFFFu) >> 4;
                     const uint32_t b16 = ((p.w2_resident ? s_w2 + (uint32_t)(j * p.w2_tile_bytes)
@@ -427,11 +453,12 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                     if (!p.w2_resident) umma_commit(e_empty(s));
                     if (j == p.n_chunks - 1) umma_commit(acc_full(as));
                     if (++s == p.e_stages) { s = 0; ph ^= 1u; }
+                    if (++ds == p.d_bufs) { ds = 0; dph ^= 1u; }
                 }
             }
         }
         __syncwarp();
-    } else if (warp < kFirstDwWarp) {
+    } else if (warp < kFirstCw) {
         // ================= pw2 epilogue: TMEM -> bias / SiLU -> bf16 -> swizzled staging -> TMA store =================
         if (p.mode >= 1) {
             EpiShared e;
@@ -446,7 +473,7 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             e.row = (warp & 3) * 32 + lane;
             const int n_chunks_out = (p.block_n + 63) >> 6;
             uint32_t res_phase = 0u, ti = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+            for (int t = blockIdx.x; t < p.total_tiles; t += grid, ++ti) {
                 const int as = (int)(ti & 1u);
                 const TileXY tc = decode_tile<GEOM>(p, t);
                 EpiTile tl; tl.n0 = 0; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
@@ -460,124 +487,153 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             }
             if (e.leader) tma_store_wait_read<0>();
         }
-    } else if (warp < kFirstDwWarp + dw_warps) {
-        // ================= depthwise groups: group g takes the chunks n = g (mod groups) =================
-        const int dwt = (int)threadIdx.x - kFirstDwWarp * 32;
-        const int g = dwt >> 8, tg = dwt & 255;
-        const int q = tg & 15, strip = tg >> 4;
-        const bool active = strip < kStrips;                                     // GEOM 1 has 15 strips for 16 slots
-        const int oy = active ? strip / kStripsX : 0, x0 = active ? (strip % kStripsX) * 8 : 0;
-        uint32_t tbl[8];
-        #pragma unroll
-        for (int i = 0; i < 8; ++i) tbl[i] = ((uint32_t)((q >> 1) ^ i) << 4) + (uint32_t)((q & 1) * 8);
-        const uint32_t item_off = (uint32_t)((oy * PITCH + x0) * 128);          // this item's first halo pixel inside a stage
-        const uint32_t d_off = (uint32_t)((oy * TW + x0) * 128);                // and its first row inside the d tile
-        const bool leader = tg == 0;
-        const int bar_id = 2 + g;
-        const int wq = warp & 3;                                                 // TMEM lane quadrant this warp may read
-        const int wsub = (warp - kFirstDwWarp) & 7;                              // warp index inside the group
-        uint32_t n = 0;
+    } else if (p.mode == 2 && warp >= kFirstCw && warp < kFirstCw + kPWarps) {
+        // ================= mode 2, pw1 epilogue warps: accumulator rows (halo pixels) -> bias / SiLU -> bf16 -> halo tile of the
+        // chunk's e stage, zero outside the image.  Two warps per TMEM lane quadrant, dealt the M tiles of the halo by parity.
+        const int wq = warp & 3, half = (warp - kFirstCw) >> 2;
+        const int hp = p.hp, mt = p.mt, img_w = p.img_w, img_h = p.img_h, e_stages = p.e_stages, n_chunks = p.n_chunks;
+        const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)p.g1_base;
+        const uint32_t g1_stride = (uint32_t)p.g1_stride;
+        const int g1_stages = p.g1_stages;
         int s = 0; uint32_t ph = 0;
-        int gsel = 0;                                                            // group whose turn it is
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            TileXY tc; tc.img = 0; tc.x0 = 0; tc.y0 = 0;
-            if (p.mode != 1) tc = decode_tile<GEOM>(p, t);
-            for (int j = 0; j < p.n_chunks; ++j, ++n) {
-                const int s_cur = s; const uint32_t ph_cur = ph;
-                if (++s == p.e_stages) { s = 0; ph ^= 1u; }
-                const bool mine = gsel == g;
-                if (++gsel == p.dw_groups) gsel = 0;
-                if (!mine) continue;
-                const uint32_t st = s_e0 + (uint32_t)(s_cur * p.stage_bytes);
-                const int ds = (int)(n & 1u);
-                const uint32_t d_base = s_d0 + (uint32_t)ds * kDTile;
-                // the stage holds this chunk's depthwise weights (and, modes 0/1, its halo tile); in mode 2 this also says
-                // that the previous halo tile of the stage has been consumed, by whichever group used it
-                mbar_wait_sleep(e_full(s_cur), ph_cur);
-                if (p.mode == 2) {
-                    // ---- pw1 epilogue: accumulator rows (halo pixels) -> bias / SiLU -> bf16 -> halo tile of this stage, zero outside the image
-                    const int gs = (int)(n & 1u);
-                    mbar_wait_sleep(g1_full(gs), (n >> 1) & 1u);
-                    tc_fence_after();
-                    for (int m = wsub >> 2; m < p.mt; m += 2) {
-                        const int hpix = m * 128 + wq * 32 + lane;                // halo pixel of this thread = accumulator row
-                        if (m * 128 + wq * 32 >= p.hp) break;                     // the whole warp is past the halo
-                        const int hy = hpix / HWX, hx = hpix - hy * HWX;
-                        const int gx = tc.x0 - PAD + hx, gy = tc.y0 - PAD + hy;
-                        const bool inside = hpix < p.hp && gx >= 0 && gx < p.img_w && gy >= 0 && gy < p.img_h;
-                        const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
-                        const uint32_t line = st + (uint32_t)((hy * PITCH + hx) * 128);
-                        #pragma unroll 1
-                        for (int q16 = 0; q16 < 4; ++q16) {
-                            uint32_t v[16];
-                            tmem_ld16(t_row + (uint32_t)(q16 * 16), v);
-                            tmem_ld_wait();
-                            if (hpix < p.hp) {
-                                const float4* bq = reinterpret_cast<const float4*>(s_bias + 256 + j * 64 + q16 * 16);
-                                uint32_t o[8];
-                                #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float4 hb = bq[i];
-                                    const uint32_t r0 = silu2_bf16(pack64(v[4 * i + 0], v[4 * i + 1]), kHalf2, pack64(__float_as_uint(hb.x), __float_as_uint(hb.y)));
-                                    const uint32_t r1 = silu2_bf16(pack64(v[4 * i + 2], v[4 * i + 3]), kHalf2, pack64(__float_as_uint(hb.z), __float_as_uint(hb.w)));
-                                    o[2 * i] = inside ? r0 : 0u;
-                                    o[2 * i + 1] = inside ? r1 : 0u;
-                                }
-                                #pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const uint32_t addr = line + (((uint32_t)(q16 * 2 + h) ^ (uint32_t)(hx & 7)) << 4);
-                                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[4 * h]), "r"(o[4 * h + 1]), "r"(o[4 * h + 2]), "r"(o[4 * h + 3]) : "memory");
-                                }
+        int gs = 0; uint32_t gph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += grid) {
+            const TileXY tc = decode_tile<GEOM>(p, t);
+            for (int j = 0; j < n_chunks; ++j) {
+                const uint32_t st = s_e0 + (uint32_t)s * stage_bytes;
+                mbar_wait_sleep(e_empty(s), ph ^ 1u);                         // the depthwise items of the stage's previous chunk are done
+                mbar_wait_sleep(g1_full(gs), gph);
+                tc_fence_after();
+                for (int m = half; m < mt; m += 2) {
+                    if (m * 128 + wq * 32 >= hp) break;                       // the whole warp is past the halo
+                    const int hpix = m * 128 + wq * 32 + lane;                // halo pixel of this thread = accumulator row
+                    const int hy = hpix / HWX, hx = hpix - hy * HWX;
+                    const int gx = tc.x0 - PAD + hx, gy = tc.y0 - PAD + hy;
+                    const bool inside = hpix < hp && gx >= 0 && gx < img_w && gy >= 0 && gy < img_h;
+                    const uint32_t t_row = t_lane + (uint32_t)gs * g1_stride + (uint32_t)(m * 64);
+                    const uint32_t line = st + (uint32_t)((hy * PITCH + hx) * 128);
+                    // 4 groups of 16 columns, software-pipelined: the TMEM load of group q+1 is in flight while group q is
+                    // evaluated, and a group's 16 bias values are fetched BEFORE its wait (the volatile tcgen05 statements pin
+                    // whatever follows them, so a bias load placed after the wait would expose its latency once per group)
+                    const float4* bq = reinterpret_cast<const float4*>(s_bias + 256 + j * 64);
+                    const uint32_t swz = (uint32_t)((hy * PITCH + hx) & 7);
+                    uint32_t va[16], vb[16];
+                    tmem_ld16(t_row, va);
+                    #pragma unroll
+                    for (int q16 = 0; q16 < 4; ++q16) {
+                        float4 hb[4];
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) hb[i] = bq[q16 * 4 + i];
+                        tmem_ld_wait();
+                        uint32_t (&v)[16] = (q16 & 1) ? vb : va;
+                        if (q16 < 3) tmem_ld16(t_row + (uint32_t)((q16 + 1) * 16), (q16 & 1) ? va : vb);
+                        if (inside) {
+                            uint32_t o[8];
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                o[2 * i] = silu2_bf16(pack64(v[4 * i + 0], v[4 * i + 1]), kHalf2, pack64(__float_as_uint(hb[i].x), __float_as_uint(hb[i].y)));
+                                o[2 * i + 1] = silu2_bf16(pack64(v[4 * i + 2], v[4 * i + 3]), kHalf2, pack64(__float_as_uint(hb[i].z), __float_as_uint(hb[i].w)));
+                            }
+                            #pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t addr = line + (((uint32_t)(q16 * 2 + h) ^ swz) << 4);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o[4 * h]), "r"(o[4 * h + 1]), "r"(o[4 * h + 2]), "r"(o[4 * h + 3]) : "memory");
+                            }
+                        } else if (hpix < hp) {                               // halo pixels outside the image: the depthwise conv's zero padding
+                            #pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t addr = line + (((uint32_t)(q16 * 2 + h) ^ swz) << 4);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
                             }
                         }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(g1_empty(gs));
-                    dwg_bar_sync(bar_id);                                         // the whole halo tile is written
                 }
-                // wait for the d buffer: mode 0 = its previous TMA store has read it; modes 1/2 = the MMAs that read it have retired
-                if constexpr (K == 3 && GEOM == 0) {
-                    // register-blocked item: the result is produced and stored block by block, so the buffer is needed up front
-                    if (p.mode == 0) {
-                        if (leader) { if (p.dw_groups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-                        dwg_bar_sync(bar_id);
-                    } else {
-                        mbar_wait_sleep(d_empty(ds), ((n >> 1) & 1u) ^ 1u);
-                    }
-                    const int cp = tg & 31, blk = tg >> 5, bx4 = (blk & 3) * 4, by4 = (blk >> 2) * 4;
-                    dw_block_k3<PITCH, TW>(st + (uint32_t)((by4 * PITCH + bx4) * 128), st + (uint32_t)p.off_dww + (uint32_t)(cp * 8),
-                                           st + (uint32_t)p.off_dwb + (uint32_t)(cp * 8), d_base + (uint32_t)((by4 * TW + bx4) * 128), cp, bx4 & 7);
-                } else {
-                    unsigned long long acc[8][2];
-                    {
-                        uint32_t eb[8];
-                        #pragma unroll
-                        for (int i = 0; i < 8; ++i) eb[i] = st + item_off + tbl[i] + (uint32_t)(i * 128);
-                        dw_accumulate<K, PITCH>(eb, st + (uint32_t)p.off_dww + (uint32_t)(q * 16), acc);
-                    }
-                    // the halo tile has been consumed (every load fed an FMA above); the stage may be refilled
-                    if (p.mode == 0) {
-                        if (leader) { if (p.dw_groups == 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-                        dwg_bar_sync(bar_id);
-                    } else {
-                        mbar_wait_sleep(d_empty(ds), ((n >> 1) & 1u) ^ 1u);
-                    }
-                    if (active) dw_store(d_base + d_off, st + (uint32_t)p.off_dwb + (uint32_t)(q * 16), tbl, acc);
-                }
-                fence_proxy_async_smem();
-                if (p.mode == 0) {
-                    dwg_bar_sync(bar_id);
-                    if (leader) { tma_store_4d(&tm_y, d_base, j * 64, tc.x0, tc.y0, tc.img); tma_store_commit(); }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(e_empty(s_cur));
-                } else {
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(d_full(ds)); mbar_arrive(e_empty(s_cur)); }
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(g1_empty(gs)); mbar_arrive(e_full(s)); }
+                if (++s == e_stages) { s = 0; ph ^= 1u; }
+                if (++gs == g1_stages) { gs = 0; gph ^= 1u; }
             }
         }
-        if (p.mode == 0 && leader) tma_store_wait_read<0>();
+    } else if (warp == kG1Warp) {
+        // ================= mode 2: issuer of the pw1 GEMMs (one elected thread).  It runs g1_stages chunks ahead of the pw1
+        // epilogue, also across tile boundaries, and is throttled only by its accumulator stages and the x halo buffers (a buffer
+        // is released by the last pw1 MMA of its tile) -- never by the depthwise / pw2 chain.
+        if (p.mode == 2 && elect_one()) {
+            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            mbar_wait_sleep(w_bar, 0u);
+            tc_fence_after();
+            const int kbt = p.kb1 + p.kb2;
+            const int tail1 = ((p.c_in1 - (p.kb1 - 1) * 64) + 15) >> 4;
+            const int tail2 = p.kb2 ? (((p.c_in2 - (p.kb2 - 1) * 64) + 15) >> 4) : 4;
+            int xb = 0; uint32_t xph = 0;
+            int gs = 0; uint32_t gph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += grid) {
+                mbar_wait_sleep(x_full(xb), xph);
+                tc_fence_after();
+                const uint32_t sx_cur = s_x + (uint32_t)(xb * p.x_buf_bytes);
+                for (int j = 0; j < p.n_chunks; ++j) {
+                    mbar_wait_sleep(g1_empty(gs), gph ^ 1u);
+                    tc_fence_after();
+                    for (int m = 0; m < p.mt; ++m) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(p.g1_base + gs * p.g1_stride + m * 64);
+                        for (int kb = 0; kb < kbt; ++kb) {
+                            const uint32_t a16 = ((sx_cur + (uint32_t)(kb * p.x_kb_stride + m * kDTile)) & 0x3FFFFu) >> 4;
+                            const uint32_t b16 = ((s_w1 + (uint32_t)((j * kbt + kb) * p.w1_tile_bytes)) & 0x3FFFFu) >> 4;
+                            const int ks = (kb == p.kb1 - 1) ? tail1 : ((kb == kbt - 1) ? tail2 : 4);
+                            for (int k = 0; k < ks; ++k)
+                                umma_bf16(d_tmem, hi | (uint64_t)(a16 + 2 * k), hi | (uint64_t)(b16 + 2 * k), idesc1, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(g1_full(gs));
+                    if (++gs == p.g1_stages) { gs = 0; gph ^= 1u; }
+                }
+                umma_commit(x_empty(xb));
+                if (++xb == p.x_bufs) { xb = 0; xph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= depthwise warps: the items of all chunks, in order, dealt round-robin =================
+        const int first = kFirstCw + (p.mode == 2 ? kPWarps : 0);
+        const int n_dw = kFirstCw + kCwCount - first;
+        const int d_bufs = p.d_bufs;
+        const int my_units = (int)blockIdx.x < p.units ? (p.units - 1 - (int)blockIdx.x) / grid + 1 : 0;
+        const int n_total = my_units * p.cpu;
+        const int e_stages = p.e_stages;
+        const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+        const uint32_t w_lane = (uint32_t)p.off_dww + (uint32_t)(lane * 8), b_lane = (uint32_t)p.off_dwb + (uint32_t)(lane * 8);
+        int n = 0, i = warp - first;
+        int s = 0; uint32_t ph = 0;
+        int ds = 0; uint32_t dph = 0;
+        for (;;) {
+            while (i >= kItems) {
+                i -= kItems; ++n;
+                if (++s == e_stages) { s = 0; ph ^= 1u; }
+                if (++ds == d_bufs) { ds = 0; dph ^= 1u; }
+            }
+            if (n >= n_total) break;
+            const uint32_t st = s_e0 + (uint32_t)s * stage_bytes;
+            const uint32_t d_base = s_d0 + (uint32_t)ds * kDTile;
+            mbar_wait_sleep(e_full(s), ph);                                   // halo tile + depthwise weights of chunk n
+            mbar_wait_sleep(d_empty(ds), dph ^ 1u);                           // the readers of the buffer's previous tile are done
+            if constexpr (kBlock) {
+                const int bx4 = (i & 3) * 4, by4 = (i >> 2) * 4;
+                dw_block_k3<PITCH, TW>(st + (uint32_t)((by4 * PITCH + bx4) * 128), st + w_lane, st + b_lane,
+                                       d_base + (uint32_t)((by4 * TW + bx4) * 128), lane, bx4 & 7);
+            } else {
+                const int rb = i / kStripsX, x0 = (i - rb * kStripsX) * 8, oy0 = rb * NR;
+                const uint32_t e_item = st + (uint32_t)((oy0 * PITCH + x0) * 128), d_item = d_base + (uint32_t)((oy0 * TW + x0) * 128);
+                if (TH % NR != 0 && oy0 + NR > TH) dw_rows<K, PITCH, TW, 1>(e_item, st + w_lane, st + b_lane, d_item, lane);
+                else dw_rows<K, PITCH, TW, NR>(e_item, st + w_lane, st + b_lane, d_item, lane);
+            }
+            fence_proxy_async_smem();                                         // generic-proxy writes of d -> async proxy (UMMA / TMA store)
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(d_full(ds)); mbar_arrive(e_empty(s)); }
+            i += n_dw;
+        }
     }
 
     tc_fence_before();
@@ -655,10 +711,10 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     memset(&kp, 0, sizeof(kp));
     kp.mode = q->mode; kp.ksize = k; kp.geom = geom;
     kTW = geom ? 24 : 16; kTH = geom ? 5 : 8;
-    const int kPitchB = (geom ? 32 : 24) * 128;
+    const int kPitchB = halo_pitch(k, geom) * 128;
     kp.tiles_x = ceil_div(q->w, kTW); kp.tiles_y = ceil_div(q->h, kTH); kp.batch = q->batch;
     const long long total = (long long)kp.tiles_x * kp.tiles_y * q->batch;
-    if (total > 0x3fffffffLL) return fail(YMS_E_UNSUPPORTED, "ms: too many tiles");
+    if (total * ceil_div(q->e_ch, 64) > 0x3fffffffLL) return fail(YMS_E_UNSUPPORTED, "ms: too many tiles");
     kp.total_tiles = (int)total;
     kp.mg_tiles_x = fast_div_magic(kp.tiles_x); kp.mg_tiles_y = fast_div_magic(kp.tiles_y);
     kp.e_ch = q->e_ch; kp.n_chunks = ceil_div(q->e_ch, 64);
@@ -683,7 +739,11 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     if (q->mode >= 1) {
         kp.acc_stride = kp.block_n <= 32 ? 32 : (kp.block_n <= 64 ? 64 : (kp.block_n <= 128 ? 128 : 256));
         cols = 2 * kp.acc_stride;
-        if (q->mode == 2) { kp.g1_base = cols; kp.g1_stride = kp.mt * 64; cols += 2 * kp.g1_stride; }
+        if (q->mode == 2) {
+            kp.g1_base = cols; kp.g1_stride = kp.mt * 64;
+            kp.g1_stages = cols + 3 * kp.g1_stride <= 512 ? 3 : 2;
+            cols += kp.g1_stages * kp.g1_stride;
+        }
         if (cols > 512) return fail(YMS_E_UNSUPPORTED, "ms: accumulators exceed the 512 TMEM columns");
         int pow2 = 32; while (pow2 < cols) pow2 <<= 1;
         kp.tmem_cols = pow2;
@@ -696,7 +756,7 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     int x_bytes = kp.x_bufs * kp.x_buf_bytes;
     const int w1_bytes = q->mode == 2 ? kp.n_chunks * kbt * kp.w1_tile_bytes : 0;
     const int out_bytes = q->mode >= 1 ? kDTile : 0;
-    const int tail_bytes = kp.bias_pad * 4 + (2 * kMaxE + 16) * 8 + 16;
+    const int tail_bytes = kp.bias_pad * 4 + 32 * 8 + 16;
     int fixed = x_bytes + 2 * kDTile + out_bytes + w1_bytes + tail_bytes + 1024 /* alignment slack */;
     const int w2_all = kp.n_chunks * kp.w2_tile_bytes;
     // mode 2: a second input-halo buffer lets the next tile's input land while this tile is processed; dropped when the
@@ -711,16 +771,26 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
         else stage += kp.w2_tile_bytes;
     }
     kp.stage_bytes = stage;
-    int stages = budget / stage;
-    if (stages > kMaxE) stages = kMaxE;
-    if (stages < 2) return fail(YMS_E_UNSUPPORTED, "ms: the layer does not fit in shared memory (use a lower fusion mode)");
+    // two e stages and two d buffers are the minimum; what is left goes, in this order, to a third d buffer (a depthwise warp that
+    // finishes its item of chunk n early moves on to chunk n+2 without waiting for the consumers of chunk n), a third e stage, ...
+    int stages = 2, dbufs = 2;
+    int rem = budget - 2 * stage;
+    if (rem < 0) return fail(YMS_E_UNSUPPORTED, "ms: the layer does not fit in shared memory (use a lower fusion mode)");
+    auto take = [&](int bytes) { if (rem >= bytes) { rem -= bytes; return true; } return false; };
+    if (take(kDTile)) dbufs = 3;
+    if (take(stage)) stages = 3;
+    if (dbufs == 3 && take(kDTile)) dbufs = 4;
+    if (stages == 3 && take(stage)) stages = 4;
     kp.e_stages = stages;
-    kp.dw_groups = 2;
+    kp.d_bufs = dbufs;
+    kp.n_items = items_per_chunk(k, geom);
+    kp.units = q->mode == 0 ? kp.total_tiles * kp.n_chunks : kp.total_tiles;
+    kp.cpu = q->mode == 0 ? 1 : kp.n_chunks;
     kp.stage_tx = (uint32_t)((q->mode != 2 ? hwx * hwy * 128 : 0) + k * k * 256 + 256 + ((q->mode >= 1 && !kp.w2_resident) ? kp.w2_tile_bytes : 0));
     kp.so_x = 0;
     kp.so_e = x_bytes;
     kp.so_d = kp.so_e + stages * stage;
-    kp.so_w2 = kp.so_d + 2 * kDTile;
+    kp.so_w2 = kp.so_d + dbufs * kDTile;
     kp.so_out = kp.so_w2 + (kp.w2_resident ? w2_all : 0);
     kp.so_w1 = kp.so_out + out_bytes;
     kp.so_bias = kp.so_w1 + w1_bytes;
@@ -731,8 +801,8 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     int lrc = layout(preferred);
     if (lrc == YMS_E_UNSUPPORTED) lrc = layout(1 - preferred);
     if (lrc) { delete pl; return lrc; }
-    pl->grid = kp.total_tiles < kNumSMs ? kp.total_tiles : kNumSMs;
-    pl->threads = 64 + 128 + kp.dw_groups * kGroupThreads;
+    pl->grid = kp.units < kNumSMs ? kp.units : kNumSMs;
+    pl->threads = kThreads;
 
     int rc = 0;
     const uint64_t W = (uint64_t)q->w, H = (uint64_t)q->h, N = (uint64_t)q->batch;
@@ -743,7 +813,7 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
         uint32_t es[4] = {1, 1, 1, 1};
         return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, what);
     };
-    if (q->mode != 2) rc = act_map(&pl->tm_e, q->e, q->e_ch, q->e_pixel_stride, hwx, 1, "ms e");
+    if (q->mode != 2) rc = act_map(&pl->tm_e, q->e, q->e_ch, q->e_pixel_stride, hwx, halo_pitch(k, kp.geom) == hwx ? hwy : 1, "ms e");
     else {
         rc = act_map(&pl->tm_x, q->x, q->c_in, q->x_pixel_stride, hwx, hwy, "ms x");
         if (!rc && q->c_in2) rc = act_map(&pl->tm_x2, q->x2, q->c_in2, q->x2_pixel_stride, hwx, hwy, "ms x2");
