@@ -18,6 +18,20 @@ constexpr int kStageOutBytes = 128 * 128;                             // one 128
 
 struct EpiTile { int n0, x0, y0, img; };
 
+__device__ __forceinline__ unsigned long long epi_pack(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void epi_unpack(unsigned long long v, uint32_t& lo, uint32_t& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long epi_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 struct EpiShared {
     const CUtensorMap* tm_y; const CUtensorMap* tm_res;
     uint32_t res_bar;          // mbarrier of this group for the residual TMA load
@@ -56,18 +70,34 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
             res_phase ^= 1u;
         }
         const uint32_t line = e.s_out + (uint32_t)e.row * 128u;
-        #pragma unroll 1
+        // Four groups of 16 columns, software-pipelined: the TMEM load of group q+1 is in flight while group q is evaluated, and a
+        // group's bias values are fetched BEFORE its wait (the volatile tcgen05 statements pin what follows them: a bias load
+        // after the wait exposes its shared-memory latency once per group).  bias / SiLU run as packed fp32 pairs (fma.rn.f32x2:
+        // the same two IEEE fmas as the scalar form, half the issue slots).
+        // (the up-add variant keeps one buffer: its partial-sum prefetch already holds 32 registers)
+        uint32_t va[16], vb[kUp ? 1 : 16];
+        if (!kUp) tmem_ld16(t_row + (uint32_t)cbase, va);
+        #pragma unroll
         for (int q16 = 0; q16 < 4; ++q16) {
             const int c0 = cbase + q16 * 16;
             if (c0 >= e.block_n) break;
-            uint32_t v[16];
+            float4 b4[4];
+            {
+                const float4* bq = reinterpret_cast<const float4*>(e.s_bias + tl.n0 + c0);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) b4[j] = bq[j];               // act: 0.5 * bias
+            }
             if (kUp && q16 < 3 && c0 + 16 < e.block_n) {
                 const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + c0 + 16);
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) un[j] = __ldg(uq + j);
             }
-            tmem_ld16(t_row + (uint32_t)c0, v);
+            if (kUp) tmem_ld16(t_row + (uint32_t)c0, va);
             tmem_ld_wait();
+            uint32_t (&v)[16] = (!kUp && (q16 & 1)) ? *reinterpret_cast<uint32_t (*)[16]>(&vb[0]) : va;
+            if constexpr (!kUp) {
+                if (q16 < 3 && c0 + 16 < e.block_n) tmem_ld16(t_row + (uint32_t)(c0 + 16), (q16 & 1) ? va : *reinterpret_cast<uint32_t (*)[16]>(&vb[0]));
+            }
             if (kUp) {
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -79,24 +109,29 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                 }
             }
             float f[16];
-            const float4* bq = reinterpret_cast<const float4*>(e.s_bias + tl.n0 + c0);
             if (e.act) {
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 hb = bq[j];                 // 0.5 * bias
-                    f[4 * j + 0] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 0]), 0.5f, hb.x));
-                    f[4 * j + 1] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, hb.y));
-                    f[4 * j + 2] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, hb.z));
-                    f[4 * j + 3] = silu_from_half(fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, hb.w));
+                for (int j = 0; j < 8; ++j) {
+                    const float4 hb = b4[j >> 1];
+                    const unsigned long long h = epi_fma2(epi_pack(v[2 * j], v[2 * j + 1]), 0x3f0000003f000000ull,
+                                                          (j & 1) ? epi_pack(__float_as_uint(hb.z), __float_as_uint(hb.w))
+                                                                  : epi_pack(__float_as_uint(hb.x), __float_as_uint(hb.y)));
+                    uint32_t h0, h1;
+                    epi_unpack(h, h0, h1);
+                    float t0, t1;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(__uint_as_float(h0)));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(__uint_as_float(h1)));
+                    uint32_t r0, r1;
+                    epi_unpack(epi_fma2(h, epi_pack(__float_as_uint(t0), __float_as_uint(t1)), h), r0, r1);
+                    f[2 * j] = __uint_as_float(r0); f[2 * j + 1] = __uint_as_float(r1);
                 }
             } else {
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 b4 = bq[j];
-                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4[j].x;
+                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
+                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
+                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
                 }
             }
             #pragma unroll

@@ -363,6 +363,59 @@ __device__ __forceinline__ bool apply_kept_smem(const float4* kb, int from, int 
     return removed;
 }
 
+// Division-free part of the finite predicate: straight-line code (no branch: four of these interleave), the decision in two
+// flags.  `unc` marks the pairs that need the exactly rounded quotient (the 4e-6-wide band around the threshold, or values
+// outside the magnitude guards).
+struct PairFlags { bool hit, unc; float inter, uni; };
+__device__ __forceinline__ PairFlags pair_flags(const float4& bi, const float4& bj, float aj, float thr_f) {
+    PairFlags r;
+    const float ai = box_area(bi);
+    const float w = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.0f);
+    const float h = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.0f);
+    r.inter = __fmul_rn(w, h);
+    r.uni = __fsub_rn(__fadd_rn(ai, aj), r.inter);
+    const float t = __fmul_rn(thr_f, r.uni);
+    const bool guard = r.inter > 1e-15f && r.uni > 1e-15f && r.uni < 1e15f;
+    r.hit = guard && r.inter >= __fmul_rn(t, 1.000002f);
+    const bool sure_f = (guard && r.inter <= __fmul_rn(t, 0.999998f)) || !(r.inter > 0.0f);
+    r.unc = !(r.hit || sure_f);
+    return r;
+}
+
+// Same, with the kept boxes given as positions into the CTA's (immutable) sorted box array: kp[from, to) -> sb[kp[g]].
+template <bool kFinite>
+__device__ __forceinline__ bool apply_kept_pos(const float4* sb, const unsigned short* kp, int from, int to, const float4& bj, float aj,
+                                               bool removed, float thr_f) {
+    int g = from;
+    for (; g + 4 <= to; g += 4) {
+        if (__all_sync(0xffffffffu, removed)) return true;
+        const int p0 = kp[g], p1 = kp[g + 1], p2 = kp[g + 2], p3 = kp[g + 3];
+        const float4 b0 = sb[p0], b1 = sb[p1], b2 = sb[p2], b3 = sb[p3];
+        if (kFinite) {
+            const PairFlags f0 = pair_flags(b0, bj, aj, thr_f), f1 = pair_flags(b1, bj, aj, thr_f);
+            const PairFlags f2 = pair_flags(b2, bj, aj, thr_f), f3 = pair_flags(b3, bj, aj, thr_f);
+            removed = removed || f0.hit || f1.hit || f2.hit || f3.hit;
+            if (__any_sync(0xffffffffu, f0.unc || f1.unc || f2.unc || f3.unc)) {       // rare: some pair sits in the threshold band
+                if (f0.unc && __fdiv_rn(f0.inter, f0.uni) > thr_f) removed = true;
+                if (f1.unc && __fdiv_rn(f1.inter, f1.uni) > thr_f) removed = true;
+                if (f2.unc && __fdiv_rn(f2.inter, f2.uni) > thr_f) removed = true;
+                if (f3.unc && __fdiv_rn(f3.inter, f3.uni) > thr_f) removed = true;
+            }
+        } else {
+            const bool h0 = pair_hit<false>(b0, box_area(b0), bj, aj, thr_f);
+            const bool h1 = pair_hit<false>(b1, box_area(b1), bj, aj, thr_f);
+            const bool h2 = pair_hit<false>(b2, box_area(b2), bj, aj, thr_f);
+            const bool h3 = pair_hit<false>(b3, box_area(b3), bj, aj, thr_f);
+            removed = removed || h0 || h1 || h2 || h3;
+        }
+    }
+    for (; g < to; ++g) {
+        const float4 b0 = sb[kp[g]];
+        removed = removed || pair_hit<kFinite>(b0, box_area(b0), bj, aj, thr_f);
+    }
+    return removed;
+}
+
 struct NmsArgs {
     const float4* boxes; const float* scores; const int32_t* labels; const int32_t* n_valid;
     int n, num_classes, groups; float conf; float thr_f;
@@ -376,6 +429,7 @@ struct NmsArgs {
     int mask_tile_limit;           // bitmask path only when the largest class of the CTA has at most this many 32-box blocks
     int poll_ns;                   // back-off unit of the pipelined greedy path's progress polling (library option nms_poll_ns, default 256 ns per chunk ahead)
     int seg_sort;                  // 1 (default): counting scatter by class + per-segment sorts; 0 (library option nms_sort_bitonic): one bitonic sort of all keys
+    int region_bytes;              // shared-memory bytes of the key | box | kept-position (or mask tile) region in front of the class tables
 };
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
@@ -384,7 +438,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     const int G = a.groups;
     const int b = blockIdx.x / G, g = blockIdx.x % G;
     const int nc = a.num_classes;
-    int* cls_start = reinterpret_cast<int*>(smem_raw + kKeyRegionBytes);            // [nc + 1] (a CTA may own up to nc classes)
+    int* cls_start = reinterpret_cast<int*>(smem_raw + a.region_bytes);             // [nc + 1] (a CTA may own up to nc classes)
     int* cls_count = cls_start + (nc + 1);                                          // [nc + 1] kept counts, then offsets
     int* chunk_base = cls_count + (nc + 1);                                         // [nc + 1]; first: the image's class histogram
     volatile unsigned* state = reinterpret_cast<volatile unsigned*>(chunk_base + (nc + 1));   // [nc + 1] (done chunks<<16 | kept) / next row block
@@ -449,11 +503,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     const int m = s_count;
     int n_pad = 32;
     while (n_pad < m) n_pad <<= 1;
-    const bool fast = (m <= kFastCap);
+    // fast path: keys, boxes and the kept-position list (2 bytes per candidate) of the CTA fit the region
+    const bool fast = (m <= kFastCap) && ((size_t)n_pad * 8 + (size_t)m * 18 + 64 <= (size_t)a.region_bytes);
     const bool in_smem = (n_pad <= kSortTile);
     float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)n_pad * 8);        // fast path only: boxes right after the keys
     unsigned* smask = reinterpret_cast<unsigned*>(sbox + m);                        // bitmask path: tiles after the boxes
-    const int mask_tile_cap = fast ? (int)((kKeyRegionBytes - (size_t)n_pad * 8 - (size_t)m * 16) / 128) : 0;
+    const int mask_tile_cap = fast ? (int)(((size_t)a.region_bytes - (size_t)n_pad * 8 - (size_t)m * 16) / 128) : 0;
+    unsigned short* kpos = reinterpret_cast<unsigned short*>(sbox + m);             // pipelined fast path: kept positions, class by class
     unsigned long long* keys = in_smem ? skeys : (a.ws_keys + (size_t)blockIdx.x * a.n_pad_full);
     __syncthreads();
     if (tid == 0) s_count = 0;
@@ -511,15 +567,66 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     if (seg_sort) {
         // segments of more than kWarpSortMax keys: the whole CTA, one after the other; the rest: one warp per segment, all
         // in parallel and without block-wide barriers (bench workload: 54 -> ~15 kcycles for ~2100 keys in ~20 classes)
-        for (int c = 0; c < ncl; ++c) {
-            const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
-            if (len > kWarpSortMax) segment_sort<true>(skeys + s0, len, tid, kNmsThreads);
+        // Larger segments: runs of kWarpSortMax keys are sorted by warps in registers like the small segments, then merged
+        // pairwise, level by level, by RANK -- every key finds its place in the merged run with one binary search over the
+        // sibling run (keys are unique), all keys of all large segments in parallel, ping-pong between the key array and the
+        // (still unused) box region.  Measured: a 2962-key class 110 -> ~15 kcycles, the bench workload's 300..750-key classes
+        // ~20 -> ~8 kcycles each against the block-wide shared-memory bitonic network this replaces (one barrier per step).
+        unsigned long long* scratch = skeys + n_pad;
+        const bool can_merge = (size_t)n_pad * 8 + (size_t)m * 8 <= (size_t)a.region_bytes;
+        if (!can_merge) {
+            for (int c = 0; c < ncl; ++c) {
+                const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
+                if (len > kWarpSortMax) segment_sort<true>(skeys + s0, len, tid, kNmsThreads);
+            }
         }
         for (int c = warp; c < ncl; c += kNmsWarps) {
             const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
             if (len <= kWarpSortMax) warp_sort_segment(skeys + s0, len, lane);
         }
+        int maxlen = 0;
+        if (can_merge) {
+            int item = 0;
+            for (int c = 0; c < ncl; ++c) {                    // every warp walks the (short) class table: uniform, no atomics
+                const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
+                if (len <= kWarpSortMax) continue;
+                maxlen = max(maxlen, len);
+                for (int r0 = 0; r0 < len; r0 += kWarpSortMax, ++item)
+                    if ((item & (kNmsWarps - 1)) == warp) warp_sort_regs<kWarpSortMax / 32>(skeys + s0 + r0, min(kWarpSortMax, len - r0), lane);
+            }
+        }
         __syncthreads();
+        if (maxlen) {
+            bool in_scratch = false;
+            for (int w = kWarpSortMax; w < maxlen; w <<= 1) {
+                const unsigned long long* src = in_scratch ? scratch : skeys;
+                unsigned long long* dst = in_scratch ? skeys : scratch;
+                for (int c = 0; c < ncl; ++c) {
+                    const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
+                    if (len <= kWarpSortMax) continue;
+                    for (int e = tid; e < len; e += kNmsThreads) {
+                        const int l0 = e & ~(2 * w - 1);                       // first key of the pair of runs
+                        const int r0 = min(l0 + w, len), r1 = min(l0 + 2 * w, len);
+                        const unsigned long long key = src[s0 + e];
+                        const bool left = e < r0;
+                        int lo = left ? r0 : l0, hi = left ? r1 : r0;          // sibling run [lo, hi): count its keys below mine
+                        const int base = lo;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (src[s0 + mid] < key) lo = mid + 1; else hi = mid; }
+                        dst[s0 + l0 + (e - (left ? l0 : r0)) + (lo - base)] = key;
+                    }
+                }
+                __syncthreads();
+                in_scratch = !in_scratch;
+            }
+            if (in_scratch) {
+                for (int c = 0; c < ncl; ++c) {
+                    const int s0 = cls_start[c], len = cls_start[c + 1] - s0;
+                    if (len <= kWarpSortMax) continue;
+                    for (int e = tid; e < len; e += kNmsThreads) skeys[s0 + e] = scratch[s0 + e];
+                }
+                __syncthreads();
+            }
+        }
     } else if (in_smem) {
         for (int k = 2; k <= n_pad; k <<= 1) bitonic_tile_steps(skeys, n_pad, 0, k, k >> 1);
     } else {
@@ -699,6 +806,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                 const float aj = box_area(bj);
                 bool removed = !have;
                 int applied = 0, kept = 0;
+#ifdef YMS_PROF
+                long long* tr = (a.prof && blockIdx.x == 0 && lo == 0 && j < 128) ? a.prof + 16 * gridDim.x + 4 * j : nullptr;
+                if (tr && lane == 0) tr[0] = clock64();
+#endif
                 for (;;) {
                     unsigned st = 0;
                     if (lane == 0) st = state[c];
@@ -715,6 +826,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                     // saturated the issue ports and starved the one warp per class that is on the critical chain.
                     __nanosleep(ahead <= 1 ? 32u : (unsigned)min(a.poll_ns * ahead, 4096));
                 }
+#ifdef YMS_PROF
+                if (tr && lane == 0) { tr[1] = clock64(); tr[3] = kept; }
+#endif
                 const unsigned surv = resolve_chunk(bj, aj, removed, a.thr_f, lane);
                 __syncwarp();                                  // every lane has read its chunk box before the in-place compaction
                 if (!removed) {
@@ -725,9 +839,119 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) state[c] = ((unsigned)(j + 1) << 16) | (unsigned)(kept + __popc(surv));
+#ifdef YMS_PROF
+                if (tr && lane == 0) tr[2] = clock64();
+#endif
             }
         };
-        if (nonfinite || !fast) run_chunks(std::false_type{}); else run_chunks(std::true_type{});
+        // Fast path (keys, boxes and kept positions in shared memory).  The chain of a class is sequential -- chunk j can only be
+        // resolved once chunk j-1 is final -- and, measured (profiling build, per-chunk time stamps): one chain step cost 4.6 kcycles
+        // on a 93-chunk class (MS-Block leg: 430 of the CTA's 790 kcycles) and 12 kcycles on the bench workload's 12-chunk classes,
+        // of which only ~1 kcycle is inherent.  Everything that does not depend on the predecessor's RESULT is therefore done
+        // while waiting: H (bit i of lane l: box i of chunk j-1 would suppress my box l -- against every box of the predecessor
+        // that is still alive, not just its final survivors) and M (row i: which later boxes of my own chunk box i would
+        // suppress).  Once the predecessor publishes its survivor mask S, the step is  removed |= (H & S) != 0;  a 32-step sweep
+        // over M on bit masks;  publish.  Every chunk keeps its current removed mask in a word of shared memory (cw[j]; final: ~S),
+        // so H only counts rows that can still survive; both masks are built right after the chunk's first pass over the kept list.  Sorted boxes and keys stay
+        // immutable (the kept list holds 16-bit POSITIONS), so a chunk may read its predecessor's boxes at any time.
+        auto run_chunks_fast = [&](auto finite_tag) {
+            constexpr bool kFinite = decltype(finite_tag)::value;
+            for (int ci = warp; ci < total_chunks; ci += kNmsWarps) {
+                int lo = 0, hi = ncl - 1;                      // largest c with chunk_base[c] <= ci
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= ci) lo = mid; else hi = mid - 1; }
+                const int c = perm[lo], j = ci - chunk_base[lo];
+                const int s0 = cls_start[c], s1 = cls_start[c + 1];
+                const int pos = s0 + 32 * j + lane;
+                const bool have = pos < s1;
+                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (have) bj = sbox[pos];
+                const float aj = box_area(bj);
+                bool removed = !have;
+                int applied = 0, kept = 0;
+                unsigned H = 0u, Mrow = 0u, s_pred = 0u;
+                bool pre = false;                              // H and M have been computed
+                volatile unsigned* cw = remw_all + (s0 >> 5) + c;             // removed masks of the class's chunks (zeroed above)
+                unsigned published = 0u;
+#ifdef YMS_PROF
+                long long* tr = (a.prof && blockIdx.x == 0 && lo == 0 && j < 128) ? a.prof + 16 * gridDim.x + 4 * j : nullptr;
+                if (tr && lane == 0) tr[0] = clock64();
+#endif
+                for (;;) {
+                    unsigned st = 0;
+                    if (lane == 0) st = state[c];
+                    st = __shfl_sync(0xffffffffu, st, 0);
+                    __threadfence_block();
+                    kept = (int)(st & 0xffffu);
+                    const int ahead = j - (int)(st >> 16);     // chunks of this class that are not final yet
+                    int lim = kept;
+                    if (ahead == 0 && pre) {                   // the last popc(S) kept boxes are the predecessor's survivors: H covers them
+                        s_pred = ~cw[j - 1];
+                        lim = kept - __popc(s_pred);
+                    }
+                    removed = apply_kept_pos<kFinite>(sbox, kpos + s0, applied, lim, bj, aj, removed, a.thr_f);
+                    applied = lim;
+                    if (ahead == 0) break;
+                    const unsigned rem_now = __ballot_sync(0xffffffffu, removed);
+                    if (rem_now != published) { published = rem_now; if (lane == 0) cw[j] = rem_now; }
+                    if (!pre) {
+                        // right after the first pass over the kept list: only the boxes of this chunk that are still alive need
+                        // rows / columns.  H is built TRANSPOSED -- lane i holds box i of the predecessor, the loop runs over my
+                        // alive boxes l, the ballot over the predecessor's lanes IS H of lane l -- so both masks cost one pair
+                        // test per alive box of this chunk, not per box of the predecessor.
+                        pre = true;
+                        const float4 bp = sbox[s0 + 32 * (j - 1) + lane];      // the predecessor is a full chunk
+                        const float ap = box_area(bp);
+                        const bool p_alive = !((cw[j - 1] >> lane) & 1u);      // predecessor's boxes that may still survive (superset of S)
+                        const unsigned alive0 = ~rem_now;
+                        const float4* ob = sbox + s0 + 32 * j;
+                        unsigned todo = alive0;
+                        while (todo) {                                         // warp-uniform
+                            const int i = __ffs(todo) - 1;
+                            todo &= todo - 1u;
+                            const float4 bi = ob[i];
+                            const float ai = box_area(bi);
+                            const unsigned hcol = __ballot_sync(0xffffffffu, p_alive && pair_hit<kFinite>(bp, ap, bi, ai, a.thr_f));
+                            const unsigned row = __ballot_sync(0xffffffffu, (lane > i) && pair_hit<kFinite>(bi, ai, bj, aj, a.thr_f));
+                            if (lane == i) { H = hcol; Mrow = row; }
+                        }
+                        continue;                                              // the chain has moved on meanwhile: poll again at once
+                    }
+                    // Back-off by distance; the chunk next in line spins (one warp per class: cheap, and its wake-up latency is
+                    // chain latency)
+                    if (ahead > 1) __nanosleep((unsigned)min(a.poll_ns * ahead, 4096));
+                }
+#ifdef YMS_PROF
+                if (tr && lane == 0) { tr[1] = clock64(); tr[3] = kept; }
+#endif
+                unsigned alive;
+                if (pre) {
+                    removed = removed || ((H & s_pred) != 0u);
+                    alive = ~__ballot_sync(0xffffffffu, removed);
+                    #pragma unroll
+                    for (int b8 = 0; b8 < 4; ++b8) {
+                        if (((alive >> (8 * b8)) & 0xffu) == 0u) continue;     // warp-uniform
+                        unsigned r[8];
+                        #pragma unroll
+                        for (int q = 0; q < 8; ++q) r[q] = __shfl_sync(0xffffffffu, Mrow, 8 * b8 + q);
+                        #pragma unroll
+                        for (int q = 0; q < 8; ++q) if ((alive >> (8 * b8 + q)) & 1u) alive &= ~r[q];
+                    }
+                } else {
+                    alive = resolve_chunk(bj, aj, removed, a.thr_f, lane);
+                }
+                if ((alive >> lane) & 1u) kpos[s0 + kept + __popc(alive & ((1u << lane) - 1u))] = (unsigned short)pos;
+                if (lane == 0) cw[j] = ~alive;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) state[c] = ((unsigned)(j + 1) << 16) | (unsigned)(kept + __popc(alive));
+#ifdef YMS_PROF
+                if (tr && lane == 0) tr[2] = clock64();
+#endif
+            }
+        };
+        if (!fast) run_chunks(std::false_type{});
+        else if (nonfinite) run_chunks_fast(std::false_type{});
+        else run_chunks_fast(std::true_type{});
         __syncthreads();
         for (int c = tid; c < ncl; c += kNmsThreads) cls_count[c] = (int)(state[c] & 0xffffu);
     }
@@ -753,7 +977,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     int32_t* out = (G == 1) ? (a.keep + (size_t)b * n) : (a.ws_stage + (size_t)blockIdx.x * n);
     for (int c = warp; c < ncl; c += kNmsWarps) {
         const int off = cls_count[c], cnt = cls_count[c + 1] - off, s0 = cls_start[c];
-        for (int r = lane; r < cnt; r += 32) out[off + r] = (int32_t)(keys[s0 + r] & kIdxMask);
+        if (fast && !use_mask) for (int r = lane; r < cnt; r += 32) out[off + r] = (int32_t)(keys[kpos[s0 + r]] & kIdxMask);
+        else for (int r = lane; r < cnt; r += 32) out[off + r] = (int32_t)(keys[s0 + r] & kIdxMask);
     }
     if (G == 1) {
         for (int i = my_total + tid; i < n; i += kNmsThreads) out[i] = -1;
@@ -882,8 +1107,14 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
         if (e != cudaSuccess) return fail((int)e, "nms: ticket memset failed");
     }
-    const size_t smem = kKeyRegionBytes + (size_t)(num_classes + 2) * 4 * 4 + (size_t)(kFastCap / 32 + num_classes + 4) * 4 + 16;   // class tables + removed words
-    if (smem > 232448) return fail(YMS_E_UNSUPPORTED, "nms: %d classes need %zu bytes of shared memory (limit 232448)", num_classes, smem);
+    const size_t tables = (size_t)(num_classes + 2) * 4 * 4 + (size_t)(kFastCap / 32 + num_classes + 4) * 4 + 16;   // class tables + removed words
+    if (kKeyRegionBytes + tables > 232448) return fail(YMS_E_UNSUPPORTED, "nms: %d classes need %zu bytes of shared memory (limit 232448)", num_classes, kKeyRegionBytes + tables);
+    // keys | boxes | kept positions: 192 KB hold the sort tile and 8192 candidates without the position list; what the class tables
+    // leave of another 16 KB lets a full 8192-candidate CTA stay on the fast path
+    size_t region = (232448 - tables) & ~(size_t)15;
+    if (region > kKeyRegionBytes + (size_t)kFastCap * 2 + 64) region = kKeyRegionBytes + (size_t)kFastCap * 2 + 64;
+    a.region_bytes = (int)region;
+    const size_t smem = region + tables;
     static std::atomic<size_t> attr_bytes[64];           // per device: cudaFuncSetAttribute is a per-device setting
     int dev_id = 0;
     cudaGetDevice(&dev_id);
