@@ -573,7 +573,7 @@ def gpu_library_baseline(ctx, version, B, HW, steps=5):
             "cudnn": torch.backends.cudnn.version(), "kind": "port"}
 
 
-def verify(ctx, model, x, out):
+def verify(ctx, model, x, out, version="s", block="c2f"):
     """Post-run self-check of what was timed (rank 0): (1) the keep lists of three images of the batch against the C oracle of the
     reference's post-process run on OUR decoded predictions -- bit-exact; (2) the raw head logits of image 0 against the CPU
     oracle under the same numeric contract (bf16 storage, fp32 accumulate) -- rel-L2 under the random-weight bf16 gate of the
@@ -596,14 +596,15 @@ def verify(ctx, model, x, out):
             ok &= bool(count[i] == want.size and np.array_equal(keep[i, :count[i]].astype(np.int64), want))
             res["images_checked"].append(i)
         res["nms_bit_exact"] = ok
-        sd = W.calibrated_state_dict("s", seed=1)
+        sd = W.calibrated_state_dict(version, seed=1, block=block)
         raws = model.forward_raw(x)
         with torch.no_grad():
             emu = O.forward_bf16_contract(sd, x[:1].cpu(), return_parts=True)
         rel = max(float((a[:1, ..., :64 + nc].permute(0, 3, 1, 2).float().cpu() - b).norm() / b.norm()) for a, b in zip(raws, emu["raw"]))
+        gate = 0.15 if block == "c2f" else 0.3      # tests/test_gpu_model.py::test_batch32_at_the_benchmarked_shape (ms: parity unpinned, 1.5 x its bf16 floor)
         res["forward_rel_l2_image0"] = round(rel, 4)
-        res["forward_gate"] = 0.15
-        res["ok"] = bool(ok and rel < 0.15)
+        res["forward_gate"] = gate
+        res["ok"] = bool(ok and rel < gate)
     except Exception as e:  # noqa: BLE001
         res["ok"] = False
         res["error"] = repr(e)[:200]
@@ -694,7 +695,7 @@ def run_native(args):
         breakdown = {"step_ms": round(ms / args.steps, 4), "conv_ms": r["ms"], "stem_ms": round(stem_ms, 3), "nms_ms": round(nms_ms, 3),
                      "decode": "fused into the epilogue of the head's final 1x1 convs (inside conv_ms)" if fused else "head_decode_v2_kernel"}
         if world == 1:
-            verified = verify(ctx, model, x, model.detect(x, CONF, IOU))
+            verified = verify(ctx, model, x, model.detect(x, CONF, IOU), args.version, args.block)
     del out
     legs = {}
     if not args.no_configs:

@@ -383,14 +383,14 @@ __device__ __forceinline__ PairFlags pair_flags(const float4& bi, const float4& 
 }
 
 // Same, with the kept boxes given as positions into the CTA's (immutable) sorted box array: kp[from, to) -> sb[kp[g]].
-template <bool kFinite>
-__device__ __forceinline__ bool apply_kept_pos(const float4* sb, const unsigned short* kp, int from, int to, const float4& bj, float aj,
+template <bool kFinite, typename BoxAt>
+__device__ __forceinline__ bool apply_kept_pos(BoxAt sb, const unsigned short* kp, int from, int to, const float4& bj, float aj,
                                                bool removed, float thr_f) {
     int g = from;
     for (; g + 4 <= to; g += 4) {
         if (__all_sync(0xffffffffu, removed)) return true;
         const int p0 = kp[g], p1 = kp[g + 1], p2 = kp[g + 2], p3 = kp[g + 3];
-        const float4 b0 = sb[p0], b1 = sb[p1], b2 = sb[p2], b3 = sb[p3];
+        const float4 b0 = sb(p0), b1 = sb(p1), b2 = sb(p2), b3 = sb(p3);
         if (kFinite) {
             const PairFlags f0 = pair_flags(b0, bj, aj, thr_f), f1 = pair_flags(b1, bj, aj, thr_f);
             const PairFlags f2 = pair_flags(b2, bj, aj, thr_f), f3 = pair_flags(b3, bj, aj, thr_f);
@@ -410,7 +410,7 @@ __device__ __forceinline__ bool apply_kept_pos(const float4* sb, const unsigned 
         }
     }
     for (; g < to; ++g) {
-        const float4 b0 = sb[kp[g]];
+        const float4 b0 = sb(kp[g]);
         removed = removed || pair_hit<kFinite>(b0, box_area(b0), bj, aj, thr_f);
     }
     return removed;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     int* cls_count = cls_start + (nc + 1);                                          // [nc + 1] kept counts, then offsets
     int* chunk_base = cls_count + (nc + 1);                                         // [nc + 1]; first: the image's class histogram
     volatile unsigned* state = reinterpret_cast<volatile unsigned*>(chunk_base + (nc + 1));   // [nc + 1] (done chunks<<16 | kept) / next row block
-    unsigned* remw_all = const_cast<unsigned*>(reinterpret_cast<volatile unsigned*>(state + (nc + 1)));   // [kFastCap/32 + nc + 2] removed words
+    unsigned* remw_all = const_cast<unsigned*>(reinterpret_cast<volatile unsigned*>(state + (nc + 1)));   // [kSortTile/32 + nc + 2] removed words
     __shared__ int s_count, s_next, s_last, s_clo, s_chi;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -509,7 +509,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     float4* sbox = reinterpret_cast<float4*>(smem_raw + (size_t)n_pad * 8);        // fast path only: boxes right after the keys
     unsigned* smask = reinterpret_cast<unsigned*>(sbox + m);                        // bitmask path: tiles after the boxes
     const int mask_tile_cap = fast ? (int)(((size_t)a.region_bytes - (size_t)n_pad * 8 - (size_t)m * 16) / 128) : 0;
-    unsigned short* kpos = reinterpret_cast<unsigned short*>(sbox + m);             // pipelined fast path: kept positions, class by class
+    // kept positions (16 bit) of the pipelined path, class by class: after the boxes (fast) or, when only the keys fit shared
+    // memory ("mid": up to 16384 candidates, boxes gathered from the read-only input by index), right after the keys
+    const bool mid = !fast && in_smem && m <= 65535 && ((size_t)n_pad * 8 + (size_t)m * 2 + 64 <= (size_t)a.region_bytes);
+    unsigned short* kpos = fast ? reinterpret_cast<unsigned short*>(sbox + m) : reinterpret_cast<unsigned short*>(skeys + n_pad);
     unsigned long long* keys = in_smem ? skeys : (a.ws_keys + (size_t)blockIdx.x * a.n_pad_full);
     __syncthreads();
     if (tid == 0) s_count = 0;
@@ -690,6 +693,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         use_mask = (!nonfinite && mask_tile_cap >= 2 * wmax && mask_tile_cap >= 64 && wmax <= a.mask_tile_limit) ? 1 : 0;
         __syncthreads();
         if (tid == 0) s_last = 0;
+    } else if (mid) {
+        for (int i = tid; i < (m >> 5) + ncl + 2; i += kNmsThreads) remw_all[i] = 0u;   // removed masks of the pipelined path's chunks
     }
 
     if (use_mask) {
@@ -854,8 +859,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
         // over M on bit masks;  publish.  Every chunk keeps its current removed mask in a word of shared memory (cw[j]; final: ~S),
         // so H only counts rows that can still survive; both masks are built right after the chunk's first pass over the kept list.  Sorted boxes and keys stay
         // immutable (the kept list holds 16-bit POSITIONS), so a chunk may read its predecessor's boxes at any time.
-        auto run_chunks_fast = [&](auto finite_tag) {
+        auto run_chunks_fast = [&](auto finite_tag, auto smem_tag) {
             constexpr bool kFinite = decltype(finite_tag)::value;
+            constexpr bool kBoxSmem = decltype(smem_tag)::value;
+            auto bx = [&](int q) -> float4 { return kBoxSmem ? sbox[q] : __ldg(boxes + (int)(keys[q] & kIdxMask)); };
             for (int ci = warp; ci < total_chunks; ci += kNmsWarps) {
                 int lo = 0, hi = ncl - 1;                      // largest c with chunk_base[c] <= ci
                 while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (chunk_base[mid] <= ci) lo = mid; else hi = mid - 1; }
@@ -864,7 +871,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                 const int pos = s0 + 32 * j + lane;
                 const bool have = pos < s1;
                 float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (have) bj = sbox[pos];
+                if (have) bj = bx(pos);
                 const float aj = box_area(bj);
                 bool removed = !have;
                 int applied = 0, kept = 0;
@@ -888,7 +895,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                         s_pred = ~cw[j - 1];
                         lim = kept - __popc(s_pred);
                     }
-                    removed = apply_kept_pos<kFinite>(sbox, kpos + s0, applied, lim, bj, aj, removed, a.thr_f);
+                    removed = apply_kept_pos<kFinite>(bx, kpos + s0, applied, lim, bj, aj, removed, a.thr_f);
                     applied = lim;
                     if (ahead == 0) break;
                     const unsigned rem_now = __ballot_sync(0xffffffffu, removed);
@@ -899,16 +906,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
                         // alive boxes l, the ballot over the predecessor's lanes IS H of lane l -- so both masks cost one pair
                         // test per alive box of this chunk, not per box of the predecessor.
                         pre = true;
-                        const float4 bp = sbox[s0 + 32 * (j - 1) + lane];      // the predecessor is a full chunk
+                        const float4 bp = bx(s0 + 32 * (j - 1) + lane);        // the predecessor is a full chunk
                         const float ap = box_area(bp);
                         const bool p_alive = !((cw[j - 1] >> lane) & 1u);      // predecessor's boxes that may still survive (superset of S)
                         const unsigned alive0 = ~rem_now;
-                        const float4* ob = sbox + s0 + 32 * j;
                         unsigned todo = alive0;
                         while (todo) {                                         // warp-uniform
                             const int i = __ffs(todo) - 1;
                             todo &= todo - 1u;
-                            const float4 bi = ob[i];
+                            float4 bi;                                         // my box i, broadcast
+                            bi.x = __shfl_sync(0xffffffffu, bj.x, i); bi.y = __shfl_sync(0xffffffffu, bj.y, i);
+                            bi.z = __shfl_sync(0xffffffffu, bj.z, i); bi.w = __shfl_sync(0xffffffffu, bj.w, i);
                             const float ai = box_area(bi);
                             const unsigned hcol = __ballot_sync(0xffffffffu, p_alive && pair_hit<kFinite>(bp, ap, bi, ai, a.thr_f));
                             const unsigned row = __ballot_sync(0xffffffffu, (lane > i) && pair_hit<kFinite>(bi, ai, bj, aj, a.thr_f));
@@ -949,9 +957,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
 #endif
             }
         };
-        if (!fast) run_chunks(std::false_type{});
-        else if (nonfinite) run_chunks_fast(std::false_type{});
-        else run_chunks_fast(std::true_type{});
+        if (fast) { if (nonfinite) run_chunks_fast(std::false_type{}, std::true_type{}); else run_chunks_fast(std::true_type{}, std::true_type{}); }
+        else if (mid) run_chunks_fast(std::false_type{}, std::false_type{});
+        else run_chunks(std::false_type{});
         __syncthreads();
         for (int c = tid; c < ncl; c += kNmsThreads) cls_count[c] = (int)(state[c] & 0xffffu);
     }
@@ -977,7 +985,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
     int32_t* out = (G == 1) ? (a.keep + (size_t)b * n) : (a.ws_stage + (size_t)blockIdx.x * n);
     for (int c = warp; c < ncl; c += kNmsWarps) {
         const int off = cls_count[c], cnt = cls_count[c + 1] - off, s0 = cls_start[c];
-        if (fast && !use_mask) for (int r = lane; r < cnt; r += 32) out[off + r] = (int32_t)(keys[kpos[s0 + r]] & kIdxMask);
+        if ((fast && !use_mask) || mid) for (int r = lane; r < cnt; r += 32) out[off + r] = (int32_t)(keys[kpos[s0 + r]] & kIdxMask);
         else for (int r = lane; r < cnt; r += 32) out[off + r] = (int32_t)(keys[s0 + r] & kIdxMask);
     }
     if (G == 1) {
@@ -1107,7 +1115,7 @@ extern "C" int yms_nms_batched(const float* boxes, const float* scores, const in
         cudaError_t e = cudaMemsetAsync(a.ws_ticket, 0, sizeof(unsigned int) * batch, st);
         if (e != cudaSuccess) return fail((int)e, "nms: ticket memset failed");
     }
-    const size_t tables = (size_t)(num_classes + 2) * 4 * 4 + (size_t)(kFastCap / 32 + num_classes + 4) * 4 + 16;   // class tables + removed words
+    const size_t tables = (size_t)(num_classes + 2) * 4 * 4 + (size_t)(kSortTile / 32 + num_classes + 4) * 4 + 16;   // class tables + removed words
     if (kKeyRegionBytes + tables > 232448) return fail(YMS_E_UNSUPPORTED, "nms: %d classes need %zu bytes of shared memory (limit 232448)", num_classes, kKeyRegionBytes + tables);
     // keys | boxes | kept positions: 192 KB hold the sort tile and 8192 candidates without the position list; what the class tables
     // leave of another 16 KB lets a full 8192-candidate CTA stay on the fast path
