@@ -39,13 +39,19 @@ CONV_CASES = [
     ("3x3s2_slices", 2, 40, 40, 128, 128, 3, 2, 1, 0, 0, 0, 1),
     ("3x3s2_odd_out", 1, 24, 40, 64, 64, 3, 2, 1, 0, 0, 0, 0),
     ("3x3_f32_320", 1, 64, 64, 64, 64, 3, 1, 0, 0, 0, 1, 0),
+    ("3x3_128_128_w40", 4, 40, 40, 128, 128, 3, 1, 1, 1, 0, 0, 1),      # streamed weights, residual, slices, many items per CTA / cluster
+    ("3x3_256_256_w20", 8, 20, 20, 256, 256, 3, 1, 1, 0, 0, 0, 0),
+    ("3x3_64_144_w80", 2, 80, 80, 64, 144, 3, 1, 1, 0, 0, 0, 0),        # N = 144: three 64-channel output chunks, the last one partial
 ]
 
 
 def _variants(case):
-    """3x3/s1 bf16 single-source layers have three tcgen05 implementations (the per-layer autotuner picks one)."""
+    """3x3/s1 bf16 single-source layers have four tcgen05 implementations (the per-layer autotuner picks one); variant 5 = the
+    CTA-pair kernel (cta_group::2), for c_out <= 256."""
     name, B, H, W, cin, cout, k, s, act, res, cin2, f32, sl = case
-    return (0, 1, 2, 3) if (k == 3 and s == 1 and not f32 and not cin2) else (0,)
+    if not (k == 3 and s == 1 and not f32 and not cin2):
+        return (0,)
+    return (0, 1, 2, 3, 5) if cout <= 256 else (0, 1, 2, 3)
 
 
 @pytest.mark.parametrize("case,variant", [(c, v) for c in CONV_CASES for v in _variants(c)],

@@ -310,6 +310,219 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     YMS_PROF_ONLY(if (prof && threadIdx.x == 0) prof[12] = clock64() - prof_t_entry;)
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (yms_conv_params.variant == 5).  At N = 128 one tcgen05.mma (M = 128, K = 16) reads 4 KB of A and 4 KB
+// of B from shared memory per 64 cycles of tensor-pipe work -- exactly the 128 B/cycle the SM has, so every other byte that
+// moves through shared memory (TMA writes, the epilogue's staging) stretches the MMAs (role accounting: ~134 cycles per
+// MMA in-kernel against 64 in isolation).  Two CTAs of a cluster on the two SMs of a TPC instead run ONE MMA of M = 256:
+// each supplies the halo tile of its own 8 x th sub-tile (the cluster owns two x-adjacent sub-tiles) and HALF of the weight
+// tile (N/2 rows), the tensor cores exchange the halves: 6 KB per 64 cycles per SM, and half the weight traffic from L2.
+// Accumulator rows 0..127 / 128..255 live in the TMEM of CTA 0 / CTA 1: the epilogue is the single-CTA one, per CTA.
+// Protocol: the leader (rank 0) issues all MMAs; the full barriers are the leader's and are signalled by the TMA loads of both
+// CTAs (cta_group::2 loads, expect_tx of the pair's bytes by the leader's producer); tcgen05.commit arrives on the empty /
+// accumulator-full barriers of both CTAs (multicast); the epilogue groups of both CTAs arrive on the leader's
+// accumulator-empty barrier.  Same per-CTA shared-memory layout and ring discipline as conv3x3_kernel<1>.
+__global__ void __launch_bounds__(kThreads3, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                    const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
+                    const __grid_constant__ Conv3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    const uint32_t base = smem_u32(smem_dyn);
+    unsigned char* gbase = smem_dyn;
+    if (base & 1023u) __trap();
+    const uint32_t rank = cluster_ctarank();
+    const bool leader_cta = rank == 0;
+    const int half_n = p.block_n >> 1;
+    const int b_tile_bytes = (half_n * 128 + 1023) & ~1023;          // this CTA's half of a weight tile
+    const int a_region = ((p.a_stages * p.halo_stage) + 1023) & ~1023;
+    const int b_region = (p.resident ? 9 * p.kb : 3 * p.b_stages) * b_tile_bytes;     // streamed: one ring slot = the three taps of a kernel row
+    const uint32_t smem_a = base;
+    const uint32_t smem_b = base + a_region;
+    const uint32_t smem_out0 = smem_b + b_region;
+    unsigned char* g_out0 = gbase + a_region + b_region;
+    float* s_bias = reinterpret_cast<float*>(g_out0 + kEpiGroups * kStageOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int slot) { return bar0 + 8u * slot; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int gps = kEpiGroups / p.acc_stages;             // epilogue groups sharing one accumulator stage
+
+    if (warp == 0) {
+        if (lane == 0) {
+            prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
+            if (p.has_res) prefetch_tmap(&tm_res);
+        }
+        for (int i = lane; i < kNumBars; i += 32) {
+            const bool is_tempty = i >= kBarTEmpty && i < kBarTEmpty + 4;
+            mbar_init(bar(i), is_tempty ? 2 * 4 * gps : 1);          // accumulator-empty (leader's): the epilogue warps of BOTH CTAs
+        }
+        fence_barrier_init();
+        __syncwarp();
+    }
+    cluster_sync_all();                                    // the peer's barriers exist before anything signals them
+    if (warp == 0 && p.resident && elect_one()) {
+        // each CTA fetches ITS half of every weight tile; the leader's barrier collects the bytes of both
+        if (leader_cta) mbar_expect_tx(bar(kBarW), 2u * (uint32_t)(9 * p.kb) * (uint32_t)(half_n * 128));
+        for (int tap = 0; tap < 9; ++tap)
+            for (int cb = 0; cb < p.kb; ++cb)
+                tma_load_3d_2sm(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, (int)rank * half_n, tap);
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    for (int i = threadIdx.x; i < p.bias_pad; i += kThreads3) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t out_bytes = (uint32_t)(8 * p.th) * 128u;
+    const int acc_stride = 512 / p.acc_stages;
+    const int cid = (int)cluster_id_x(), ncl = (int)num_clusters_x();
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs: own halo tile, own half of the weights) =================
+        if (elect_one()) {
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            for (int t = cid; t < p.total_items; t += ncl) {
+                const Item it = decode_item(p, t);
+                for (int cb = 0; cb < p.kb; ++cb) {
+                    mbar_wait(bar(kBarAEmpty + as), aph ^ 1u);
+                    if (leader_cta) mbar_expect_tx(bar(kBarAFull + as), 2u * p.halo_bytes);
+                    tma_load_4d_2sm(smem_a + as * p.halo_stage, &tm_x, bar(kBarAFull + as),
+                                    cb * kBlockK, (it.sx * 2 + (int)rank) * 8 - 1, it.ty * p.th - 1, it.img);
+                    if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                    if (!p.resident) {
+                        for (int ky = 0; ky < 3; ++ky) {             // a slot = the 3 taps of a kernel row: a third of the ring hand-shakes
+                            mbar_wait(bar(kBarBEmpty + bs), bph ^ 1u);
+                            if (leader_cta) mbar_expect_tx(bar(kBarBFull + bs), 6u * (uint32_t)(half_n * 128));
+                            for (int kx = 0; kx < 3; ++kx)
+                                tma_load_3d_2sm(smem_b + (bs * 3 + kx) * b_tile_bytes, &tm_w, bar(kBarBFull + bs), cb * kBlockK, (int)rank * half_n, ky * 3 + kx);
+                            if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: one elected thread of the LEADER =================
+        if (leader_cta && elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint64_t hi_a = (1ull << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            const uint64_t hi_b = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            const uint32_t halo16 = (uint32_t)p.halo_stage >> 4;
+            const uint32_t btile16 = (uint32_t)b_tile_bytes >> 4;
+            if (p.resident) { mbar_wait(bar(kBarW), 0u); tc_fence_after(); }
+            const uint32_t a0_16 = (smem_a & 0x3FFFFu) >> 4, b0_16 = (smem_b & 0x3FFFFu) >> 4;
+            const int tail = ((p.c_in - (p.kb - 1) * kBlockK) + 15) >> 4;
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t a_ready = 0, b_ready = 0;
+            for (int t = cid; t < p.total_items; t += ncl) {
+                mbar_wait(bar(kBarTEmpty + acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+                for (int cb = 0; cb < p.kb; ++cb) {
+                    if (!a_ready) mbar_wait(bar(kBarAFull + as), aph);
+                    tc_fence_after();
+                    int nas = as + 1; uint32_t naph = aph;
+                    if (nas == p.a_stages) { nas = 0; naph ^= 1u; }
+                    a_ready = mbar_try_wait(bar(kBarAFull + nas), naph);
+                    const int ksteps = (cb == p.kb - 1) ? tail : 4;
+                    const uint32_t a16 = a0_16 + (uint32_t)as * halo16;
+                    const uint32_t first = (cb != 0) ? 1u : 0u;
+                    const bool last_cb = (cb == p.kb - 1);
+                    if (p.resident) {
+                        const uint32_t b16 = b0_16 + (uint32_t)cb * btile16;
+                        const uint32_t bstride16 = (uint32_t)p.kb * btile16;
+                        #pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t toff = (uint32_t)((tap / 3) * kHaloPitch + (tap % 3)) * 8u;
+                            #pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < ksteps)
+                                    umma_bf16_2sm(d_tmem, hi_a | (uint64_t)(a16 + toff + 2 * k), hi_b | (uint64_t)(b16 + tap * bstride16 + 2 * k),
+                                                  idesc, (tap | k) ? 1u : first);
+                        }
+                        umma_commit_2sm(bar(kBarAEmpty + as));
+                        if (last_cb) umma_commit_2sm(bar(kBarTFull + acc));
+                    } else {
+                        #pragma unroll 1
+                        for (int ky = 0; ky < 3; ++ky) {
+                            if (!b_ready) mbar_wait(bar(kBarBFull + bs), bph);
+                            tc_fence_after();
+                            int nbs = bs + 1; uint32_t nbph = bph;
+                            if (nbs == p.b_stages) { nbs = 0; nbph ^= 1u; }
+                            b_ready = mbar_try_wait(bar(kBarBFull + nbs), nbph);
+                            #pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const uint32_t b16 = b0_16 + (uint32_t)(bs * 3 + kx) * btile16;
+                                const uint32_t toff = (uint32_t)(ky * kHaloPitch + kx) * 8u;
+                                #pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < ksteps)
+                                        umma_bf16_2sm(d_tmem, hi_a | (uint64_t)(a16 + toff + 2 * k), hi_b | (uint64_t)(b16 + 2 * k), idesc,
+                                                      (ky | kx | k) ? 1u : first);
+                            }
+                            umma_commit_2sm(bar(kBarBEmpty + bs));
+                            if (ky == 2) {
+                                umma_commit_2sm(bar(kBarAEmpty + as));
+                                if (last_cb) umma_commit_2sm(bar(kBarTFull + acc));
+                            }
+                            bs = nbs; bph = nbph;
+                        }
+                    }
+                    as = nas; aph = naph;
+                }
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (both CTAs, each its own 128 accumulator rows = its own sub-tile) =================
+        const int grp = (warp - 2) >> 2;
+        const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        EpiShared e;
+        e.tm_y = &tm_y; e.tm_res = &tm_res;
+        e.res_bar = bar(kBarRes + grp);
+        e.s_out = smem_out0 + grp * kStageOutBytes;
+        e.s_bias = s_bias;
+        e.block_n = p.block_n; e.c_out = p.c_out; e.act = p.act; e.has_res = p.has_res;
+        e.out_bytes = out_bytes;
+        e.bar_id = 1 + grp;
+        e.leader = ((warp - 2) & 3) == 0 && lane == 0;
+        e.row = (warp & 3) * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(stage_id * acc_stride);
+        const int n_chunks = (p.block_n + 63) >> 6;
+        uint32_t res_phase = 0u, acc_phase = 0u;
+        for (int t = cid + stage_id * ncl; t < p.total_items; t += p.acc_stages * ncl) {
+            const Item it = decode_item(p, t);
+            mbar_wait(bar(kBarTFull + stage_id), acc_phase);
+            acc_phase ^= 1u;
+            tc_fence_after();
+            EpiTile tl;
+            tl.n0 = 0; tl.x0 = (it.sx * 2 + (int)rank) * 8; tl.y0 = it.ty * p.th; tl.img = it.img;
+            if (tl.x0 < p.out_w)                                     // (the pair's second sub-tile may lie outside the image)
+                for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_lane, tl, ch);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar(kBarTEmpty + stage_id), 0u);
+        }
+        if (e.leader) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                    // nobody leaves (or frees TMEM) while the peer may still signal or be read
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
 }  // namespace
 
 int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
@@ -338,8 +551,11 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.bias = q->bias;
     k.halo_bytes = (uint32_t)(kHaloPitch * (k.th + 2) * 128);
     k.desc_mode = 0;
+    // variant 5: CTA-pair kernel (conv3x3_pair_kernel): two x-adjacent sub-tiles per cluster, half a weight tile per CTA
+    k.pair = (q->variant == 5) ? 1 : 0;
+    if (k.pair && (k.n_tiles != 1 || k.tiles_x < 2)) return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 5): needs c_out <= 256 and a map at least 9 pixels wide");
 
-    const int b_tile = (k.block_n * 128 + 1023) & ~1023;
+    const int b_tile = ((k.pair ? k.block_n / 2 : k.block_n) * 128 + 1023) & ~1023;
     const int halo_stage = (int)k.halo_bytes;
     k.halo_stage = halo_stage;
     const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16;
@@ -351,7 +567,15 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         return n;
     };
     k.resident = (k.n_tiles == 1 && max_a_stages(1, resident_bytes) >= 2) ? 1 : 0;
-    if (k.resident) {
+    if (k.pair) {
+        k.sub = 1;                                         // per CTA; the cluster covers two sub-tiles
+        k.b_stages = k.resident ? 0 : 3;                   // ring slots of THREE half tiles (the taps of one kernel row)
+        for (;;) {
+            k.a_stages = max_a_stages(1, k.resident ? resident_bytes : 3 * k.b_stages * b_tile);
+            if (k.a_stages >= 2 || k.resident || k.b_stages == 2) break;
+            --k.b_stages;
+        }
+    } else if (k.resident) {
         // two sub-tiles per item when they fit: their MMAs use independent accumulators and are
         // interleaved, which hides part of the ~100-cycle per-instruction tcgen05.mma latency
         const long long sub_tiles = (long long)k.tiles_x * k.tiles_y * k.batch;
@@ -379,18 +603,19 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     if (k.a_stages < 2) return fail(YMS_E_UNSUPPORTED, "conv3x3: tile does not fit in shared memory");
     k.acc_stages = (k.sub * k.block_n <= 128) ? 4 : ((k.sub * k.block_n <= 256) ? 2 : 1);
     k.planes = k.sub; k.wtiles = 9; k.pitch = kHaloPitch; k.s2pair = 0;
-    k.super_x = ceil_div(k.tiles_x, k.sub);
+    k.super_x = ceil_div(k.tiles_x, k.pair ? 2 : k.sub);
     k.total_items = k.super_x * k.tiles_y * k.batch * k.n_tiles;
     k.mg_n_tiles = fast_div_magic(k.n_tiles); k.mg_super_x = fast_div_magic(k.super_x); k.mg_tiles_y = fast_div_magic(k.tiles_y);
     pl->grid = k.total_items < kNumSMs ? k.total_items : kNumSMs;
-    pl->smem = (size_t)((k.a_stages * k.sub * halo_stage + 1023) & ~1023) + (size_t)(k.resident ? resident_bytes : k.b_stages * b_tile) + fixed;
+    if (k.pair) pl->grid = 2 * (k.total_items < kNumSMs / 2 ? k.total_items : kNumSMs / 2);          // clusters of two CTAs
+    pl->smem = (size_t)((k.a_stages * k.sub * halo_stage + 1023) & ~1023) + (size_t)(k.resident ? resident_bytes : (k.pair ? 3 : 1) * k.b_stages * b_tile) + fixed;
 
     int rc;
     if ((rc = encode_act(&pl->tm_x, q->x, q->c_in, q->x_pixel_stride, q->batch, H, W, false, kHaloPitch, k.th + 2, 1, "x(halo)"))) return rc;
     {
         uint64_t dims[3] = {(uint64_t)q->c_in, (uint64_t)q->c_out, 9};
         uint64_t strides[2] = {(uint64_t)q->c_in * 2, (uint64_t)q->c_in * 2 * (uint64_t)q->c_out};
-        uint32_t box[3] = {kBlockK, (uint32_t)k.block_n, 1};
+        uint32_t box[3] = {kBlockK, (uint32_t)(k.pair ? k.block_n / 2 : k.block_n), 1};
         uint32_t es[3] = {1, 1, 1};
         if ((rc = encode_map(&pl->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q->weight, dims, strides, box, es, "w"))) return rc;
     }
@@ -409,6 +634,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e != cudaSuccess) return fail((int)e, "conv3x3: smem attribute: %s", cudaGetErrorString(e));
     }
     return 0;
@@ -484,7 +710,8 @@ int conv3_plan_run(const yms_conv_plan* pl0, cudaStream_t stream) {
     plc.k3.prof = g_prof_buf;
     const yms_conv_plan* pl = &plc;
     cudaError_t le;
-    if (pl->k3.sub == 1) le = launch_pdl(conv3x3_kernel<1>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    if (pl->k3.pair) le = launch_pdl_cluster(conv3x3_pair_kernel, pl->grid, kThreads3, pl->smem, stream, 2, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    else if (pl->k3.sub == 1) le = launch_pdl(conv3x3_kernel<1>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else if (pl->k3.sub == 2) le = launch_pdl(conv3x3_kernel<2>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else le = launch_pdl(conv3x3_kernel<4>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     if (le != cudaSuccess) return fail((int)le, "conv3x3_kernel launch: %s", cudaGetErrorString(le));

@@ -443,7 +443,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     yms_conv_plan* pl = new (std::nothrow) yms_conv_plan();
     if (!pl) return fail(YMS_E_ARG, "conv: out of host memory");
     pl->kind = 0;
-    if (q->variant < 0 || q->variant > 4) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..4"); }
+    if (q->variant < 0 || q->variant > 5) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..5"); }
     if (q->variant == 4) {                                       // stride-2 pair-line kernel, pair-packed weights (conv3x3.cu)
         int rc4 = conv3_s2pair_plan_init(pl, q);
         if (rc4) { delete pl; return rc4; }

@@ -66,6 +66,7 @@ struct Conv3Params {
     int bias_pad;
     int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
     int s2pair;                                // stride-2 pair-line mode (c_in == 32, dense input): see conv3x3.cu
+    int pair;                                  // CTA-pair kernel (cta_group::2, M = 256): two x-adjacent sub-tiles per cluster, each CTA half of B
     int planes;                                // TMA boxes per A stage (== sub, or 2 parity planes in s2pair mode)
     int wtiles;                                // resident weight tiles per 64-channel block (9 taps, or 6 pair-packed tiles)
     int pitch;                                 // lines per halo row (10, or 9 pixel pairs in s2pair mode)
@@ -81,17 +82,30 @@ extern long long* g_prof_buf;                  // set by yms_debug_set_prof (cap
 inline uint32_t fast_div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
 
 // Launch with the programmatic-stream-serialization attribute (kernels call pdl_wait() before touching
-// global data).  YMS_PDL=0 disables it.
+// global data).  The library option pdl_off disables it.  `cluster` > 1: thread-block clusters of that many CTAs along x.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, int cluster, Args&&... args) {
     const bool enabled = !g_opt.pdl_off;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (enabled) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_pdl_cluster(kernel, grid, block, smem, stream, 1, std::forward<Args>(args)...);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode();

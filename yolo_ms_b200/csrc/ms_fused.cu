@@ -82,6 +82,7 @@ struct MsParams {
     int e_ch, n_chunks, tail_ksteps;             // expanded channels, 64-channel chunks, k-steps of the last chunk
     int c_out, block_n, act2;
     int e_stages, n_items, d_bufs, g1_stages;
+    uint32_t p_mask; int n_p;                    // mode 2: compute warps that run the pw1 epilogue (the others are depthwise warps)
     int w2_resident, w2_tile_bytes;
     int acc_stride, tmem_cols;
     int stage_bytes, off_dww, off_dwb, off_w2;   // layout of one e stage
@@ -317,11 +318,11 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         }
         if (lane < kNumBars) {
             uint32_t cnt = 1;
-            if (lane < kMaxE) cnt = 1u + (p.mode == 2 ? (uint32_t)kPWarps : 0u);                              // e_full: producer (+ pw1 epilogue warps)
+            if (lane < kMaxE) cnt = 1u + (uint32_t)p.n_p;                              // e_full: producer (+ pw1 epilogue warps)
             else if (lane < 2 * kMaxE) cnt = (uint32_t)kItems + ((p.mode >= 1 && !p.w2_resident) ? 1u : 0u);  // e_empty: items (+ MMA commit)
             else if (lane < 12) cnt = (uint32_t)kItems;                                                       // d_full: items
             else if (lane >= 18 && lane < 20) cnt = 4u;                                                       // acc_empty: 4 epilogue warps
-            else if (lane >= 25 && lane < 28) cnt = (uint32_t)kPWarps;                                        // g1_empty: pw1 epilogue warps
+            else if (lane >= 25 && lane < 28) cnt = (uint32_t)max(p.n_p, 1);                                        // g1_empty: pw1 epilogue warps
             mbar_init(bar0 + 8u * lane, cnt);
         }
         fence_barrier_init();
@@ -487,7 +488,7 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
             }
             if (e.leader) tma_store_wait_read<0>();
         }
-    } else if (p.mode == 2 && warp >= kFirstCw && warp < kFirstCw + kPWarps) {
+    } else if (warp >= kFirstCw && warp < kFirstCw + kCwCount && ((p.p_mask >> (warp - kFirstCw)) & 1u)) {
         // ================= mode 2, pw1 epilogue warps: accumulator rows (halo pixels) -> bias / SiLU -> bf16 -> halo tile of the
         // chunk's e stage, zero outside the image.  Two warps per TMEM lane quadrant, dealt the M tiles of the halo by parity.
         const int wq = warp & 3, half = (warp - kFirstCw) >> 2;
@@ -597,15 +598,15 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
         __syncwarp();
     } else {
         // ================= depthwise warps: the items of all chunks, in order, dealt round-robin =================
-        const int first = kFirstCw + (p.mode == 2 ? kPWarps : 0);
-        const int n_dw = kFirstCw + kCwCount - first;
+        const uint32_t d_mask = ~p.p_mask & ((1u << kCwCount) - 1u);          // compute warps without pw1-epilogue work
+        const int n_dw = __popc(d_mask);
         const int d_bufs = p.d_bufs;
         const int my_units = (int)blockIdx.x < p.units ? (p.units - 1 - (int)blockIdx.x) / grid + 1 : 0;
         const int n_total = my_units * p.cpu;
         const int e_stages = p.e_stages;
         const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
         const uint32_t w_lane = (uint32_t)p.off_dww + (uint32_t)(lane * 8), b_lane = (uint32_t)p.off_dwb + (uint32_t)(lane * 8);
-        int n = 0, i = warp - first;
+        int n = 0, i = __popc(d_mask & ((1u << (warp - kFirstCw)) - 1u));
         int s = 0; uint32_t ph = 0;
         int ds = 0; uint32_t dph = 0;
         for (;;) {
@@ -784,6 +785,16 @@ extern "C" int yms_ms_plan_create(const yms_ms_params* q, yms_ms_plan** out) {
     kp.e_stages = stages;
     kp.d_bufs = dbufs;
     kp.n_items = items_per_chunk(k, geom);
+    // mode 2: compute warp w (TMEM lane quadrant (kFirstCw + w) & 3, M-tile parity w >> 2) is a pw1-epilogue warp iff one of its
+    // M tiles holds halo pixels in its quadrant (18 x 10 = 180 halo pixels: 6 of the 8 candidates); the rest join the depthwise warps
+    kp.p_mask = 0; kp.n_p = 0;
+    if (q->mode == 2)
+        for (int w = 0; w < kPWarps; ++w) {
+            const int wq = (kFirstCw + w) & 3;
+            bool any = false;
+            for (int m = w >> 2; m < kp.mt; m += 2) any |= m * 128 + wq * 32 < kp.hp;
+            if (any) { kp.p_mask |= 1u << w; ++kp.n_p; }
+        }
     kp.units = q->mode == 0 ? kp.total_tiles * kp.n_chunks : kp.total_tiles;
     kp.cpu = q->mode == 0 ? 1 : kp.n_chunks;
     kp.stage_tx = (uint32_t)((q->mode != 2 ? hwx * hwy * 128 : 0) + k * k * 256 + 256 + ((q->mode >= 1 && !kp.w2_resident) ? kp.w2_tile_bytes : 0));

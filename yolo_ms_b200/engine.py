@@ -176,7 +176,7 @@ class Program:
             best.desc = default_plan.desc + (f" [v{best.variant}]" if best.variant else "")
             return best
         best, best_t = default_plan, timed(default_plan)
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 5):
             try:
                 cand = ops.ConvPlan(kw["x"], kw["weight"], kw["bias"], kw["y"], ksize=kw["ksize"], stride=kw["stride"], act=kw["act"],
                                     residual=kw["residual"], x2=kw["x2"], variant=variant)
