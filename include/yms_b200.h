@@ -64,7 +64,9 @@ typedef struct yms_conv_params {
                                          4 = stride-2 pair-line kernel for 3x3/s2 with c_in == 32 on a dense input: `weight` is then
                                          PAIR-PACKED bf16 [6][c_out][64]: tile 2*ky = [w(ky,1) | w(ky,2)], tile 2*ky+1 = [0 | w(ky,0)].
                                          5 = CTA-pair halo kernel (cta_group::2, M = 256: two x-adjacent sub-tiles per 2-CTA cluster, each CTA
-                                         half of every weight tile; c_out <= 256, maps at least 9 pixels wide).
+                                         half of every weight tile; c_out <= 256, maps at least 9 pixels wide); for every other bf16-output
+                                         convolution (1x1, 3x3/s2, two sources) 5 selects the CTA-pair variant of the generic kernel (two
+                                         consecutive M tiles per cluster); 6 = that generic CTA-pair kernel for a 3x3/s1 layer.
                                          Results agree to fp32 accumulation order; used by the host-side per-layer autotuner. */
     /* tensors */
     const void* x;   int64_t x_pixel_stride;      /* bf16, elements between consecutive pixels   */

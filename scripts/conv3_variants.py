@@ -35,7 +35,7 @@ for ci, co, hw, res in CASES:
     y = torch.empty(B, hw, hw, co, device=DEV, dtype=torch.bfloat16)
     r = torch.randn(B, hw, hw, co, generator=g).to(DEV).to(torch.bfloat16) if res else None
     out, ref = [], None
-    for v in (1, 2, 3, 5):
+    for v in (1, 2, 3, 5, 6):
         try:
             pl = ops.ConvPlan(x, w, b, y, ksize=3, stride=1, act=True, residual=r, variant=v)
         except YmsError as e:

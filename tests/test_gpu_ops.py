@@ -49,9 +49,11 @@ def _variants(case):
     """3x3/s1 bf16 single-source layers have four tcgen05 implementations (the per-layer autotuner picks one); variant 5 = the
     CTA-pair kernel (cta_group::2), for c_out <= 256."""
     name, B, H, W, cin, cout, k, s, act, res, cin2, f32, sl = case
-    if not (k == 3 and s == 1 and not f32 and not cin2):
+    if f32:
         return (0,)
-    return (0, 1, 2, 3, 5) if cout <= 256 else (0, 1, 2, 3)
+    if not (k == 3 and s == 1 and not cin2):
+        return (0, 5)                                   # generic kernel: single CTA / CTA pair
+    return (0, 1, 2, 3, 5, 6) if cout <= 256 else (0, 1, 2, 3, 6)
 
 
 @pytest.mark.parametrize("case,variant", [(c, v) for c in CONV_CASES for v in _variants(c)],
@@ -77,7 +79,12 @@ def test_conv_gemm_matches_torch_fp32(ops, case, variant):
     yfull = torch.full((B, Ho, Wo, cout + pad_c), 7.0, device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
     y = yfull[..., 8:8 + cout] if sl else yfull
     wpk = wt.permute(2, 3, 0, 1).reshape(k * k, cout, ktot).contiguous()
-    ops.ConvPlan(x, wpk, bias, y, ksize=k, stride=s, act=bool(act), residual=r, x2=x2, variant=variant).run()
+    try:
+        ops.ConvPlan(x, wpk, bias, y, ksize=k, stride=s, act=bool(act), residual=r, x2=x2, variant=variant).run()
+    except Exception as e:                                # the CTA-pair variants need two M tiles / sub-tiles: "unsupported" is the contract
+        if variant in (5, 6) and "code -2" in str(e):
+            pytest.skip(str(e))
+        raise
     xin = x.float() if x2 is None else torch.cat([x.float(), x2.float()], -1)
     ref = F.conv2d(xin.permute(0, 3, 1, 2), wt.float(), bias, stride=s, padding=k // 2)
     ref = F.silu(ref) if act else ref

@@ -361,6 +361,218 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     YMS_PROF_ONLY(if (prof && threadIdx.x == 0) prof[12] = clock64() - prof_t_entry;)
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (yms_conv_params.variant == 5; bf16 output, no decode / up-add epilogue).  Two CTAs of a cluster on the
+// two SMs of a TPC run ONE tcgen05.mma of M = 256 per k-step: CTA r owns M tile 2c + r of cluster item c (same N tile),
+// loads its own A tile and HALF of the weight tile (N/2 rows); the accumulator rows of its tile stay in its own TMEM, so the
+// epilogue is the single-CTA one.  What it buys on the layers this kernel runs (1x1 with K >= 256 on the 40x40 / 20x20 maps,
+// 3x3/s2, 3x3 on 20x20): per k-block the single-thread issue path costs ~290 + 4 x 36 cycles against 4 x 64 cycles of
+// tensor-pipe work at N = 128 -- issue-bound -- and every CTA re-streams the whole weight tile from L2; the pair issues the
+// same number of instructions for twice the work and fetches each weight byte once per TPC.
+// Protocol as in conv3x3_pair_kernel: full barriers in the leader (rank 0), signalled by the cta_group::2 TMA loads of both
+// CTAs; commits multicast to the empty / accumulator-full barriers of both; both epilogues arrive on the leader's
+// accumulator-empty barrier.
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
+                      const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
+                      const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ ConvKernelParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // same offset in both CTAs (same kernel, same dynamic size)
+    unsigned char* gbase = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t rank = cluster_ctarank();
+    const bool leader_cta = rank == 0;
+    const int half_n = p.block_n >> 1;
+    const int b_tile_bytes = half_n * 128;
+    const int b_tile_pad = (b_tile_bytes + 1023) & ~1023;
+    const int stage_bytes = kATileBytes + (p.resident ? 0 : b_tile_pad);
+    const int kb_total_res = p.taps * (p.kb1 + p.kb2);
+    const int ring_bytes = p.num_stages * stage_bytes + (p.resident ? kb_total_res * b_tile_pad : 0);
+    const uint32_t smem_a0 = base;
+    const uint32_t smem_bres = base + p.num_stages * stage_bytes;
+    const uint32_t smem_out0 = base + ring_bytes;
+    unsigned char* g_out0 = gbase + ring_bytes;
+    float* s_bias = reinterpret_cast<float*>(g_out0 + p.epi_groups * kStageOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 4 + s); };
+    auto res_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 8 + s); };
+    auto w_bar = [&]() { return bar0 + 8u * (2 * kMaxStages + 12); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int gps = p.epi_groups / p.acc_stages;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
+            if (p.kb2) prefetch_tmap(&tm_x2);
+            prefetch_tmap(&tm_y);
+            if (p.has_res) prefetch_tmap(&tm_res);
+        }
+        if (lane < 2 * kMaxStages + 13) {
+            const bool is_tempty = lane >= 2 * kMaxStages + 4 && lane < 2 * kMaxStages + 8;
+            mbar_init(bar0 + 8u * lane, is_tempty ? 2 * 4 * gps : 1);   // accumulator-empty (leader's): epilogue warps of BOTH CTAs
+        }
+        fence_barrier_init();
+        __syncwarp();
+    }
+    cluster_sync_all();                                    // the peer's barriers exist before anything signals them
+    if (warp == 0 && p.resident && elect_one()) {
+        const int kpt = p.kb1 + p.kb2;
+        if (leader_cta) mbar_expect_tx(w_bar(), 2u * (uint32_t)kb_total_res * (uint32_t)b_tile_bytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+            for (int kb = 0; kb < kpt; ++kb)
+                tma_load_3d_2sm(smem_bres + (tap * kpt + kb) * b_tile_pad, &tm_w, w_bar(),
+                                kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, (int)rank * half_n, tap);
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.bias_pad; i += blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const int kb_per_tap = p.kb1 + p.kb2;
+    const int num_kb = p.taps * kb_per_tap;
+    const int pad = p.ksize >> 1;
+    const uint32_t a_bytes = (uint32_t)(p.tw * p.th) * 128u;
+    const int acc_stride = p.tmem_cols / p.acc_stages;
+    const uint32_t stage_tx = 2u * (a_bytes + (p.resident ? 0u : (uint32_t)b_tile_bytes));
+    const int cid = (int)cluster_id_x(), ncl = (int)num_clusters_x();
+    // cluster item u = (N tile, pair of M tiles); this CTA's tile as an index of the single-CTA enumeration (N tile fastest)
+    auto my_tile = [&](int u, bool& valid) {
+        const int mp = (int)fast_div((uint32_t)u, p.mg_n_tiles), nt = u - mp * p.n_tiles;
+        int m = 2 * mp + (int)rank;
+        valid = m < p.m_tiles;
+        if (!valid) m = p.m_tiles - 1;                     // odd tile count: the spare CTA re-loads its neighbour's tile and stores nothing
+        return m * p.n_tiles + nt;
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int u = cid; u < p.total_tiles; u += ncl) {
+                bool valid;
+                const TileCoord tc = decode_tile(p, my_tile(u, valid));
+                const int n0 = tc.n_tile * p.block_n + (int)rank * half_n;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+                    const int xin = tc.x0 * p.stride + kx - pad;
+                    const int yin = tc.y0 * p.stride + ky - pad;
+                    for (int kb = 0; kb < kb_per_tap; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t sa = smem_a0 + stage * stage_bytes;
+                        const uint32_t sb = sa + kATileBytes;
+                        if (leader_cta) mbar_expect_tx(full_bar(stage), stage_tx);
+                        if (p.s2_dense) {
+                            const int px = (kx != 1), py = (ky != 1);
+                            asm volatile(
+                                "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                                ::"r"(sa), "l"(reinterpret_cast<uint64_t>(&tm_x)), "r"(full_bar(stage) & kPeerBitMask), "r"(px * p.c_in1 + kb * kBlockK),
+                                  "r"(tc.x0 - (kx == 0)), "r"(py), "r"(tc.y0 - (ky == 0)), "r"(tc.img) : "memory");
+                            if (!p.resident) tma_load_3d_2sm(sb, &tm_w, full_bar(stage), kb * kBlockK, n0, tap);
+                        } else if (kb < p.kb1) {
+                            tma_load_4d_2sm(sa, &tm_x, full_bar(stage), kb * kBlockK, xin, yin, tc.img);
+                            if (!p.resident) tma_load_3d_2sm(sb, &tm_w, full_bar(stage), kb * kBlockK, n0, tap);
+                        } else {
+                            tma_load_4d_2sm(sa, &tm_x2, full_bar(stage), (kb - p.kb1) * kBlockK, xin, yin, tc.img);
+                            if (!p.resident) tma_load_3d_2sm(sb, &tm_w, full_bar(stage), p.c_in1 + (kb - p.kb1) * kBlockK, n0, tap);
+                        }
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: one elected thread of the LEADER =================
+        if (leader_cta && elect_one()) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            if (p.resident) { mbar_wait(w_bar(), 0u); tc_fence_after(); }
+            const uint64_t hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            const uint32_t a0_16 = (smem_a0 & 0x3FFFFu) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+            const uint32_t bres16 = (smem_bres & 0x3FFFFu) >> 4, btile16 = (uint32_t)b_tile_pad >> 4;
+            const int tail1 = ((p.c_in1 - (p.kb1 - 1) * kBlockK) + 15) >> 4;
+            const int tail2 = p.kb2 ? (((p.c_in2 - (p.kb2 - 1) * kBlockK) + 15) >> 4) : 4;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t ready = 0;
+            for (int u = cid; u < p.total_tiles; u += ncl) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
+                int kbi = 0;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kb = 0; kb < kb_per_tap; ++kb, ++kbi) {
+                        if (!ready) mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        int nstage = stage + 1; uint32_t nphase = phase;
+                        if (nstage == p.num_stages) { nstage = 0; nphase ^= 1u; }
+                        ready = mbar_try_wait(full_bar(nstage), nphase);
+                        const int ksteps = (kb == p.kb1 - 1) ? tail1 : ((kb == kb_per_tap - 1) ? tail2 : 4);
+                        const uint32_t a16 = a0_16 + (uint32_t)stage * stage16;
+                        const uint32_t b16 = p.resident ? bres16 + (uint32_t)kbi * btile16 : a16 + (uint32_t)(kATileBytes >> 4);
+                        umma_bf16_2sm(d_tmem, hi | (uint64_t)a16, hi | (uint64_t)b16, idesc, kbi ? 1u : 0u);
+                        #pragma unroll
+                        for (int k = 1; k < 4; ++k)
+                            if (k < ksteps) umma_bf16_2sm(d_tmem, hi | (uint64_t)(a16 + 2 * k), hi | (uint64_t)(b16 + 2 * k), idesc, 1u);
+                        umma_commit_2sm(empty_bar(stage));
+                        if (kbi == num_kb - 1) umma_commit_2sm(tfull_bar(acc));
+                        stage = nstage; phase = nphase;
+                    }
+                }
+                if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue (both CTAs, each its own tile) =================
+        const int grp = (warp - 2) >> 2;
+        const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        EpiShared e;
+        e.tm_y = &tm_y; e.tm_res = &tm_res;
+        e.res_bar = res_bar(grp);
+        e.s_out = smem_out0 + grp * kStageOutBytes;
+        e.s_bias = s_bias;
+        e.block_n = p.block_n; e.c_out = p.c_out; e.act = p.act; e.has_res = p.has_res;
+        e.out_bytes = a_bytes;
+        e.bar_id = 1 + grp;
+        e.leader = ((warp - 2) & 3) == 0 && lane == 0;
+        e.row = (warp & 3) * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(stage_id * acc_stride);
+        const int n_chunks = (p.block_n + 63) >> 6;
+        uint32_t res_phase = 0u, acc_phase = 0u;
+        for (int u = cid + stage_id * ncl; u < p.total_tiles; u += p.acc_stages * ncl) {
+            bool valid;
+            const TileCoord tc = decode_tile(p, my_tile(u, valid));
+            EpiTile tl; tl.n0 = tc.n_tile * p.block_n; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
+            mbar_wait(tfull_bar(stage_id), acc_phase);
+            acc_phase ^= 1u;
+            tc_fence_after();
+            if (valid)
+                for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(stage_id), 0u);
+        }
+        if (e.leader) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -443,14 +655,14 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     yms_conv_plan* pl = new (std::nothrow) yms_conv_plan();
     if (!pl) return fail(YMS_E_ARG, "conv: out of host memory");
     pl->kind = 0;
-    if (q->variant < 0 || q->variant > 5) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..5"); }
+    if (q->variant < 0 || q->variant > 6) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..6"); }
     if (q->variant == 4) {                                       // stride-2 pair-line kernel, pair-packed weights (conv3x3.cu)
         int rc4 = conv3_s2pair_plan_init(pl, q);
         if (rc4) { delete pl; return rc4; }
         *out = pl;
         return 0;
     }
-    if (q->ksize == 3 && q->stride == 1 && q->out_dtype == YMS_DTYPE_BF16 && q->c_in2 == 0 && q->variant != 1) {
+    if (q->ksize == 3 && q->stride == 1 && q->out_dtype == YMS_DTYPE_BF16 && q->c_in2 == 0 && q->variant != 1 && q->variant != 6) {
         int rc3 = conv3_plan_init(pl, q);
         if (rc3) { delete pl; return rc3; }
         *out = pl;
@@ -495,16 +707,23 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     kp.ksize = q->ksize; kp.taps = q->ksize * q->ksize; kp.stride = q->stride;
     kp.act = q->act ? 1 : 0; kp.out_f32 = (q->out_dtype == YMS_DTYPE_F32); kp.has_res = q->residual ? 1 : 0;
     kp.total_tiles = kp.tiles_x * kp.tiles_y * kp.batch * kp.n_tiles;
+    // variant 5 (outside the 3x3/s1 halo kernels, which have their own pair variant): CTA-pair kernel, bf16 output only
+    kp.pair = (q->variant == 5 || q->variant == 6) ? 1 : 0;
+    kp.m_tiles = kp.tiles_x * kp.tiles_y * kp.batch;
+    if (kp.pair) {
+        if (q->out_dtype != YMS_DTYPE_BF16 || kp.m_tiles < 2) { delete pl; return fail(YMS_E_UNSUPPORTED, "conv (variant 5): needs bf16 output and at least two M tiles"); }
+        kp.total_tiles = ceil_div(kp.m_tiles, 2) * kp.n_tiles;                    // cluster items
+    }
     kp.bias_pad = kp.n_tiles * kp.block_n + 64;
     kp.bias = q->bias;
     kp.y_f32 = kp.out_f32 ? reinterpret_cast<float*>(q->y) : nullptr;
     kp.y_ps = q->y_pixel_stride;
 
-    const int b_bytes = (kp.block_n * 128 + 1023) & ~1023;
+    const int b_bytes = ((kp.pair ? kp.block_n / 2 : kp.block_n) * 128 + 1023) & ~1023;     // pair: half a weight tile per CTA
     const int res_bytes = kp.taps * (kp.kb1 + kp.kb2) * b_bytes;
     // "half" CTAs (yms_debug_set_option("conv_half", 1), experimental): 2 epilogue groups, 2 x 128 TMEM columns, <= 113 KB -> two CTAs per SM.  Only for
     // N <= 128 (two accumulator stages must remain) and when at least 3 ring stages fit beside resident / streamed weights.
-    const bool want_half = g_opt.conv_half != 0;
+    const bool want_half = g_opt.conv_half != 0 && !kp.pair;
     int groups = kEpiGroups, limit = kSmemLimit;
     if (want_half && kp.block_n <= 128) {
         const int fixed_h = 2 * kStageOutBytes + kp.bias_pad * 4 + (2 * kMaxStages + 16) * 8 + 1024;
@@ -525,6 +744,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     pl->smem = (size_t)stages * stage_bytes + (kp.resident ? res_bytes : 0) + fixed;
     const int max_ctas = kNumSMs * (groups == 2 ? 2 : 1);
     pl->grid = kp.total_tiles < max_ctas ? kp.total_tiles : max_ctas;
+    if (kp.pair) pl->grid = 2 * (kp.total_tiles < kNumSMs / 2 ? kp.total_tiles : kNumSMs / 2);      // clusters of two CTAs
     pl->threads = 64 + groups * kEpiGroupThreads;
 
     int rc;
@@ -546,7 +766,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     {
         uint64_t dims[3] = {(uint64_t)K_total, (uint64_t)q->c_out, (uint64_t)kp.taps};
         uint64_t strides[2] = {(uint64_t)K_total * 2, (uint64_t)K_total * 2 * (uint64_t)q->c_out};
-        uint32_t box[3] = {kBlockK, (uint32_t)kp.block_n, 1};
+        uint32_t box[3] = {kBlockK, (uint32_t)(kp.pair ? kp.block_n / 2 : kp.block_n), 1};
         uint32_t es[3] = {1, 1, 1};
         if ((rc = encode_map(&pl->tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q->weight, dims, strides, box, es, "w"))) { delete pl; return rc; }
     }
@@ -564,6 +784,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     if (first_use_on_device(attr_seen)) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) { delete pl; return fail((int)e, "conv: smem attribute: %s", cudaGetErrorString(e)); }
     }
     *out = pl;
@@ -602,8 +823,8 @@ extern "C" int yms_conv_plan_fuse_decode(yms_conv_plan* pl, const yms_decode_fus
 extern "C" int yms_conv_plan_add_upsampled(yms_conv_plan* pl, const float* t, int64_t t_pixel_stride, int out_h, int out_w) {
     if (!pl || !t) return fail(YMS_E_ARG, "add_upsampled: null argument");
     ConvKernelParams& kp = pl->kp;
-    if (pl->kind != 0 || kp.ksize != 1 || kp.out_f32 || kp.dec.mode)
-        return fail(YMS_E_UNSUPPORTED, "add_upsampled: the plan must be a 1x1 convolution with bf16 output");
+    if (pl->kind != 0 || kp.ksize != 1 || kp.out_f32 || kp.dec.mode || kp.pair)
+        return fail(YMS_E_UNSUPPORTED, "add_upsampled: the plan must be a 1x1 convolution with bf16 output (not the CTA-pair variant)");
     if (out_h <= 0 || out_w <= 0 || ((out_h | out_w) & 1) || (long long)kp.out_w % ((long long)out_h * out_w))
         return fail(YMS_E_ARG, "add_upsampled: even H, W that divide the plan's pixels are required");
     if ((kp.c_out % 16) || kp.n_tiles * kp.block_n != kp.c_out)      // every accumulator column must be a real channel of t
@@ -620,8 +841,10 @@ extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     if (pl->kind == 1) return conv3_plan_run(pl, (cudaStream_t)stream);
     ConvKernelParams kp = pl->kp;
     kp.prof = g_prof_buf;
-    cudaError_t le = launch_pdl(kp.dec.mode ? conv_gemm_kernel<true> : conv_gemm_kernel<false>, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
-                                pl->tm_y, pl->tm_res, kp);
+    cudaError_t le = kp.pair
+        ? launch_pdl_cluster(conv_gemm_pair_kernel, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, 2, pl->tm_x, pl->tm_x2, pl->tm_w, pl->tm_y, pl->tm_res, kp)
+        : launch_pdl(kp.dec.mode ? conv_gemm_kernel<true> : conv_gemm_kernel<false>, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
+                     pl->tm_y, pl->tm_res, kp);
     if (le != cudaSuccess) return fail((int)le, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");
 }

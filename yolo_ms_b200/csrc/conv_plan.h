@@ -35,6 +35,8 @@ struct ConvKernelParams {
     int num_stages, total_tiles;
     int resident;                              // all weight tiles of the (single) N tile stay in smem
     int s2_dense;                              // stride-2 input is a dense NHWC tensor: 5-D parity view, no traversal stride
+    int pair;                                  // CTA-pair kernel (cta_group::2, M = 256): two consecutive M tiles per cluster, each CTA half of B
+    int m_tiles;                               //   M tiles (tiles_x * tiles_y * batch); an odd count leaves the last cluster's second CTA without a tile
     int acc_stages;                            // TMEM accumulator stages == active epilogue groups (1, 2 or 4)
     int epi_groups;                            // epilogue groups of 4 warps: 4 (one 576-thread CTA per SM) or 2 ("half" CTAs: 320
                                                // threads, <= 113 KB of shared memory, 256 TMEM columns, so that TWO CTAs -- of this

@@ -103,6 +103,10 @@ class Program:
         if AUTOTUNE and ksize == 3 and stride == 1 and x2 is None and y.dtype == torch.bfloat16:
             plan = self._autotune(plan, dict(x=x, weight=weight_packed, bias=bias, y=y, ksize=ksize, stride=stride, act=act,
                                              residual=residual, x2=x2))
+        elif AUTOTUNE and y.dtype == torch.bfloat16 and up_add is None and plan.variant == 0:
+            # 1x1 / 3x3-s2 / two-source layers on the generic kernel: single CTA or CTA pair (variant 5)
+            plan = self._autotune(plan, dict(x=x, weight=weight_packed, bias=bias, y=y, ksize=ksize, stride=stride, act=act,
+                                             residual=residual, x2=x2), variants=(5,), tag=f"pair{0 if x2 is None else x2.shape[-1]}")
         self.plans.append(plan)
         self.hold(weight_packed, bias)
         self._push(plan.run, plan.desc)
@@ -148,7 +152,7 @@ class Program:
             return cand
         return default_plan
 
-    def _autotune(self, default_plan, kw):
+    def _autotune(self, default_plan, kw, variants=(1, 2, 3, 5, 6), tag="3x3"):
         """Measure, don't guess: the 3x3/s1 layers have three tcgen05 implementations whose winner depends on the map
         size (tile quantisation on 20x20 / 40x40 maps), c_out (resident vs streamed weights) and the tile count per CTA.
         Each candidate runs on the layer's real buffers at program-build time; the fastest one is kept."""
@@ -162,7 +166,7 @@ class Program:
             b.record()
             b.synchronize()
             return a.elapsed_time(b)
-        key = _tune_key("3x3", kw["x"], kw["y"], kw["ksize"], kw["stride"], kw["act"], kw["residual"])
+        key = _tune_key(tag, kw["x"], kw["y"], kw["ksize"], kw["stride"], kw["act"], kw["residual"])
         known = _TUNE_CACHE.get(key)
         if known is not None:                                     # decided earlier in this process: rebuild that variant, no timing
             best = default_plan
@@ -176,7 +180,7 @@ class Program:
             best.desc = default_plan.desc + (f" [v{best.variant}]" if best.variant else "")
             return best
         best, best_t = default_plan, timed(default_plan)
-        for variant in (1, 2, 3, 5):
+        for variant in variants:
             try:
                 cand = ops.ConvPlan(kw["x"], kw["weight"], kw["bias"], kw["y"], ksize=kw["ksize"], stride=kw["stride"], act=kw["act"],
                                     residual=kw["residual"], x2=kw["x2"], variant=variant)
