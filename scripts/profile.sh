@@ -19,10 +19,10 @@ prof() {  # name regex skip count
   ncu -i $OUT/prof_$1_$TAG.ncu-rep --page raw --csv > $OUT/prof_$1_${TAG}_raw.csv 2>/dev/null
   rm -f $OUT/prof_$1_$TAG.ncu-rep
 }
-prof gemm conv_gemm_kernel 0 6           # c2f_2.conv1 (1x1 64->64 @160), c2f_2.conv2, conv3 (3x3/s2), c2f_4.conv1, c2f_4.conv2, conv5
-prof conv3 conv3x3_kernel 0 5            # conv1 (pair-line s2), the two 160x160 bottleneck convs, first two 80x80
+prof gemm "conv_gemm_(pair_)?kernel" 0 6           # c2f_2.conv1 (1x1 64->64 @160), c2f_2.conv2, conv3 (3x3/s2), c2f_4.conv1, c2f_4.conv2, conv5
+prof conv3 "conv3x3_(pair_)?kernel" 0 8            # conv1 (pair-line s2), the two 160x160 bottleneck convs, the 80x80 ones (CTA-pair kernel where the autotuner picked it)
 prof post 'nms_kernel|head_decode|stem_t' 0 3
-prof dec conv_gemm_kernel 26 9           # the LAST conv_gemm launches of the step: the six decode-fused final head convs (75 registers)
+prof dec "conv_gemm_(pair_)?kernel" 26 9           # the LAST conv_gemm launches of the step: the six decode-fused final head convs (75 registers)
                                          # + the head's 20x20 3x3 layers the autotuner gave to the generic kernel
 du -sh $OUT; ls $OUT | grep $TAG
 # 3. MS-Block variant: launch list of one step + --set full of the fused layer kernel (160x160 pw1->dw->pw2, 80x80, 40x40 dw->pw2 / dw, 20x20)

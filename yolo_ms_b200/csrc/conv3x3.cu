@@ -341,7 +341,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const uint32_t smem_b = base + a_region;
     const uint32_t smem_out0 = smem_b + b_region;
     unsigned char* g_out0 = gbase + a_region + b_region;
-    float* s_bias = reinterpret_cast<float*>(g_out0 + kEpiGroups * kStageOutBytes);
+    float* s_bias = reinterpret_cast<float*>(g_out0 + p.epi_groups * kStageOutBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_bias) + p.bias_pad * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int slot) { return bar0 + 8u * slot; };
@@ -349,7 +349,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int gps = kEpiGroups / p.acc_stages;             // epilogue groups sharing one accumulator stage
+    const int gps = p.epi_groups / p.acc_stages;           // epilogue groups sharing one accumulator stage
 
     if (warp == 0) {
         if (lane == 0) {
@@ -372,7 +372,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 tma_load_3d_2sm(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, (int)rank * half_n, tap);
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512);
-    for (int i = threadIdx.x; i < p.bias_pad; i += kThreads3) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+    for (int i = threadIdx.x; i < p.bias_pad; i += (int)blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -558,7 +558,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     const int b_tile = ((k.pair ? k.block_n / 2 : k.block_n) * 128 + 1023) & ~1023;
     const int halo_stage = (int)k.halo_bytes;
     k.halo_stage = halo_stage;
-    const int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16;
+    int fixed = kEpiGroups * kStageOutBytes + k.bias_pad * 4 + kNumBars * 8 + 16;
     const int resident_bytes = 9 * k.kb * b_tile;
     // largest ring depth (in items of `sub` halos) that fits next to `other` bytes of weights
     auto max_a_stages = [&](int sub, int other) {
@@ -566,7 +566,15 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         while (n < kRing && ((((n + 1) * sub * halo_stage + 1023) & ~1023) + other + fixed <= kSmemLimit3)) ++n;
         return n;
     };
+    k.epi_groups = kEpiGroups;
     k.resident = (k.n_tiles == 1 && max_a_stages(1, resident_bytes) >= 2) ? 1 : 0;
+    if (k.pair && !k.resident && k.n_tiles == 1) {
+        // half tiles per CTA: with TWO epilogue groups (32 KB of staging instead of 64) the weights of a 128 -> 128 layer
+        // (9 x 2 x 8 KB) stay resident next to a two-deep halo ring -- no weight traffic from L2, no weight ring hand-shakes
+        fixed -= 2 * kStageOutBytes;
+        if (max_a_stages(1, resident_bytes) >= 2) { k.resident = 1; k.epi_groups = 2; }
+        else fixed += 2 * kStageOutBytes;
+    }
     if (k.pair) {
         k.sub = 1;                                         // per CTA; the cluster covers two sub-tiles
         k.b_stages = k.resident ? 0 : 3;                   // ring slots of THREE half tiles (the taps of one kernel row)
@@ -602,6 +610,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     if (k.a_stages > kRing) k.a_stages = kRing;
     if (k.a_stages < 2) return fail(YMS_E_UNSUPPORTED, "conv3x3: tile does not fit in shared memory");
     k.acc_stages = (k.sub * k.block_n <= 128) ? 4 : ((k.sub * k.block_n <= 256) ? 2 : 1);
+    if (k.acc_stages > k.epi_groups) k.acc_stages = k.epi_groups;
     k.planes = k.sub; k.wtiles = 9; k.pitch = kHaloPitch; k.s2pair = 0;
     k.super_x = ceil_div(k.tiles_x, k.pair ? 2 : k.sub);
     k.total_items = k.super_x * k.tiles_y * k.batch * k.n_tiles;
@@ -710,7 +719,7 @@ int conv3_plan_run(const yms_conv_plan* pl0, cudaStream_t stream) {
     plc.k3.prof = g_prof_buf;
     const yms_conv_plan* pl = &plc;
     cudaError_t le;
-    if (pl->k3.pair) le = launch_pdl_cluster(conv3x3_pair_kernel, pl->grid, kThreads3, pl->smem, stream, 2, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    if (pl->k3.pair) le = launch_pdl_cluster(conv3x3_pair_kernel, pl->grid, 64 + pl->k3.epi_groups * kEpiGroupThreads, pl->smem, stream, 2, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else if (pl->k3.sub == 1) le = launch_pdl(conv3x3_kernel<1>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else if (pl->k3.sub == 2) le = launch_pdl(conv3x3_kernel<2>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else le = launch_pdl(conv3x3_kernel<4>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);

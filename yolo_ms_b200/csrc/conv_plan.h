@@ -69,6 +69,7 @@ struct Conv3Params {
     int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
     int s2pair;                                // stride-2 pair-line mode (c_in == 32, dense input): see conv3x3.cu
     int pair;                                  // CTA-pair kernel (cta_group::2, M = 256): two x-adjacent sub-tiles per cluster, each CTA half of B
+    int epi_groups;                            // pair kernel: epilogue groups of 4 warps (4, or 2 when that is what lets the weights stay resident)
     int planes;                                // TMA boxes per A stage (== sub, or 2 parity planes in s2pair mode)
     int wtiles;                                // resident weight tiles per 64-channel block (9 taps, or 6 pair-packed tiles)
     int pitch;                                 // lines per halo row (10, or 9 pixel pairs in s2pair mode)

@@ -519,16 +519,18 @@ ms_layer_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant_
                     // whatever follows them, so a bias load placed after the wait would expose its latency once per group)
                     const float4* bq = reinterpret_cast<const float4*>(s_bias + 256 + j * 64);
                     const uint32_t swz = (uint32_t)((hy * PITCH + hx) & 7);
+                    const int nq = min(4, (p.e_ch - j * 64 + 15) >> 4);            // 16-column groups of real channels in this chunk
                     uint32_t va[16], vb[16];
                     tmem_ld16(t_row, va);
                     #pragma unroll
                     for (int q16 = 0; q16 < 4; ++q16) {
+                        if (q16 >= nq) break;                                      // tail chunk (E % 64 != 0): the rest is zero padding of the weights
                         float4 hb[4];
                         #pragma unroll
                         for (int i = 0; i < 4; ++i) hb[i] = bq[q16 * 4 + i];
                         tmem_ld_wait();
                         uint32_t (&v)[16] = (q16 & 1) ? vb : va;
-                        if (q16 < 3) tmem_ld16(t_row + (uint32_t)((q16 + 1) * 16), (q16 & 1) ? va : vb);
+                        if (q16 + 1 < nq) tmem_ld16(t_row + (uint32_t)((q16 + 1) * 16), (q16 & 1) ? va : vb);
                         if (inside) {
                             uint32_t o[8];
                             #pragma unroll
