@@ -6,7 +6,9 @@
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
-CMD="python bench.py --profile-step --warmup 3"
+rm -f $OUT/tune_$TAG.txt $OUT/tune_ms_$TAG.txt
+# the plain run of step 1 times the per-layer kernel variants and writes its choices; every ncu pass (whose timings would be perturbed) reads them
+CMD="python bench.py --profile-step --warmup 3 --tune-cache $OUT/tune_$TAG.txt"
 mkdir -p $OUT
 # 1. launch list of one steady-state step: duration + DRAM bytes per launch
 $CMD > $OUT/plain_$TAG.log 2>&1 && \
@@ -26,7 +28,7 @@ prof dec "conv_gemm_(pair_)?kernel" 26 9           # the LAST conv_gemm launches
                                          # + the head's 20x20 3x3 layers the autotuner gave to the generic kernel
 du -sh $OUT; ls $OUT | grep $TAG
 # 3. MS-Block variant: launch list of one step + --set full of the fused layer kernel (160x160 pw1->dw->pw2, 80x80, 40x40 dw->pw2 / dw, 20x20)
-CMDMS="python bench.py --block ms --profile-step --warmup 3"
+CMDMS="python bench.py --block ms --profile-step --warmup 3 --tune-cache $OUT/tune_ms_$TAG.txt"
 $CMDMS > /dev/null 2>&1 && \
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     --csv --log-file $OUT/launches_ms_$TAG.csv $CMDMS > $OUT/ncu_launches_ms_$TAG.log 2>&1

@@ -43,6 +43,22 @@ def pack_weight(w: torch.Tensor) -> torch.Tensor:
 _TUNE_CACHE: dict = {}
 
 
+def save_tune_cache(path: str) -> None:
+    """Write the autotuner's decisions of this process (layer geometry -> chosen kernel variant) as text."""
+    with open(path, "w") as f:
+        f.write(repr(sorted(_TUNE_CACHE.items(), key=repr)))
+
+
+def load_tune_cache(path: str) -> int:
+    """Adopt decisions saved by save_tune_cache (e.g. so that a run under a profiler, whose timings are perturbed, builds the
+    SAME programs as the plain run before it).  Returns the number of entries read."""
+    import ast
+    with open(path) as f:
+        items = ast.literal_eval(f.read())
+    _TUNE_CACHE.update(dict(items))
+    return len(items)
+
+
 def _tune_key(kind, x, y, ksize, stride, act, residual):
     return (kind, str(x.device), tuple(x.shape), x.stride(-2), tuple(y.shape), y.stride(-2), ksize, stride, bool(act),
             None if residual is None else residual.stride(-2))
