@@ -49,12 +49,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    // The suspend-time hint is only an upper bound: measured (ncu, csrc/ms_fused.cu) the probe returns early often enough that
-    // the ~20 waiting warps of a CTA issued a quarter of the kernel's instructions in this loop.  An explicit short sleep
-    // between probes hands those issue slots to the warps that compute; the stages are buffered, so ~100 ns of extra wake-up
-    // latency does not show.
     while (!mbar_try_wait_hint(bar, parity, 4000u)) {
-        __nanosleep(64);
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
