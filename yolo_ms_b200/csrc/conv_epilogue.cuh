@@ -53,11 +53,16 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                                                     const float* up_row = nullptr) {
     {
         const int cbase = ch * 64;
-        float4 u[4], un[4];                                  // kUp: partial sums of this / the next 16-channel group (software pipeline:
-        if (kUp) {                                           // the L2 latency of a group's loads hides behind the previous group's work)
-            const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + cbase);
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) u[j] = __ldg(uq + j);
+        // kUp: partial sums of this / the next 16-channel group (software pipeline: the L2 latency of a group's loads hides behind
+        // the previous group's work).  Lanes 2i and 2i+1 are the two x-neighbours of ONE half-resolution pixel (tiles start at even
+        // pixels, W is even), i.e. they need the same 64 bytes: each loads HALF of them (32 B) and the pair swaps halves with
+        // shuffles -- half the load instructions and half the cache lines per instruction of "every lane loads its 64 bytes",
+        // which made this epilogue LSU-bound (the up-add cost as much as the GEMM).
+        const int up_half = (e.row & 1) * 2;                 // float4 index of this lane's half
+        float4 u[2], un[2];
+        if (kUp) {
+            const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + cbase) + up_half;
+            u[0] = __ldg(uq); u[1] = __ldg(uq + 1);
         }
         if (e.leader) tma_store_wait_read<0>();            // previous store of this group has left the staging buffer
         group_bar_sync(e.bar_id);
@@ -74,7 +79,7 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
         // group's bias values are fetched BEFORE its wait (the volatile tcgen05 statements pin what follows them: a bias load
         // after the wait exposes its shared-memory latency once per group).  bias / SiLU run as packed fp32 pairs (fma.rn.f32x2:
         // the same two IEEE fmas as the scalar form, half the issue slots).
-        // (the up-add variant keeps one buffer: its partial-sum prefetch already holds 32 registers)
+        // (the up-add variant keeps one buffer: a second one spills and costs 25 % of the layer)
         uint32_t va[16], vb[kUp ? 1 : 16];
         if (!kUp) tmem_ld16(t_row + (uint32_t)cbase, va);
         #pragma unroll
@@ -88,9 +93,8 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                 for (int j = 0; j < 4; ++j) b4[j] = bq[j];               // act: 0.5 * bias
             }
             if (kUp && q16 < 3 && c0 + 16 < e.block_n) {
-                const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + c0 + 16);
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) un[j] = __ldg(uq + j);
+                const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + c0 + 16) + up_half;
+                un[0] = __ldg(uq); un[1] = __ldg(uq + 1);
             }
             if (kUp) tmem_ld16(t_row + (uint32_t)c0, va);
             tmem_ld_wait();
@@ -100,11 +104,20 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
             }
             if (kUp) {
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + u[j].x);
-                    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + u[j].y);
-                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + u[j].z);
-                    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + u[j].w);
+                for (int j = 0; j < 2; ++j) {
+                    float4 o;                                // the partner's half
+                    o.x = __shfl_xor_sync(0xffffffffu, u[j].x, 1); o.y = __shfl_xor_sync(0xffffffffu, u[j].y, 1);
+                    o.z = __shfl_xor_sync(0xffffffffu, u[j].z, 1); o.w = __shfl_xor_sync(0xffffffffu, u[j].w, 1);
+                    const bool hi_mine = up_half != 0;       // selects keep v[] statically indexed (registers)
+                    const float4 lo = hi_mine ? o : u[j], hi = hi_mine ? u[j] : o;
+                    v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + lo.x);
+                    v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + lo.y);
+                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + lo.z);
+                    v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + lo.w);
+                    v[4 * j + 8] = __float_as_uint(__uint_as_float(v[4 * j + 8]) + hi.x);
+                    v[4 * j + 9] = __float_as_uint(__uint_as_float(v[4 * j + 9]) + hi.y);
+                    v[4 * j + 10] = __float_as_uint(__uint_as_float(v[4 * j + 10]) + hi.z);
+                    v[4 * j + 11] = __float_as_uint(__uint_as_float(v[4 * j + 11]) + hi.w);
                     u[j] = un[j];
                 }
             }
