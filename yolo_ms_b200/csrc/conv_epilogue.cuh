@@ -48,22 +48,26 @@ struct EpiShared {
 // into the same buffer).  Callers deal (sub-tile, chunk) units to the groups that share a stage.
 // kUp: `up_row` points at this thread's pixel of an fp32 [.., c_out] tensor of PARTIAL SUMS that is added to the accumulator before
 // bias / activation (the low-resolution half of a 1x1 convolution over cat[upsample2x(a), b], see yms_conv_plan_add_upsampled).
+// The partial sums of a chunk live in UpRegs (this lane's HALF of its 16-channel groups, see below); the caller fills them for the
+// first chunk (up_regs_load) and each call refills a group's registers from `next` -- the same lane's values of the NEXT chunk
+// this thread will process, `next_groups` 16-channel groups of it -- as soon as the group is consumed: a whole chunk of work
+// (>= an L2 round trip) lies between a load and its use.  A one-group look-ahead left most of that latency exposed four times per
+// chunk and made the up-add cost as much as the GEMM.
+struct UpRegs { float4 u[8]; };
+__device__ __forceinline__ void up_regs_load(UpRegs& r, const float* chunk_row, int row, int groups) {
+    const float4* q = reinterpret_cast<const float4*>(chunk_row) + (row & 1) * 2;
+    #pragma unroll
+    for (int g = 0; g < 4; ++g)
+        if (g < groups) { r.u[2 * g] = __ldg(q + 4 * g); r.u[2 * g + 1] = __ldg(q + 4 * g + 1); }
+}
 template <bool kUp = false>
 __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t& res_phase, uint32_t t_row, const EpiTile& tl, int ch,
-                                                    const float* up_row = nullptr) {
+                                                    UpRegs* up = nullptr, const float* next = nullptr, int next_groups = 0) {
     {
         const int cbase = ch * 64;
-        // kUp: partial sums of this / the next 16-channel group (software pipeline: the L2 latency of a group's loads hides behind
-        // the previous group's work).  Lanes 2i and 2i+1 are the two x-neighbours of ONE half-resolution pixel (tiles start at even
-        // pixels, W is even), i.e. they need the same 64 bytes: each loads HALF of them (32 B) and the pair swaps halves with
-        // shuffles -- half the load instructions and half the cache lines per instruction of "every lane loads its 64 bytes",
-        // which made this epilogue LSU-bound (the up-add cost as much as the GEMM).
+        // kUp: lanes 2i and 2i+1 are the two x-neighbours of ONE half-resolution pixel (tiles start at even pixels, W is even), i.e.
+        // they need the same 64 bytes per 16-channel group: each holds HALF of them (32 B) and the pair swaps halves with shuffles.
         const int up_half = (e.row & 1) * 2;                 // float4 index of this lane's half
-        float4 u[2], un[2];
-        if (kUp) {
-            const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + cbase) + up_half;
-            u[0] = __ldg(uq); u[1] = __ldg(uq + 1);
-        }
         if (e.leader) tma_store_wait_read<0>();            // previous store of this group has left the staging buffer
         group_bar_sync(e.bar_id);
         if (e.has_res) {
@@ -92,10 +96,6 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) b4[j] = bq[j];               // act: 0.5 * bias
             }
-            if (kUp && q16 < 3 && c0 + 16 < e.block_n) {
-                const float4* uq = reinterpret_cast<const float4*>(up_row + tl.n0 + c0 + 16) + up_half;
-                un[0] = __ldg(uq); un[1] = __ldg(uq + 1);
-            }
             if (kUp) tmem_ld16(t_row + (uint32_t)c0, va);
             tmem_ld_wait();
             uint32_t (&v)[16] = (!kUp && (q16 & 1)) ? *reinterpret_cast<uint32_t (*)[16]>(&vb[0]) : va;
@@ -106,10 +106,11 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     float4 o;                                // the partner's half
-                    o.x = __shfl_xor_sync(0xffffffffu, u[j].x, 1); o.y = __shfl_xor_sync(0xffffffffu, u[j].y, 1);
-                    o.z = __shfl_xor_sync(0xffffffffu, u[j].z, 1); o.w = __shfl_xor_sync(0xffffffffu, u[j].w, 1);
+                    const float4 mine = up->u[2 * q16 + j];
+                    o.x = __shfl_xor_sync(0xffffffffu, mine.x, 1); o.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+                    o.z = __shfl_xor_sync(0xffffffffu, mine.z, 1); o.w = __shfl_xor_sync(0xffffffffu, mine.w, 1);
                     const bool hi_mine = up_half != 0;       // selects keep v[] statically indexed (registers)
-                    const float4 lo = hi_mine ? o : u[j], hi = hi_mine ? u[j] : o;
+                    const float4 lo = hi_mine ? o : mine, hi = hi_mine ? mine : o;
                     v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + lo.x);
                     v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + lo.y);
                     v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + lo.z);
@@ -118,7 +119,7 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                     v[4 * j + 9] = __float_as_uint(__uint_as_float(v[4 * j + 9]) + hi.y);
                     v[4 * j + 10] = __float_as_uint(__uint_as_float(v[4 * j + 10]) + hi.z);
                     v[4 * j + 11] = __float_as_uint(__uint_as_float(v[4 * j + 11]) + hi.w);
-                    u[j] = un[j];
+                    if (q16 < next_groups) up->u[2 * q16 + j] = __ldg(reinterpret_cast<const float4*>(next) + 4 * q16 + up_half + j);
                 }
             }
             float f[16];

@@ -138,12 +138,14 @@ __device__ __forceinline__ void epilogue_decode(const DecodeFuse& d, const float
     }
 }
 
-// kDec: instantiation with the decode-fused epilogue (its register footprint stays out of the plain convolution kernel)
-template <bool kDec>
+// kMode: 0 plain (bf16 / fp32 output), 1 decode-fused epilogue, 2 up-add epilogue -- separate instantiations keep each epilogue's
+// register footprint (decode state, 32 registers of prefetched partial sums) out of the plain convolution kernel
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_x2,
                  const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_y,
                  const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ ConvKernelParams p) {
+    constexpr bool kDec = kMode == 1, kUpAdd = kMode == 2;
     extern __shared__ unsigned char smem_dyn[];
     long long pw0 = 0, pw1 = 0, pw2 = 0;            // wait-cycle accumulators (dead code unless -DYMS_PROF)
     (void)pw0; (void)pw1; (void)pw2;
@@ -321,25 +323,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(stage_id * acc_stride);
             const int n_chunks = (p.block_n + 63) >> 6;
             uint32_t res_phase = 0u, acc_phase = 0u;
-            for (int t = blockIdx.x + stage_id * gridDim.x; t < p.total_tiles; t += p.acc_stages * gridDim.x) {
+            // up-add: this thread's row of the half-resolution partial sums for tile t (nearest upsample: (y, x) reads (y/2, x/2)),
+            // offset to the tile's first output channel
+            auto up_row_of = [&](int t) -> const float* {
+                const TileCoord c = decode_tile(p, t);
+                uint32_t m = (uint32_t)(c.x0 + e.row);
+                if (m >= (uint32_t)p.out_w) m = (uint32_t)p.out_w - 1u;                 // rows past the last pixel are clipped by the store
+                const uint32_t img = m / (uint32_t)p.up_hw, rem = m - img * (uint32_t)p.up_hw;
+                const uint32_t y = rem / (uint32_t)p.up_w, x = rem - y * (uint32_t)p.up_w;
+                return p.up + ((size_t)img * (size_t)(p.up_hw >> 2) + (size_t)(y >> 1) * (size_t)(p.up_w >> 1) + (x >> 1)) * (size_t)p.up_ps
+                       + c.n_tile * p.block_n;
+            };
+            auto up_groups = [&](int ch) { const int g = (p.block_n - ch * 64) >> 4; return g < 4 ? g : 4; };
+            const int t_first = blockIdx.x + stage_id * gridDim.x, t_step = p.acc_stages * gridDim.x;
+            UpRegs upr;
+            const float* up_cur = nullptr;
+            if (kUpAdd && t_first < p.total_tiles && sub_id < n_chunks) {
+                up_cur = up_row_of(t_first);
+                up_regs_load(upr, up_cur + sub_id * 64, e.row, up_groups(sub_id));
+            }
+            for (int t = t_first; t < p.total_tiles; t += t_step) {
                 const TileCoord tc = decode_tile(p, t);
                 EpiTile tl; tl.n0 = tc.n_tile * p.block_n; tl.x0 = tc.x0; tl.y0 = tc.y0; tl.img = tc.img;
+                const float* up_next = (kUpAdd && t + t_step < p.total_tiles) ? up_row_of(t + t_step) : nullptr;
                 mbar_wait_acc(tfull_bar(stage_id), acc_phase, pw0);
                 acc_phase ^= 1u;
                 tc_fence_after();
                 if constexpr (kDec) {
                     epilogue_decode(p.dec, s_bias, p.c_out, t_row, e.s_out, e.row, lane, (uint32_t)(tl.x0 + e.row), (uint32_t)p.out_w);
+                } else if constexpr (kUpAdd) {
+                    for (int ch = sub_id; ch < n_chunks; ch += gps) {
+                        const bool more = ch + gps < n_chunks;                          // next unit: this tile's next chunk, else the next tile's first
+                        const float* nx = more ? up_cur + (ch + gps) * 64 : (up_next ? up_next + sub_id * 64 : nullptr);
+                        epilogue_chunk_bf16<true>(e, res_phase, t_row, tl, ch, &upr, nx, nx ? up_groups(more ? ch + gps : sub_id) : 0);
+                    }
+                    up_cur = up_next;
                 } else if (p.out_f32) {
                     const int n_chunks32 = (p.block_n + 31) >> 5;
                     for (int ch = sub_id; ch < n_chunks32; ch += gps) epilogue_chunk_f32(e, t_row, tl, ch);
-                } else if (p.up) {
-                    // this thread's pixel of the half-resolution partial sums (nearest upsample: (y, x) reads (y/2, x/2))
-                    uint32_t m = (uint32_t)(tl.x0 + e.row);
-                    if (m >= (uint32_t)p.out_w) m = (uint32_t)p.out_w - 1u;             // rows past the last pixel are clipped by the store
-                    const uint32_t img = m / (uint32_t)p.up_hw, rem = m - img * (uint32_t)p.up_hw;
-                    const uint32_t y = rem / (uint32_t)p.up_w, x = rem - y * (uint32_t)p.up_w;
-                    const float* up_row = p.up + ((size_t)img * (size_t)(p.up_hw >> 2) + (size_t)(y >> 1) * (size_t)(p.up_w >> 1) + (x >> 1)) * (size_t)p.up_ps;
-                    for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16<true>(e, res_phase, t_row, tl, ch, up_row);
                 } else {
                     for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
                 }
@@ -782,8 +803,9 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
 
     static std::atomic<unsigned long long> attr_seen{0};
     if (first_use_on_device(attr_seen)) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) { delete pl; return fail((int)e, "conv: smem attribute: %s", cudaGetErrorString(e)); }
     }
@@ -843,7 +865,7 @@ extern "C" int yms_conv_plan_run(const yms_conv_plan* pl, void* stream) {
     kp.prof = g_prof_buf;
     cudaError_t le = kp.pair
         ? launch_pdl_cluster(conv_gemm_pair_kernel, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, 2, pl->tm_x, pl->tm_x2, pl->tm_w, pl->tm_y, pl->tm_res, kp)
-        : launch_pdl(kp.dec.mode ? conv_gemm_kernel<true> : conv_gemm_kernel<false>, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
+        : launch_pdl(kp.dec.mode ? conv_gemm_kernel<1> : kp.up ? conv_gemm_kernel<2> : conv_gemm_kernel<0>, pl->grid, pl->threads, pl->smem, (cudaStream_t)stream, pl->tm_x, pl->tm_x2, pl->tm_w,
                      pl->tm_y, pl->tm_res, kp);
     if (le != cudaSuccess) return fail((int)le, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");
