@@ -67,6 +67,9 @@ typedef struct yms_conv_params {
                                          half of every weight tile; c_out <= 256, maps at least 9 pixels wide); for every other bf16-output
                                          convolution (1x1, 3x3/s2, two sources) 5 selects the CTA-pair variant of the generic kernel (two
                                          consecutive M tiles per cluster); 6 = that generic CTA-pair kernel for a 3x3/s1 layer.
+                                         7 = the CTA-pair halo kernel with virtual-row tiling, for maps whose height is not a multiple
+                                         of 16 (40, 20): the images are stacked H + 2 rows apart and cut into bands of exactly 16 rows, a
+                                         cluster takes one 8-pixel column of two consecutive bands (c_out <= 256, H >= 16).
                                          Results agree to fp32 accumulation order; used by the host-side per-layer autotuner. */
     /* tensors */
     const void* x;   int64_t x_pixel_stride;      /* bf16, elements between consecutive pixels   */

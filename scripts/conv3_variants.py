@@ -1,5 +1,5 @@
 """Device time of the 3x3/s1 convolution variants (yms_conv_params.variant: 1 generic implicit GEMM, 2 / 3 halo kernel with 1 / 2
-sub-tiles per item, 5 CTA-pair halo kernel) on the bench shapes of the `s` model at batch 32; each variant replayed 10x in a CUDA
+sub-tiles per item, 5 CTA-pair halo kernel, 6 generic CTA pair, 7 CTA-pair halo kernel with virtual-row tiling) on the bench shapes of the `s` model at batch 32; each variant replayed 10x in a CUDA
 graph.   python scripts/conv3_variants.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,7 +35,7 @@ for ci, co, hw, res in CASES:
     y = torch.empty(B, hw, hw, co, device=DEV, dtype=torch.bfloat16)
     r = torch.randn(B, hw, hw, co, generator=g).to(DEV).to(torch.bfloat16) if res else None
     out, ref = [], None
-    for v in (1, 2, 3, 5, 6):
+    for v in (1, 2, 3, 5, 6, 7):
         try:
             pl = ops.ConvPlan(x, w, b, y, ksize=3, stride=1, act=True, residual=r, variant=v)
         except YmsError as e:

@@ -38,7 +38,7 @@ for i, (st, nm) in enumerate(zip(prog.steps, prog.names)):
     st()
     torch.cuda.synchronize()
     b = buf.cpu().double()
-    act = b[:, 12] > 0
+    act = (b[:, 12] > 0) & (b[:, 0] > 0)               # CTAs that issued MMAs (the leaders of CTA pairs)
     n = int(act.sum())
     if n == 0:
         continue

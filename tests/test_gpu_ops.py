@@ -42,6 +42,7 @@ CONV_CASES = [
     ("3x3_128_128_w40", 4, 40, 40, 128, 128, 3, 1, 1, 1, 0, 0, 1),      # streamed weights, residual, slices, many items per CTA / cluster
     ("3x3_256_256_w20", 8, 20, 20, 256, 256, 3, 1, 1, 0, 0, 0, 0),
     ("3x3_64_144_w80", 2, 80, 80, 64, 144, 3, 1, 1, 0, 0, 0, 0),        # N = 144: three 64-channel output chunks, the last one partial
+    ("3x3_h18_res", 3, 18, 24, 64, 64, 3, 1, 1, 1, 0, 0, 0),            # variant 7: bands of 16 virtual rows over images 20 rows apart, the last band runs past the batch
 ]
 
 
@@ -53,7 +54,7 @@ def _variants(case):
         return (0,)
     if not (k == 3 and s == 1 and not cin2):
         return (0, 5)                                   # generic kernel: single CTA / CTA pair
-    return (0, 1, 2, 3, 5, 6) if cout <= 256 else (0, 1, 2, 3, 6)
+    return (0, 1, 2, 3, 5, 6, 7) if cout <= 256 else (0, 1, 2, 3, 6)       # 7: pair kernel, virtual-row tiling
 
 
 @pytest.mark.parametrize("case,variant", [(c, v) for c in CONV_CASES for v in _variants(c)],
@@ -82,7 +83,7 @@ def test_conv_gemm_matches_torch_fp32(ops, case, variant):
     try:
         ops.ConvPlan(x, wpk, bias, y, ksize=k, stride=s, act=bool(act), residual=r, x2=x2, variant=variant).run()
     except Exception as e:                                # the CTA-pair variants need two M tiles / sub-tiles: "unsupported" is the contract
-        if variant in (5, 6) and "code -2" in str(e):
+        if variant in (5, 6, 7) and "code -2" in str(e):
             pytest.skip(str(e))
         raise
     xin = x.float() if x2 is None else torch.cat([x.float(), x2.float()], -1)

@@ -323,11 +323,25 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 // CTAs (cta_group::2 loads, expect_tx of the pair's bytes by the leader's producer); tcgen05.commit arrives on the empty /
 // accumulator-full barriers of both CTAs (multicast); the epilogue groups of both CTAs arrive on the leader's
 // accumulator-empty barrier.  Same per-CTA shared-memory layout and ring discipline as conv3x3_kernel<1>.
+//
+// kVy, virtual-row tiling (variant 7) for maps whose height is not a multiple of 16 (40 -> 3 bands of 14 rows, 20 -> 2 of 10: up to
+// 37 % of every MMA's rows are padding, plus a sixth sub-tile column for five when pairing in x).  All images are stacked into ONE
+// column of virtual rows, vh = H + 2 apart -- the two extra rows are the zero padding below one image and above the next -- and
+// that column is cut into bands of exactly 16 rows; a cluster takes one 8-pixel column of two consecutive bands.  A band inside
+// one image loads its halo with the usual single box (rows H, H + 1 are out of bounds = zero-filled).  A band that crosses into the
+// next image loads its 18 halo rows one by one through a one-row box (tm_xr): two boxes would zero-fill each other.  The two dummy
+// output rows are computed and dropped: the epilogue stores the tile as a box into the first image (TMA clips the rows past its end) and
+// the next image's rows one by one (a box at a negative row is rejected by the hardware).
+template <bool kVy>
 __global__ void __launch_bounds__(kThreads3, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                     const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
-                    const __grid_constant__ Conv3Params p) {
+                    const __grid_constant__ CUtensorMap tm_xr, const __grid_constant__ CUtensorMap tm_rr,
+                    const __grid_constant__ CUtensorMap tm_yr, const __grid_constant__ Conv3Params p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;   // wait-cycle accumulators (dead code unless -DYMS_PROF)
+    (void)pw0; (void)pw1; (void)pw2; (void)pw3;
+    YMS_PROF_ONLY(const long long prof_t_entry = clock64(); long long* prof = (p.prof && blockIdx.x < kNumSMs) ? p.prof + 16 * blockIdx.x : nullptr;)
     const uint32_t base = smem_u32(smem_dyn);
     unsigned char* gbase = smem_dyn;
     if (base & 1023u) __trap();
@@ -355,6 +369,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
             if (p.has_res) prefetch_tmap(&tm_res);
+            if (kVy) { prefetch_tmap(&tm_xr); prefetch_tmap(&tm_yr); if (p.has_res) prefetch_tmap(&tm_rr); }
         }
         for (int i = lane; i < kNumBars; i += 32) {
             const bool is_tempty = i >= kBarTEmpty && i < kBarTEmpty + 4;
@@ -382,22 +397,45 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const uint32_t out_bytes = (uint32_t)(8 * p.th) * 128u;
     const int acc_stride = 512 / p.acc_stages;
     const int cid = (int)cluster_id_x(), ncl = (int)num_clusters_x();
+    YMS_PROF_ONLY(const long long prof_t_start = clock64();)
+    // kVy: this CTA's sub-tile of item t = column sx, band 2 * (t / super_x) + rank; the band's first virtual row = row y0 of image img
+    struct VTile { int sx, img, y0; };
+    auto vtile = [&](int t) {
+        VTile v;
+        const uint32_t bp = fast_div((uint32_t)t, p.mg_super_x);
+        v.sx = t - (int)bp * p.super_x;
+        const uint32_t v0 = (2u * bp + rank) * 16u;
+        v.img = (int)fast_div(v0, p.mg_vh);
+        v.y0 = (int)v0 - v.img * p.vh;
+        return v;
+    };
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs: own halo tile, own half of the weights) =================
         if (elect_one()) {
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             for (int t = cid; t < p.total_items; t += ncl) {
-                const Item it = decode_item(p, t);
+                const Item it = kVy ? Item{} : decode_item(p, t);
+                const VTile vt = kVy ? vtile(t) : VTile{};
                 for (int cb = 0; cb < p.kb; ++cb) {
-                    mbar_wait(bar(kBarAEmpty + as), aph ^ 1u);
+                    mbar_wait_acc(bar(kBarAEmpty + as), aph ^ 1u, pw0);
                     if (leader_cta) mbar_expect_tx(bar(kBarAFull + as), 2u * p.halo_bytes);
-                    tma_load_4d_2sm(smem_a + as * p.halo_stage, &tm_x, bar(kBarAFull + as),
-                                    cb * kBlockK, (it.sx * 2 + (int)rank) * 8 - 1, it.ty * p.th - 1, it.img);
+                    if (!kVy) {
+                        tma_load_4d_2sm(smem_a + as * p.halo_stage, &tm_x, bar(kBarAFull + as),
+                                        cb * kBlockK, (it.sx * 2 + (int)rank) * 8 - 1, it.ty * p.th - 1, it.img);
+                    } else if (vt.y0 + 16 <= p.vh - 1) {             // halo rows y0 - 1 .. y0 + 16 <= H + 1: one image, rows >= H read as zeros
+                        tma_load_4d_2sm(smem_a + as * p.halo_stage, &tm_x, bar(kBarAFull + as), cb * kBlockK, vt.sx * 8 - 1, vt.y0 - 1, vt.img);
+                    } else {
+                        for (int r = 0; r < 18; ++r) {               // (image, y) of halo row r; rows H, H + 1 and images >= batch are zero fill
+                            const int y = vt.y0 - 1 + r, wrap = y >= p.vh - 1 ? 1 : 0;       // virtual row vh - 1 is row -1 of the next image
+                            tma_load_4d_2sm(smem_a + as * p.halo_stage + r * (kHaloPitch * 128), &tm_xr, bar(kBarAFull + as),
+                                            cb * kBlockK, vt.sx * 8 - 1, y - wrap * p.vh, vt.img + wrap);
+                        }
+                    }
                     if (++as == p.a_stages) { as = 0; aph ^= 1u; }
                     if (!p.resident) {
                         for (int ky = 0; ky < 3; ++ky) {             // a slot = the 3 taps of a kernel row: a third of the ring hand-shakes
-                            mbar_wait(bar(kBarBEmpty + bs), bph ^ 1u);
+                            mbar_wait_acc(bar(kBarBEmpty + bs), bph ^ 1u, pw1);
                             if (leader_cta) mbar_expect_tx(bar(kBarBFull + bs), 6u * (uint32_t)(half_n * 128));
                             for (int kx = 0; kx < 3; ++kx)
                                 tma_load_3d_2sm(smem_b + (bs * 3 + kx) * b_tile_bytes, &tm_w, bar(kBarBFull + bs), cb * kBlockK, (int)rank * half_n, ky * 3 + kx);
@@ -406,6 +444,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     }
                 }
             }
+            YMS_PROF_ONLY(if (prof) { prof[4] = clock64() - prof_t_start; prof[5] = pw0; prof[6] = pw1; })
         }
     } else if (warp == 1) {
         // ================= MMA issuer: one elected thread of the LEADER =================
@@ -415,18 +454,18 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             const uint64_t hi_b = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             const uint32_t halo16 = (uint32_t)p.halo_stage >> 4;
             const uint32_t btile16 = (uint32_t)b_tile_bytes >> 4;
-            if (p.resident) { mbar_wait(bar(kBarW), 0u); tc_fence_after(); }
+            if (p.resident) { mbar_wait_acc(bar(kBarW), 0u, pw2); tc_fence_after(); }
             const uint32_t a0_16 = (smem_a & 0x3FFFFu) >> 4, b0_16 = (smem_b & 0x3FFFFu) >> 4;
             const int tail = ((p.c_in - (p.kb - 1) * kBlockK) + 15) >> 4;
             int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
             int acc = 0; uint32_t acc_phase = 0;
             uint32_t a_ready = 0, b_ready = 0;
             for (int t = cid; t < p.total_items; t += ncl) {
-                mbar_wait(bar(kBarTEmpty + acc), acc_phase ^ 1u);
+                mbar_wait_acc(bar(kBarTEmpty + acc), acc_phase ^ 1u, pw3);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_stride);
                 for (int cb = 0; cb < p.kb; ++cb) {
-                    if (!a_ready) mbar_wait(bar(kBarAFull + as), aph);
+                    if (!a_ready) mbar_wait_acc(bar(kBarAFull + as), aph, pw0);
                     tc_fence_after();
                     int nas = as + 1; uint32_t naph = aph;
                     if (nas == p.a_stages) { nas = 0; naph ^= 1u; }
@@ -452,7 +491,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     } else {
                         #pragma unroll 1
                         for (int ky = 0; ky < 3; ++ky) {
-                            if (!b_ready) mbar_wait(bar(kBarBFull + bs), bph);
+                            if (!b_ready) mbar_wait_acc(bar(kBarBFull + bs), bph, pw1);
                             tc_fence_after();
                             int nbs = bs + 1; uint32_t nbph = bph;
                             if (nbs == p.b_stages) { nbs = 0; nbph ^= 1u; }
@@ -479,6 +518,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 }
                 if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1u; }
             }
+            YMS_PROF_ONLY(if (prof) { prof[0] = clock64() - prof_t_start; prof[1] = pw0; prof[2] = pw1; prof[3] = pw3; prof[10] = pw2;
+                                      prof[11] = (p.total_items - cid + ncl - 1) / ncl; prof[9] = prof_t_start - prof_t_entry; })
         }
         __syncwarp();
     } else {
@@ -495,27 +536,36 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         e.bar_id = 1 + grp;
         e.leader = ((warp - 2) & 3) == 0 && lane == 0;
         e.row = (warp & 3) * 32 + lane;
+        e.tm_res_row = &tm_rr; e.tm_y_row = &tm_yr;
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(stage_id * acc_stride);
         const int n_chunks = (p.block_n + 63) >> 6;
         uint32_t res_phase = 0u, acc_phase = 0u;
         for (int t = cid + stage_id * ncl; t < p.total_items; t += p.acc_stages * ncl) {
-            const Item it = decode_item(p, t);
-            mbar_wait(bar(kBarTFull + stage_id), acc_phase);
+            EpiTile tl;
+            if (kVy) {
+                const VTile vt = vtile(t);
+                tl.n0 = 0; tl.x0 = vt.sx * 8; tl.y0 = vt.y0; tl.img = vt.img; tl.vh = p.vh;
+            } else {
+                const Item it = decode_item(p, t);
+                tl.n0 = 0; tl.x0 = (it.sx * 2 + (int)rank) * 8; tl.y0 = it.ty * p.th; tl.img = it.img;
+            }
+            mbar_wait_acc(bar(kBarTFull + stage_id), acc_phase, pw0);
             acc_phase ^= 1u;
             tc_fence_after();
-            EpiTile tl;
-            tl.n0 = 0; tl.x0 = (it.sx * 2 + (int)rank) * 8; tl.y0 = it.ty * p.th; tl.img = it.img;
-            if (tl.x0 < p.out_w)                                     // (the pair's second sub-tile may lie outside the image)
-                for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16(e, res_phase, t_lane, tl, ch);
+            if (kVy ? (tl.img < p.batch && (tl.y0 < p.out_h || tl.img + 1 < p.batch))      // (a band past the last image / of dummy rows only)
+                    : (tl.x0 < p.out_w))                             // (the pair's second sub-tile may lie outside the image)
+                for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16<false, kVy>(e, res_phase, t_lane, tl, ch);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar(kBarTEmpty + stage_id), 0u);
         }
         if (e.leader) tma_store_wait_read<0>();
+        YMS_PROF_ONLY(if (prof && warp == 2 && lane == 0) { prof[7] = clock64() - prof_t_start; prof[8] = pw0; })
     }
 
     tc_fence_before();
     __syncthreads();
+    YMS_PROF_ONLY(if (prof && threadIdx.x == 0) prof[12] = clock64() - prof_t_entry;)
     cluster_sync_all();                                    // nobody leaves (or frees TMEM) while the peer may still signal or be read
     if (warp == 1) {
         tc_fence_after();
@@ -535,6 +585,13 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.th = ceil_div(H, ny);
     k.tiles_x = ceil_div(W, 8);
     k.tiles_y = ceil_div(H, k.th);
+    // variant 7: the pair kernel with virtual-row tiling (bands of exactly 16 rows over the stacked images, see conv3x3_pair_kernel)
+    k.vy = (q->variant == 7) ? 1 : 0;
+    if (k.vy) {
+        k.th = 16; k.vh = H + 2;
+        k.bands = ceil_div(q->batch * k.vh, 16);
+        k.mg_vh = fast_div_magic(k.vh);
+    }
     k.c_in = q->c_in; k.c_out = q->c_out; k.kb = ceil_div(q->c_in, kBlockK);
     if (q->c_out <= 256) {
         k.n_tiles = 1; k.block_n = ((q->c_out + 15) / 16) * 16;
@@ -552,8 +609,9 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.halo_bytes = (uint32_t)(kHaloPitch * (k.th + 2) * 128);
     k.desc_mode = 0;
     // variant 5: CTA-pair kernel (conv3x3_pair_kernel): two x-adjacent sub-tiles per cluster, half a weight tile per CTA
-    k.pair = (q->variant == 5) ? 1 : 0;
-    if (k.pair && (k.n_tiles != 1 || k.tiles_x < 2)) return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 5): needs c_out <= 256 and a map at least 9 pixels wide");
+    k.pair = (q->variant == 5 || k.vy) ? 1 : 0;
+    if (k.pair && (k.n_tiles != 1 || (!k.vy && k.tiles_x < 2))) return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 5): needs c_out <= 256 and a map at least 9 pixels wide");
+    if (k.vy && (k.bands < 2 || H < 16)) return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 7): needs maps at least 16 rows high (a band may span two images, not three)");
 
     const int b_tile = ((k.pair ? k.block_n / 2 : k.block_n) * 128 + 1023) & ~1023;
     const int halo_stage = (int)k.halo_bytes;
@@ -614,6 +672,7 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     k.planes = k.sub; k.wtiles = 9; k.pitch = kHaloPitch; k.s2pair = 0;
     k.super_x = ceil_div(k.tiles_x, k.pair ? 2 : k.sub);
     k.total_items = k.super_x * k.tiles_y * k.batch * k.n_tiles;
+    if (k.vy) { k.super_x = k.tiles_x; k.total_items = k.tiles_x * ceil_div(k.bands, 2); }     // item = one sub-tile column x two consecutive bands
     k.mg_n_tiles = fast_div_magic(k.n_tiles); k.mg_super_x = fast_div_magic(k.super_x); k.mg_tiles_y = fast_div_magic(k.tiles_y);
     pl->grid = k.total_items < kNumSMs ? k.total_items : kNumSMs;
     if (k.pair) pl->grid = 2 * (k.total_items < kNumSMs / 2 ? k.total_items : kNumSMs / 2);          // clusters of two CTAs
@@ -633,6 +692,12 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         if ((rc = encode_act(&pl->tm_res, q->residual, q->c_out, q->res_pixel_stride, q->batch, H, W, false, 8, k.th, 1, "res"))) return rc;
     } else pl->tm_res = pl->tm_y;
     pl->tm_x2 = pl->tm_x;
+    pl->tm_res2 = pl->tm_res; pl->tm_y2 = pl->tm_y;
+    if (k.vy) {
+        if ((rc = encode_act(&pl->tm_y2, q->y, q->c_out, q->y_pixel_stride, q->batch, H, W, false, 8, 1, 1, "y(row)"))) return rc;                                            // one-row boxes for the bands that cross an image boundary
+        if ((rc = encode_act(&pl->tm_x2, q->x, q->c_in, q->x_pixel_stride, q->batch, H, W, false, kHaloPitch, 1, 1, "x(halo row)"))) return rc;
+        if (q->residual && (rc = encode_act(&pl->tm_res2, q->residual, q->c_out, q->res_pixel_stride, q->batch, H, W, false, 8, 1, 1, "res(row)"))) return rc;
+    }
 
     const double m = (double)q->batch * H * W;
     pl->flops = 2.0 * m * q->c_out * (double)q->c_in * 9.0;
@@ -643,7 +708,8 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         if (e != cudaSuccess) return fail((int)e, "conv3x3: smem attribute: %s", cudaGetErrorString(e));
     }
     return 0;
@@ -719,7 +785,8 @@ int conv3_plan_run(const yms_conv_plan* pl0, cudaStream_t stream) {
     plc.k3.prof = g_prof_buf;
     const yms_conv_plan* pl = &plc;
     cudaError_t le;
-    if (pl->k3.pair) le = launch_pdl_cluster(conv3x3_pair_kernel, pl->grid, 64 + pl->k3.epi_groups * kEpiGroupThreads, pl->smem, stream, 2, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
+    if (pl->k3.pair) le = launch_pdl_cluster(pl->k3.vy ? conv3x3_pair_kernel<true> : conv3x3_pair_kernel<false>, pl->grid, 64 + pl->k3.epi_groups * kEpiGroupThreads, pl->smem, stream, 2,
+                                             pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->tm_x2, pl->tm_res2, pl->tm_y2, pl->k3);
     else if (pl->k3.sub == 1) le = launch_pdl(conv3x3_kernel<1>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else if (pl->k3.sub == 2) le = launch_pdl(conv3x3_kernel<2>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);
     else le = launch_pdl(conv3x3_kernel<4>, pl->grid, kThreads3, pl->smem, stream, pl->tm_x, pl->tm_w, pl->tm_y, pl->tm_res, pl->k3);

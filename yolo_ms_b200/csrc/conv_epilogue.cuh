@@ -16,7 +16,9 @@ constexpr int kEpiGroupThreads = 128;
 constexpr int kConvThreads = 64 + kEpiGroups * kEpiGroupThreads;      // producer warp + MMA warp + 16 epilogue warps
 constexpr int kStageOutBytes = 128 * 128;                             // one 128-row x 64-channel bf16 staging tile
 
-struct EpiTile { int n0, x0, y0, img; };
+// vh (virtual-row tiling, see conv3x3_pair_kernel<true>): images are `vh` virtual rows apart, y0 is the tile's first virtual row
+// inside image `img`; a tile whose 16 rows run past vh continues in image img + 1 at row y0 - vh.
+struct EpiTile { int n0, x0, y0, img; int vh = 0; };
 
 __device__ __forceinline__ unsigned long long epi_pack(uint32_t lo, uint32_t hi) {
     unsigned long long r;
@@ -42,6 +44,8 @@ struct EpiShared {
     int bar_id;                // named barrier of the group
     bool leader;               // thread that issues the group's TMA traffic
     int row;                   // accumulator lane == tile row of this thread
+    const CUtensorMap* tm_res_row = nullptr;   // kVy: residual / output maps with a one-row (8 pixel) box
+    const CUtensorMap* tm_y_row = nullptr;
 };
 
 // bf16 output of ONE 64-channel chunk through swizzled staging + TMA store (+ residual TMA-loaded
@@ -60,7 +64,7 @@ __device__ __forceinline__ void up_regs_load(UpRegs& r, const float* chunk_row, 
     for (int g = 0; g < 4; ++g)
         if (g < groups) { r.u[2 * g] = __ldg(q + 4 * g); r.u[2 * g + 1] = __ldg(q + 4 * g + 1); }
 }
-template <bool kUp = false>
+template <bool kUp = false, bool kVy = false>
 __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t& res_phase, uint32_t t_row, const EpiTile& tl, int ch,
                                                     UpRegs* up = nullptr, const float* next = nullptr, int next_groups = 0) {
     {
@@ -73,7 +77,15 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
         if (e.has_res) {
             if (e.leader) {
                 mbar_expect_tx(e.res_bar, e.out_bytes);
-                tma_load_4d(e.s_out, e.tm_res, e.res_bar, tl.n0 + cbase, tl.x0, tl.y0, tl.img);
+                if (kVy && tl.y0 + 16 > tl.vh) {
+                    // the tile spans two images: row by row (a second BOX would zero-fill what the first one loaded)
+                    for (int j = 0; j < 16; ++j) {
+                        const int y = tl.y0 + j, wrap = y >= tl.vh ? 1 : 0;
+                        tma_load_4d(e.s_out + (uint32_t)j * 1024u, e.tm_res_row, e.res_bar, tl.n0 + cbase, tl.x0, y - wrap * tl.vh, tl.img + wrap);
+                    }
+                } else {
+                    tma_load_4d(e.s_out, e.tm_res, e.res_bar, tl.n0 + cbase, tl.x0, tl.y0, tl.img);
+                }
             }
             mbar_wait(e.res_bar, res_phase);
             res_phase ^= 1u;
@@ -169,7 +181,10 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
         fence_proxy_async_smem();                            // generic-proxy writes -> async proxy (TMA)
         group_bar_sync(e.bar_id);
         if (e.leader) {
-            tma_store_4d(e.tm_y, e.s_out, tl.n0 + cbase, tl.x0, tl.y0, tl.img);
+            tma_store_4d(e.tm_y, e.s_out, tl.n0 + cbase, tl.x0, tl.y0, tl.img);          // rows past the image (dummy rows, the next image's) are clipped
+            if (kVy)                                         // the next image's rows, one by one (TMA stores reject negative coordinates)
+                for (int j = tl.vh - tl.y0; j < 16; ++j)
+                    tma_store_4d(e.tm_y_row, e.s_out + (uint32_t)j * 1024u, tl.n0 + cbase, tl.x0, j - (tl.vh - tl.y0), tl.img + 1);
             tma_store_commit();
         }
     }

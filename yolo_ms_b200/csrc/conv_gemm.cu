@@ -676,7 +676,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
     yms_conv_plan* pl = new (std::nothrow) yms_conv_plan();
     if (!pl) return fail(YMS_E_ARG, "conv: out of host memory");
     pl->kind = 0;
-    if (q->variant < 0 || q->variant > 6) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..6"); }
+    if (q->variant < 0 || q->variant > 7) { delete pl; return fail(YMS_E_ARG, "conv: variant must be 0..7"); }
     if (q->variant == 4) {                                       // stride-2 pair-line kernel, pair-packed weights (conv3x3.cu)
         int rc4 = conv3_s2pair_plan_init(pl, q);
         if (rc4) { delete pl; return rc4; }
@@ -689,6 +689,7 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
         *out = pl;
         return 0;
     }
+    if (q->variant == 7) { delete pl; return fail(YMS_E_UNSUPPORTED, "conv (variant 7): 3x3 stride-1 convolutions with bf16 output only"); }
     ConvKernelParams& kp = pl->kp;
     memset(&kp, 0, sizeof(kp));
     const int out_h = q->in_h / q->stride, out_w = q->in_w / q->stride;

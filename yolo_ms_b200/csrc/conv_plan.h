@@ -69,6 +69,8 @@ struct Conv3Params {
     int desc_mode;                             // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7
     int s2pair;                                // stride-2 pair-line mode (c_in == 32, dense input): see conv3x3.cu
     int pair;                                  // CTA-pair kernel (cta_group::2, M = 256): two x-adjacent sub-tiles per cluster, each CTA half of B
+    int vy, vh, bands;                         // pair kernel, virtual-row tiling: images vh = H + 2 virtual rows apart, `bands` bands of 16 rows
+    uint32_t mg_vh;
     int epi_groups;                            // pair kernel: epilogue groups of 4 warps (4, or 2 when that is what lets the weights stay resident)
     int planes;                                // TMA boxes per A stage (== sub, or 2 parity planes in s2pair mode)
     int wtiles;                                // resident weight tiles per 64-channel block (9 taps, or 6 pair-packed tiles)
@@ -124,7 +126,7 @@ int conv3_plan_run(const ::yms_conv_plan* pl, cudaStream_t stream);
 }  // namespace yms
 
 struct yms_conv_plan {
-    CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_res;
+    CUtensorMap tm_x, tm_x2, tm_w, tm_y, tm_res, tm_res2, tm_y2;
     int kind;                   // 0: generic implicit GEMM, 1: 3x3 stride-1 halo kernel
     yms::ConvKernelParams kp;
     yms::Conv3Params k3;

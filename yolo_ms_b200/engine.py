@@ -168,7 +168,7 @@ class Program:
             return cand
         return default_plan
 
-    def _autotune(self, default_plan, kw, variants=(1, 2, 3, 5, 6), tag="3x3"):
+    def _autotune(self, default_plan, kw, variants=(1, 2, 3, 5, 6, 7), tag="3x3"):
         """Measure, don't guess: the 3x3/s1 layers have three tcgen05 implementations whose winner depends on the map
         size (tile quantisation on 20x20 / 40x40 maps), c_out (resident vs streamed weights) and the tile count per CTA.
         Each candidate runs on the layer's real buffers at program-build time; the fastest one is kept."""
