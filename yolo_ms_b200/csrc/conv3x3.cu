@@ -365,6 +365,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int lane = threadIdx.x & 31;
     const int gps = p.epi_groups / p.acc_stages;           // epilogue groups sharing one accumulator stage
 
+    // this thread's first bias value: the load is issued BEFORE the cluster barrier, whose set-up then hides its DRAM latency
+    const float bias0 = ((int)threadIdx.x < p.c_out) ? p.bias[threadIdx.x] : 0.f;
     if (warp == 0) {
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
@@ -387,7 +389,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 tma_load_3d_2sm(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, (int)rank * half_n, tap);
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512);
-    for (int i = threadIdx.x; i < p.bias_pad; i += (int)blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+    if ((int)threadIdx.x < p.bias_pad) s_bias[threadIdx.x] = p.act ? 0.5f * bias0 : bias0;
+    for (int i = (int)(threadIdx.x + blockDim.x); i < p.bias_pad; i += (int)blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

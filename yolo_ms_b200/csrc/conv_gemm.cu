@@ -177,6 +177,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Bias: the epilogue threads fetch it into registers HERE and stage it in shared memory after the CTA-wide sync, among
+    // themselves.  Staged before the sync, its DRAM round trip (~1 us: a few hundred bytes nobody else touched since the last step)
+    // was the longest leg of a prologue that every launch pays and that, at one CTA per SM, nothing overlaps.
+    const int et = (int)threadIdx.x - 64, n_et = (int)blockDim.x - 64;
+    float bias_r0 = 0.f, bias_r1 = 0.f;
+    if (et >= 0) {
+        if (et < p.c_out) bias_r0 = p.bias[et];
+        if (et + n_et < p.c_out) bias_r1 = p.bias[et + n_et];
+    }
     if (warp == 0) {                                  // one barrier per lane: the prologue is paid by every launch
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
@@ -203,7 +212,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         __syncwarp();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-    for (int i = threadIdx.x; i < p.bias_pad; i += blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -309,6 +317,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int grp = (warp - 2) >> 2;
         const int gps = p.epi_groups / p.acc_stages;       // groups sharing one accumulator stage
         const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        if (et < p.bias_pad) s_bias[et] = p.act ? 0.5f * bias_r0 : bias_r0;
+        if (et + n_et < p.bias_pad) s_bias[et + n_et] = p.act ? 0.5f * bias_r1 : bias_r1;
+        for (int i = et + 2 * n_et; i < p.bias_pad; i += n_et) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+        epi_all_bar_sync(n_et);                            // the staged bias is visible to every epilogue warp
         {
             EpiShared e;
             e.tm_y = &tm_y; e.tm_res = &tm_res;
@@ -427,6 +439,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int lane = threadIdx.x & 31;
     const int gps = p.epi_groups / p.acc_stages;
 
+    // this thread's first bias value: the load is issued BEFORE the cluster barrier, whose set-up then hides its DRAM latency
+    const float bias0 = ((int)threadIdx.x < p.c_out) ? p.bias[threadIdx.x] : 0.f;
     if (warp == 0) {
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
@@ -451,7 +465,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                 kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, (int)rank * half_n, tap);
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-    for (int i = threadIdx.x; i < p.bias_pad; i += blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
+    if ((int)threadIdx.x < p.bias_pad) s_bias[threadIdx.x] = p.act ? 0.5f * bias0 : bias0;
+    for (int i = (int)(threadIdx.x + blockDim.x); i < p.bias_pad; i += (int)blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

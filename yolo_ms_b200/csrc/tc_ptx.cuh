@@ -175,6 +175,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void group_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// all epilogue warps of a CTA (`threads` of them); named barrier 15 (the per-group barriers are 1 .. 8)
+__device__ __forceinline__ void epi_all_bar_sync(int threads) { asm volatile("bar.sync 15, %0;" ::"r"(threads) : "memory"); }
 // exact t / d for t * d < 2^32 with magic = ceil(2^32 / d) (host side: fast_div_magic); d == 1 -> magic 0
 __device__ __forceinline__ uint32_t fast_div(uint32_t t, uint32_t magic) { return magic ? __umulhi(t, magic) : t; }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }

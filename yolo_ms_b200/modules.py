@@ -272,14 +272,24 @@ class MSBlock(_Compiled):
             P.ms_layer(pl)
         return dst
 
-    def emit(self, P, x, out=None):
+    def emit(self, P, x, out=None, up_src=None):
         """One buffer [x0 | x1 | x2 | y1 | y2] (5c channels): in_conv fills the first three slots, the branches the last two.
         The branch inputs x1 + x0 and x2 + y1 are then ADJACENT slices ([x0|x1], [x2|y1]): one 2c-wide source each, and
-        out_conv reads cat[x0, y1, y2] as x0 plus the adjacent pair [y1|y2]."""
+        out_conv reads cat[x0, y1, y2] as x0 plus the adjacent pair [y1|y2].
+        up_src (neck only): as in C2f.emit -- x is [upsample2x(up_src) | skip] with the first slot NOT written, and in_conv is
+        split into a half-resolution fp32 partial-sum conv over up_src plus a conv over the skip that adds it in its epilogue."""
         c = self.mid_channels
         b, hh, ww, _ = x.shape
         y = P.buf(b, hh, ww, 5 * c)
-        self.in_conv.emit(P, x, out=y[..., :3 * c])
+        if up_src is not None:
+            c_low = up_src.shape[-1]
+            wf, bf = self.in_conv.folded()
+            part = P.buf(b, hh // 2, ww // 2, wf.shape[0], dtype=torch.float32)
+            P.conv(pack_weight(wf[:, :c_low].contiguous()), torch.zeros_like(bf), up_src, part, ksize=1, stride=1, act=False)
+            P.conv(pack_weight(wf[:, c_low:].contiguous()), bf.contiguous(), x[..., c_low:], y[..., :3 * c], ksize=1, stride=1,
+                   act=self.in_conv.has_act, up_add=part)
+        else:
+            self.in_conv.emit(P, x, out=y[..., :3 * c])
         for bi, layers in enumerate(self.branches):
             t = y[..., 0:2 * c] if bi == 0 else y[..., 2 * c:4 * c]
             for li, layer in enumerate(layers):
@@ -449,16 +459,20 @@ class Neck(_Compiled):
         c3, c4, c5 = self.channels
         cat1, cat2, cat3, cat4 = self.__dict__.pop("_cats")
         on_output = on_output or (lambda i, t: None)
-        # C2f consumers take the upsample + concat inside their first 1x1 conv (C2f.emit, up_src); other blocks read the
+        # C2f / MS-Block consumers take the upsample + concat inside their first 1x1 conv (emit(..., up_src)); other blocks read the
         # concat buffer that upsample2x_kernel fills
-        def foldable(block, c_out):       # limits of yms_conv_plan_add_upsampled
-            return FUSE_UPSAMPLE and isinstance(block, C2f) and c_out % (16 if c_out <= 256 else 64) == 0
-        if foldable(self.c2f_1, c4):
+        def foldable(block):              # limits of yms_conv_plan_add_upsampled
+            if not FUSE_UPSAMPLE or not isinstance(block, (C2f, MSBlock)):
+                return False
+            first = block.conv1 if isinstance(block, C2f) else block.in_conv
+            c_out = first.conv.out_channels
+            return first.conv.groups == 1 and c_out % (16 if c_out <= 256 else 64) == 0
+        if foldable(self.c2f_1):
             res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:], up_src=cat4[..., c4:])
         else:
             self.up.emit(P, cat4[..., c4:], cat1[..., :c5])
             res2 = self.c2f_1.emit(P, cat1, out=cat3[..., c3:])
-        if foldable(self.c2f_2, c3):
+        if foldable(self.c2f_2):
             out1 = self.c2f_2.emit(P, cat2, up_src=res2)
         else:
             self.up.emit(P, res2, cat2[..., :c4])
