@@ -29,7 +29,7 @@ buf = torch.zeros(148, 16, dtype=torch.int64, device=dev)
 assert lib.yms_debug_set_prof(buf.data_ptr()) == 1, "not a -DYMS_PROF build"
 for st in prog.steps: st()
 torch.cuda.synchronize()
-hdr = "| # | step | ctas | tiles/cta | kernel kcyc | prologue | mma total | mma: wait A | wait B | wait acc-empty | wait W | mma busy | prod wait A-empty | wait B-empty | epi wait acc-full |"
+hdr = "| # | step | ctas | tiles/cta | kernel kcyc | prologue (barriers / tmem alloc / sync) | mma total | mma: wait A | wait B | wait acc-empty | wait W | mma busy | prod wait A-empty | wait B-empty | epi wait acc-full |"
 lines = [f"# role cycle accounting: version {version}, batch {B}, {HW}x{HW}, block {block} (kcycles, mean over CTAs)", "", hdr, "|" + "---|" * 15]
 for i, (st, nm) in enumerate(zip(prog.steps, prog.names)):
     if not nm.startswith("conv"):
@@ -44,7 +44,7 @@ for i, (st, nm) in enumerate(zip(prog.steps, prog.names)):
         continue
     m = b[act].mean(0) / 1e3
     busy = m[0] - m[1] - m[2] - m[3] - m[10]
-    lines.append(f"| {i} | {nm} | {n} | {m[11]*1e3:.1f} | {m[12]:.1f} | {m[9]:.1f} | {m[0]:.1f} | {m[1]:.1f} | {m[2]:.1f} | {m[3]:.1f} | {m[10]:.1f} | {busy:.1f} | {m[5]:.1f} | {m[6]:.1f} | {m[8]:.1f} |")
+    lines.append(f"| {i} | {nm} | {n} | {m[11]*1e3:.1f} | {m[12]:.1f} | {m[9]:.1f} ({m[15]:.1f} / {m[14]:.1f} / {m[13]:.1f}) | {m[0]:.1f} | {m[1]:.1f} | {m[2]:.1f} | {m[3]:.1f} | {m[10]:.1f} | {busy:.1f} | {m[5]:.1f} | {m[6]:.1f} | {m[8]:.1f} |")
 lib.yms_debug_set_prof(None)
 open(out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))

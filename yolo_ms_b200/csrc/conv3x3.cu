@@ -91,6 +91,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    const BiasRegs bias_regs = bias_fetch(p.bias, p.c_out);          // staged by the epilogue warps after the CTA-wide sync
     if (warp == 0) {                                  // barriers initialised lane-parallel: the prologue is paid by every launch
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
@@ -113,7 +114,6 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         __syncwarp();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-    for (int i = threadIdx.x; i < p.bias_pad; i += kThreads3) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -265,6 +265,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const int grp = (warp - 2) >> 2;
         const int gps = kEpiGroups / p.acc_stages;         // groups sharing one accumulator stage
         const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        bias_stage(s_bias, bias_regs, p.bias, p.c_out, p.bias_pad, p.act);
         {
             EpiShared e;
             e.tm_y = &tm_y; e.tm_res = &tm_res;
@@ -365,8 +366,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int lane = threadIdx.x & 31;
     const int gps = p.epi_groups / p.acc_stages;           // epilogue groups sharing one accumulator stage
 
-    // this thread's first bias value: the load is issued BEFORE the cluster barrier, whose set-up then hides its DRAM latency
-    const float bias0 = ((int)threadIdx.x < p.c_out) ? p.bias[threadIdx.x] : 0.f;
+    const BiasRegs bias_regs = bias_fetch(p.bias, p.c_out);          // staged by the epilogue warps after the CTA-wide sync
     if (warp == 0) {
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w); prefetch_tmap(&tm_y);
@@ -389,8 +389,6 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                 tma_load_3d_2sm(smem_b + (tap * p.kb + cb) * b_tile_bytes, &tm_w, bar(kBarW), cb * kBlockK, (int)rank * half_n, tap);
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 512);
-    if ((int)threadIdx.x < p.bias_pad) s_bias[threadIdx.x] = p.act ? 0.5f * bias0 : bias0;
-    for (int i = (int)(threadIdx.x + blockDim.x); i < p.bias_pad; i += (int)blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -529,6 +527,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         // ================= epilogue (both CTAs, each its own 128 accumulator rows = its own sub-tile) =================
         const int grp = (warp - 2) >> 2;
         const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        bias_stage(s_bias, bias_regs, p.bias, p.c_out, p.bias_pad, p.act);
         EpiShared e;
         e.tm_y = &tm_y; e.tm_res = &tm_res;
         e.res_bar = bar(kBarRes + grp);

@@ -34,6 +34,29 @@ __device__ __forceinline__ unsigned long long epi_fma2(unsigned long long a, uns
     return r;
 }
 
+// Bias staging, split around the CTA-wide sync of the prologue.  The epilogue threads (threadIdx.x >= 64 in every conv kernel)
+// fetch the bias into registers BEFORE that sync (bias_fetch) and stage it in shared memory after it, among themselves
+// (bias_stage, in the epilogue branch).  Staged before the sync, its DRAM round trip -- a few hundred bytes nobody touched since
+// the previous step -- was the longest leg of a prologue that every launch pays and that, at one CTA per SM, nothing overlaps.
+struct BiasRegs { float r0, r1; };
+__device__ __forceinline__ BiasRegs bias_fetch(const float* bias, int c_out) {
+    const int et = (int)threadIdx.x - 64, n_et = (int)blockDim.x - 64;
+    BiasRegs b{0.f, 0.f};
+    if (et >= 0) {
+        if (et < c_out) b.r0 = bias[et];
+        if (et + n_et < c_out) b.r1 = bias[et + n_et];
+    }
+    return b;
+}
+// act: the SiLU epilogue works on h = x / 2, so 0.5 * bias is what it adds
+__device__ __forceinline__ void bias_stage(float* s_bias, const BiasRegs& b, const float* bias, int c_out, int bias_pad, int act) {
+    const int et = (int)threadIdx.x - 64, n_et = (int)blockDim.x - 64;
+    if (et < bias_pad) s_bias[et] = act ? 0.5f * b.r0 : b.r0;
+    if (et + n_et < bias_pad) s_bias[et + n_et] = act ? 0.5f * b.r1 : b.r1;
+    for (int i = et + 2 * n_et; i < bias_pad; i += n_et) s_bias[i] = (i < c_out) ? (act ? 0.5f * bias[i] : bias[i]) : 0.f;
+    epi_all_bar_sync(n_et);                                // visible to every epilogue warp
+}
+
 struct EpiShared {
     const CUtensorMap* tm_y; const CUtensorMap* tm_res;
     uint32_t res_bar;          // mbarrier of this group for the residual TMA load

@@ -177,15 +177,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // Bias: the epilogue threads fetch it into registers HERE and stage it in shared memory after the CTA-wide sync, among
-    // themselves.  Staged before the sync, its DRAM round trip (~1 us: a few hundred bytes nobody else touched since the last step)
-    // was the longest leg of a prologue that every launch pays and that, at one CTA per SM, nothing overlaps.
-    const int et = (int)threadIdx.x - 64, n_et = (int)blockDim.x - 64;
-    float bias_r0 = 0.f, bias_r1 = 0.f;
-    if (et >= 0) {
-        if (et < p.c_out) bias_r0 = p.bias[et];
-        if (et + n_et < p.c_out) bias_r1 = p.bias[et + n_et];
-    }
+    const BiasRegs bias_regs = bias_fetch(p.bias, p.c_out);          // staged by the epilogue warps after the CTA-wide sync
     if (warp == 0) {                                  // one barrier per lane: the prologue is paid by every launch
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
@@ -199,6 +191,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         fence_barrier_init();
         __syncwarp();
+        YMS_PROF_ONLY(if (prof && lane == 0) prof[15] = clock64() - prof_t_entry;)
         // weights are constants of the program: fetched before the CTA-wide sync (overlapping the TMEM allocation and the
         // bias staging) and BEFORE the grid dependency resolves, i.e. while the previous layer is still draining
         if (p.resident && elect_one()) {
@@ -211,11 +204,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         __syncwarp();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+        YMS_PROF_ONLY(if (prof && lane == 0) prof[14] = clock64() - prof_t_entry;)
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    YMS_PROF_ONLY(if (prof && threadIdx.x == 64) prof[13] = clock64() - prof_t_entry;)
     pdl_launch_dependents();
     pdl_wait();                                   // previous grid complete: its outputs may be read, ours written
 
@@ -317,10 +314,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         const int grp = (warp - 2) >> 2;
         const int gps = p.epi_groups / p.acc_stages;       // groups sharing one accumulator stage
         const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
-        if (et < p.bias_pad) s_bias[et] = p.act ? 0.5f * bias_r0 : bias_r0;
-        if (et + n_et < p.bias_pad) s_bias[et + n_et] = p.act ? 0.5f * bias_r1 : bias_r1;
-        for (int i = et + 2 * n_et; i < p.bias_pad; i += n_et) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
-        epi_all_bar_sync(n_et);                            // the staged bias is visible to every epilogue warp
+        bias_stage(s_bias, bias_regs, p.bias, p.c_out, p.bias_pad, p.act);
         {
             EpiShared e;
             e.tm_y = &tm_y; e.tm_res = &tm_res;
@@ -439,8 +433,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int lane = threadIdx.x & 31;
     const int gps = p.epi_groups / p.acc_stages;
 
-    // this thread's first bias value: the load is issued BEFORE the cluster barrier, whose set-up then hides its DRAM latency
-    const float bias0 = ((int)threadIdx.x < p.c_out) ? p.bias[threadIdx.x] : 0.f;
+    const BiasRegs bias_regs = bias_fetch(p.bias, p.c_out);          // staged by the epilogue warps after the CTA-wide sync
     if (warp == 0) {
         if (lane == 0) {
             prefetch_tmap(&tm_x); prefetch_tmap(&tm_w);
@@ -465,8 +458,6 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                                 kb < p.kb1 ? kb * kBlockK : p.c_in1 + (kb - p.kb1) * kBlockK, (int)rank * half_n, tap);
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-    if ((int)threadIdx.x < p.bias_pad) s_bias[threadIdx.x] = p.act ? 0.5f * bias0 : bias0;
-    for (int i = (int)(threadIdx.x + blockDim.x); i < p.bias_pad; i += (int)blockDim.x) s_bias[i] = (i < p.c_out) ? (p.act ? 0.5f * p.bias[i] : p.bias[i]) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -571,6 +562,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         // ================= epilogue (both CTAs, each its own tile) =================
         const int grp = (warp - 2) >> 2;
         const int stage_id = grp / gps, sub_id = grp - stage_id * gps;
+        bias_stage(s_bias, bias_regs, p.bias, p.c_out, p.bias_pad, p.act);
         EpiShared e;
         e.tm_y = &tm_y; e.tm_res = &tm_res;
         e.res_bar = res_bar(grp);
