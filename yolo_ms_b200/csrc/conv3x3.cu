@@ -330,9 +330,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 // column of virtual rows, vh = H + 2 apart -- the two extra rows are the zero padding below one image and above the next -- and
 // that column is cut into bands of exactly 16 rows; a cluster takes one 8-pixel column of two consecutive bands.  A band inside
 // one image loads its halo with the usual single box (rows H, H + 1 are out of bounds = zero-filled).  A band that crosses into the
-// next image loads its 18 halo rows one by one through a one-row box (tm_xr): two boxes would zero-fill each other.  The two dummy
+// next image loads its 18 halo rows two by two through a two-row box (tm_xr; H is even, so a row pair never spans two images): two boxes would zero-fill each other.  The two dummy
 // output rows are computed and dropped: the epilogue stores the tile as a box into the first image (TMA clips the rows past its end) and
-// the next image's rows one by one (a box at a negative row is rejected by the hardware).
+// the next image's rows two by two (a box at a negative row is rejected by the hardware).
 template <bool kVy>
 __global__ void __launch_bounds__(kThreads3, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -427,7 +427,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
                     } else if (vt.y0 + 16 <= p.vh - 1) {             // halo rows y0 - 1 .. y0 + 16 <= H + 1: one image, rows >= H read as zeros
                         tma_load_4d_2sm(smem_a + as * p.halo_stage, &tm_x, bar(kBarAFull + as), cb * kBlockK, vt.sx * 8 - 1, vt.y0 - 1, vt.img);
                     } else {
-                        for (int r = 0; r < 18; ++r) {               // (image, y) of halo row r; rows H, H + 1 and images >= batch are zero fill
+                        // TWO rows per box: H is even, so the bands (16 rows) and the images (vh rows) start at even virtual rows and
+                        // a pair of halo rows (odd, even) never spans two images; rows H, H + 1 and images >= batch are zero fill
+                        for (int r = 0; r < 18; r += 2) {
                             const int y = vt.y0 - 1 + r, wrap = y >= p.vh - 1 ? 1 : 0;       // virtual row vh - 1 is row -1 of the next image
                             tma_load_4d_2sm(smem_a + as * p.halo_stage + r * (kHaloPitch * 128), &tm_xr, bar(kBarAFull + as),
                                             cb * kBlockK, vt.sx * 8 - 1, y - wrap * p.vh, vt.img + wrap);
@@ -613,7 +615,8 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     // variant 5: CTA-pair kernel (conv3x3_pair_kernel): two x-adjacent sub-tiles per cluster, half a weight tile per CTA
     k.pair = (q->variant == 5 || k.vy) ? 1 : 0;
     if (k.pair && (k.n_tiles != 1 || (!k.vy && k.tiles_x < 2))) return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 5): needs c_out <= 256 and a map at least 9 pixels wide");
-    if (k.vy && (k.bands < 2 || H < 16)) return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 7): needs maps at least 16 rows high (a band may span two images, not three)");
+    if (k.vy && (k.bands < 2 || H < 16 || (H & 1)))
+        return fail(YMS_E_UNSUPPORTED, "conv3x3 (variant 7): needs maps of even height, at least 16 rows (a band may span two images, not three; two-row boxes)");
 
     const int b_tile = ((k.pair ? k.block_n / 2 : k.block_n) * 128 + 1023) & ~1023;
     const int halo_stage = (int)k.halo_bytes;
@@ -696,9 +699,10 @@ int conv3_plan_init(yms_conv_plan* pl, const yms_conv_params* q) {
     pl->tm_x2 = pl->tm_x;
     pl->tm_res2 = pl->tm_res; pl->tm_y2 = pl->tm_y;
     if (k.vy) {
-        if ((rc = encode_act(&pl->tm_y2, q->y, q->c_out, q->y_pixel_stride, q->batch, H, W, false, 8, 1, 1, "y(row)"))) return rc;                                            // one-row boxes for the bands that cross an image boundary
-        if ((rc = encode_act(&pl->tm_x2, q->x, q->c_in, q->x_pixel_stride, q->batch, H, W, false, kHaloPitch, 1, 1, "x(halo row)"))) return rc;
-        if (q->residual && (rc = encode_act(&pl->tm_res2, q->residual, q->c_out, q->res_pixel_stride, q->batch, H, W, false, 8, 1, 1, "res(row)"))) return rc;
+        // two-row boxes for the bands that cross an image boundary
+        if ((rc = encode_act(&pl->tm_y2, q->y, q->c_out, q->y_pixel_stride, q->batch, H, W, false, 8, 2, 1, "y(rows)"))) return rc;
+        if ((rc = encode_act(&pl->tm_x2, q->x, q->c_in, q->x_pixel_stride, q->batch, H, W, false, kHaloPitch, 2, 1, "x(halo rows)"))) return rc;
+        if (q->residual && (rc = encode_act(&pl->tm_res2, q->residual, q->c_out, q->res_pixel_stride, q->batch, H, W, false, 8, 2, 1, "res(rows)"))) return rc;
     }
 
     const double m = (double)q->batch * H * W;

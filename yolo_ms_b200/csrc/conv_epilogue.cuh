@@ -67,7 +67,7 @@ struct EpiShared {
     int bar_id;                // named barrier of the group
     bool leader;               // thread that issues the group's TMA traffic
     int row;                   // accumulator lane == tile row of this thread
-    const CUtensorMap* tm_res_row = nullptr;   // kVy: residual / output maps with a one-row (8 pixel) box
+    const CUtensorMap* tm_res_row = nullptr;   // kVy: residual / output maps with a two-row (2 x 8 pixel) box
     const CUtensorMap* tm_y_row = nullptr;
 };
 
@@ -101,8 +101,9 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
             if (e.leader) {
                 mbar_expect_tx(e.res_bar, e.out_bytes);
                 if (kVy && tl.y0 + 16 > tl.vh) {
-                    // the tile spans two images: row by row (a second BOX would zero-fill what the first one loaded)
-                    for (int j = 0; j < 16; ++j) {
+                    // the tile spans two images: two rows at a time (a second full BOX would zero-fill what the first one loaded;
+                    // y0 and vh are even, so a row pair stays in one image)
+                    for (int j = 0; j < 16; j += 2) {
                         const int y = tl.y0 + j, wrap = y >= tl.vh ? 1 : 0;
                         tma_load_4d(e.s_out + (uint32_t)j * 1024u, e.tm_res_row, e.res_bar, tl.n0 + cbase, tl.x0, y - wrap * tl.vh, tl.img + wrap);
                     }
@@ -205,8 +206,8 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
         group_bar_sync(e.bar_id);
         if (e.leader) {
             tma_store_4d(e.tm_y, e.s_out, tl.n0 + cbase, tl.x0, tl.y0, tl.img);          // rows past the image (dummy rows, the next image's) are clipped
-            if (kVy)                                         // the next image's rows, one by one (TMA stores reject negative coordinates)
-                for (int j = tl.vh - tl.y0; j < 16; ++j)
+            if (kVy)                                         // the next image's rows, two by two (TMA stores reject negative coordinates)
+                for (int j = tl.vh - tl.y0; j < 16; j += 2)
                     tma_store_4d(e.tm_y_row, e.s_out + (uint32_t)j * 1024u, tl.n0 + cbase, tl.x0, j - (tl.vh - tl.y0), tl.img + 1);
             tma_store_commit();
         }
