@@ -722,11 +722,24 @@ extern "C" int yms_conv_plan_create(const yms_conv_params* q, yms_conv_plan** ou
         kp.block_n = ((q->c_out + 15) / 16) * 16;
     } else {
         // several N tiles: every tile must be whole 64-channel store boxes (a partial box would
-        // spill into the next tile's channels); pick the width that pads c_out the least.
+        // spill into the next tile's channels); among the widths that pad c_out the least, the one with the shortest makespan
+        // over the persistent CTAs / clusters: waves x (tile width + a fixed per-tile cost of ~32 columns).  A 20 x 20 map at
+        // batch 32 has 100 M tiles: 512 channels as 2 x 256 are 200 tiles = 2 waves of 256 columns on 148 CTAs, as 4 x 128 they
+        // are 3 waves of 128.
         int best_pad = 1 << 30;
         for (int bn = 64; bn <= 256; bn += 64) {
-            int padded = ceil_div(q->c_out, bn) * bn;
-            if (padded <= best_pad) { best_pad = padded; kp.block_n = bn; }
+            const int padded = ceil_div(q->c_out, bn) * bn;
+            if (padded < best_pad) best_pad = padded;
+        }
+        const int m_tiles0 = kp.tiles_x * kp.tiles_y * kp.batch;
+        const bool pair0 = (q->variant == 5 || q->variant == 6);
+        const long long m_items = pair0 ? ceil_div(m_tiles0, 2) : m_tiles0, ctas = pair0 ? kNumSMs / 2 : kNumSMs;
+        long long best_cost = -1;
+        for (int bn = 64; bn <= 256; bn += 64) {
+            if (ceil_div(q->c_out, bn) * bn != best_pad) continue;
+            const long long items = m_items * ceil_div(q->c_out, bn);
+            const long long cost = ((items + ctas - 1) / ctas) * (bn + 32);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; kp.block_n = bn; }
         }
         kp.n_tiles = ceil_div(q->c_out, kp.block_n);
     }
