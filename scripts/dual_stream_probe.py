@@ -58,3 +58,22 @@ for parts in (2, 4):
     t2 = timed(step)
     print(f"{parts} streams, batch {B // parts} each: {t2:.4f} ms/step, {B / t2 * 1e3:.0f} images/s", flush=True)
     del ms
+# two FULL batches in flight: step i + 1 on the other stream, no dependency between them (the NMS of one step, which leaves most SMs
+# idle while its longest class chain finishes, then runs next to the other step's convolutions)
+ms = [make(B, 7 + i) for i in range(2)]
+streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+main = torch.cuda.current_stream(dev)
+
+
+def step2():
+    ev = torch.cuda.Event(); ev.record(main)
+    for (mm, xx), st in zip(ms, streams):
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            mm.detect(xx, 0.25, 0.45)
+    for st in streams:
+        main.wait_stream(st)
+
+
+t3 = timed(step2)
+print(f"2 streams, batch {B} each (two steps in flight): {t3 / 2:.4f} ms/step, {2 * B / t3 * 1e3:.0f} images/s", flush=True)

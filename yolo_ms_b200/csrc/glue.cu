@@ -61,41 +61,43 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(__nv_bfloat16* buf, long
     *reinterpret_cast<uint4*>(o + 3 * c) = m13;
 }
 
-// Shared-memory version for maps up to 48x48: one CTA = one image x 8 channels.  The three chained
-// 5x5 pools are computed as chained SEPARABLE passes (row max of 5, then column max of 5) on the
+// Shared-memory version for maps up to 48x48: one CTA = one image x 8 * V channels (V = 2 when c % 16 == 0: the two 16-byte
+// vectors of a pixel are read / written by adjacent threads, i.e. whole 32-byte sectors; with V = 1 every access moves half a
+// sector).  The three chained 5x5 pools are computed as chained SEPARABLE passes (row max of 5, then column max of 5) on the
 // plane held in shared memory: 30 smem reads per output instead of 169 global reads.
 constexpr int kPoolMaxHW = 48 * 48;
+template <int V>
 __global__ void __launch_bounds__(256) sppf_pool_smem_kernel(__nv_bfloat16* buf, long long ps, int h, int w, int c) {
     extern __shared__ uint4 s_pool[];
     const int g = blockIdx.x, b = blockIdx.y;
-    const int hw = h * w;
+    const int hw = h * w, n = hw * V;                              // item i = (pixel i / V, vector i % V)
     uint4* s_a = s_pool;
-    uint4* s_t = s_pool + hw;
-    __nv_bfloat16* base = buf + (size_t)b * hw * ps + g * 8;
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) s_a[i] = *reinterpret_cast<const uint4*>(base + (size_t)i * ps);
+    uint4* s_t = s_pool + n;
+    __nv_bfloat16* base = buf + (size_t)b * hw * ps + g * (8 * V);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_a[i] = *reinterpret_cast<const uint4*>(base + (size_t)(i / V) * ps + (i % V) * 8);
     __syncthreads();
     for (int level = 1; level <= 3; ++level) {
-        for (int i = threadIdx.x; i < hw; i += blockDim.x) {       // row pass: s_t = max over x-2..x+2 of s_a
-            const int y = i / w, x = i - y * w;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {        // row pass: s_t = max over x-2..x+2 of s_a
+            const int px = i / V, y = px / w, x = px - y * w;
             uint4 m = s_a[i];
             #pragma unroll
             for (int d = 1; d <= 2; ++d) {
-                if (x - d >= 0) m = max_bf16x8(m, s_a[i - d]);
-                if (x + d < w) m = max_bf16x8(m, s_a[i + d]);
+                if (x - d >= 0) m = max_bf16x8(m, s_a[i - d * V]);
+                if (x + d < w) m = max_bf16x8(m, s_a[i + d * V]);
             }
             s_t[i] = m;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < hw; i += blockDim.x) {       // column pass: s_a = max over y-2..y+2 of s_t
-            const int y = i / w;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {        // column pass: s_a = max over y-2..y+2 of s_t
+            const int px = i / V, y = px / w;
             uint4 m = s_t[i];
             #pragma unroll
             for (int d = 1; d <= 2; ++d) {
-                if (y - d >= 0) m = max_bf16x8(m, s_t[i - d * w]);
-                if (y + d < h) m = max_bf16x8(m, s_t[i + d * w]);
+                if (y - d >= 0) m = max_bf16x8(m, s_t[i - d * w * V]);
+                if (y + d < h) m = max_bf16x8(m, s_t[i + d * w * V]);
             }
             s_a[i] = m;
-            *reinterpret_cast<uint4*>(base + (size_t)i * ps + (size_t)level * c) = m;
+            *reinterpret_cast<uint4*>(base + (size_t)px * ps + (size_t)level * c + (i % V) * 8) = m;
         }
         __syncthreads();
     }
@@ -154,14 +156,17 @@ extern "C" int yms_sppf_pool(void* buf, int64_t ps, int batch, int h, int w, int
     if (batch <= 0 || h <= 0 || w <= 0 || c <= 0 || (c % 8) != 0) return fail(YMS_E_ARG, "sppf: bad sizes (c % 8 == 0)");
     if (!buf || !aligned16(buf) || (ps % 8) != 0 || ps < 4 * (int64_t)c) return fail(YMS_E_ARG, "sppf: bad buffer");
     if (h * w <= kPoolMaxHW) {
-        dim3 grid(c / 8, batch);
-        const size_t smem = (size_t)2 * h * w * sizeof(uint4);
+        const int v = (c % 16 == 0 && 2 * h * w <= kPoolMaxHW) ? 2 : 1;
+        dim3 grid(c / (8 * v), batch);
+        const size_t smem = (size_t)2 * v * h * w * sizeof(uint4);
         static std::atomic<unsigned long long> attr_seen{0};
         if (first_use_on_device(attr_seen)) {
-            cudaError_t e = cudaFuncSetAttribute(sppf_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPoolMaxHW * (int)sizeof(uint4));
+            cudaError_t e = cudaFuncSetAttribute(sppf_pool_smem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPoolMaxHW * (int)sizeof(uint4));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(sppf_pool_smem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPoolMaxHW * (int)sizeof(uint4));
             if (e != cudaSuccess) return fail((int)e, "sppf: smem attribute");
         }
-        sppf_pool_smem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(buf), ps, h, w, c);
+        if (v == 2) sppf_pool_smem_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(buf), ps, h, w, c);
+        else sppf_pool_smem_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(buf), ps, h, w, c);
         return check_launch("sppf_pool_smem_kernel");
     }
     long long total = (long long)h * w * (c / 8);
