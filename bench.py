@@ -273,13 +273,17 @@ def e2e_u8(ctx, model, B, HW, steps, warmup, seed, sample_clocks):
     c0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
     c1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
     fin = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    h0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    h1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
 
     def loop(n):
         for i in range(n):
             b = i & 1
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(ev_done[b])                 # input buffer b free again (step i-2 has consumed it)
+                h0[i].record(copy_s)
                 u8in[b].copy_(u8_host, non_blocking=True)
+                h1[i].record(copy_s)
                 ev_copied[b].record(copy_s)
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(ev_copied[b])
@@ -310,12 +314,14 @@ def e2e_u8(ctx, model, B, HW, steps, warmup, seed, sample_clocks):
     clocks = sampler.stop(tw0, time.time()) if sampler is not None else None
     comp = sorted(c0[i].elapsed_time(c1[i]) for i in range(steps))
     gaps = sorted(fin[i - 1].elapsed_time(fin[i]) for i in range(1, steps))
+    h2d = sorted(h0[i].elapsed_time(h1[i]) for i in range(steps))
     pct = lambda v, q: round(v[min(len(v) - 1, int(q * len(v)))], 4) if v else None
     kept = int(cnt_host[(steps - 1) & 1].sum())
     return {"value": round(ctx.world * B / (wall_ms / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": int(u8_host.numel()),
             "d2h_bytes_per_step": int(B * A * 6 * 4 + B * 4), "ms_per_step": round(wall_ms, 4), "steps": steps,
             "step_ms_p50": pct(gaps, 0.5), "step_ms_p95": pct(gaps, 0.95),
             "compute_ms_per_step": round(sum(comp) / len(comp), 4), "compute_ms_p50": pct(comp, 0.5), "compute_ms_p95": pct(comp, 0.95),
+            "h2d_ms_p50": pct(h2d, 0.5), "h2d_GBs_p50": round(u8_host.numel() / (pct(h2d, 0.5) * 1e6), 1) if h2d and pct(h2d, 0.5) else None,
             "clocks": clocks, "kept_detections_last_step": kept,
             "host_calls_per_step": "1 graph launch + 1 H2D + 2 D2H copies; 0 allocations",
             "pipelined": "H2D of step i+1 and the read-back of step i-1 overlap compute of step i (3 streams, 2 buffers)",
