@@ -98,7 +98,8 @@ def test_conv_gemm_matches_torch_fp32(ops, case, variant):
 
 
 @pytest.mark.parametrize("B,H,W,c_low,c_skip,cout", [(2, 40, 40, 512, 256, 256), (3, 20, 28, 256, 128, 128), (1, 80, 80, 64, 32, 32),
-                                                     (2, 10, 6, 576, 384, 384)])
+                                                     (2, 10, 6, 576, 384, 384),
+                                                     (12, 96, 96, 32, 32, 144)])    # several tiles per epilogue group (partial sums prefetched across tiles), partial last chunk
 def test_conv1x1_over_upsampled_concat(ops, B, H, W, c_low, c_skip, cout):
     """Neck: conv1x1(cat[upsample2x(a), b]) computed as upsample2x(W_a . a) + W_b . b (yms_conv_plan_add_upsampled): a linear fp32
     1x1 plan at half resolution, then the plan over b adds it before bias + SiLU.  Reference: plain PyTorch fp32 on the same

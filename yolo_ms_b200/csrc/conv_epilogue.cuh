@@ -202,6 +202,14 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
             }
         }
+        if (kUp) {                                           // a partial chunk (fewer than four groups) refilled only its own groups
+            #pragma unroll
+            for (int q16 = 0; q16 < 4; ++q16)
+                if (q16 < next_groups && cbase + q16 * 16 >= e.block_n) {
+                    up->u[2 * q16] = __ldg(reinterpret_cast<const float4*>(next) + 4 * q16 + up_half);
+                    up->u[2 * q16 + 1] = __ldg(reinterpret_cast<const float4*>(next) + 4 * q16 + up_half + 1);
+                }
+        }
         fence_proxy_async_smem();                            // generic-proxy writes -> async proxy (TMA)
         group_bar_sync(e.bar_id);
         if (e.leader) {
