@@ -42,6 +42,8 @@ CONV_CASES = [
     ("3x3_128_128_w40", 4, 40, 40, 128, 128, 3, 1, 1, 1, 0, 0, 1),      # streamed weights, residual, slices, many items per CTA / cluster
     ("3x3_256_256_w20", 8, 20, 20, 256, 256, 3, 1, 1, 0, 0, 0, 0),
     ("3x3_64_144_w80", 2, 80, 80, 64, 144, 3, 1, 1, 0, 0, 0, 0),        # N = 144: three 64-channel output chunks, the last one partial
+    ("3x3_h16", 3, 16, 16, 64, 64, 3, 1, 1, 0, 0, 0, 0),                # variant 7 at its smallest map: vh = 18, a band's halo wraps exactly once
+    ("1x1_64_1152", 1, 20, 20, 64, 1152, 1, 1, 1, 0, 0, 0, 0),          # more bias values than two per epilogue thread (staging loop)
     ("3x3_h18_res", 3, 18, 24, 64, 64, 3, 1, 1, 1, 0, 0, 0),            # variant 7: bands of 16 virtual rows over images 20 rows apart, the last band runs past the batch
 ]
 
