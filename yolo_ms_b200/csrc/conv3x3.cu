@@ -558,7 +558,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             tc_fence_after();
             if (kVy ? (tl.img < p.batch && (tl.y0 < p.out_h || tl.img + 1 < p.batch))      // (a band past the last image / of dummy rows only)
                     : (tl.x0 < p.out_w))                             // (the pair's second sub-tile may lie outside the image)
-                for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16<false, kVy>(e, res_phase, t_lane, tl, ch);
+                for (int ch = sub_id; ch < n_chunks; ch += gps) epilogue_chunk_bf16<false, kVy ? 1 : 0>(e, res_phase, t_lane, tl, ch);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar(kBarTEmpty + stage_id), 0u);

@@ -18,7 +18,8 @@ constexpr int kStageOutBytes = 128 * 128;                             // one 128
 
 // vh (virtual-row tiling, see conv3x3_pair_kernel<true>): images are `vh` virtual rows apart, y0 is the tile's first virtual row
 // inside image `img`; a tile whose 16 rows run past vh continues in image img + 1 at row y0 - vh.
-struct EpiTile { int n0, x0, y0, img; int vh = 0; };
+// kStore == 2 (the stem's half tiles): rows 0..63 are stored at (x0, y0, img), rows 64..127 at (x1, y1, img1).
+struct EpiTile { int n0, x0, y0, img; int vh = 0; int x1 = 0, y1 = 0, img1 = 0; };
 
 __device__ __forceinline__ unsigned long long epi_pack(uint32_t lo, uint32_t hi) {
     unsigned long long r;
@@ -87,10 +88,12 @@ __device__ __forceinline__ void up_regs_load(UpRegs& r, const float* chunk_row, 
     for (int g = 0; g < 4; ++g)
         if (g < groups) { r.u[2 * g] = __ldg(q + 4 * g); r.u[2 * g + 1] = __ldg(q + 4 * g + 1); }
 }
-template <bool kUp = false, bool kVy = false>
+// kStore: 0 one box per tile, 1 virtual-row tiling (conv3x3_pair_kernel<true>), 2 two half-tile boxes (stem_tma_kernel)
+template <bool kUp = false, int kStore = 0>
 __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t& res_phase, uint32_t t_row, const EpiTile& tl, int ch,
                                                     UpRegs* up = nullptr, const float* next = nullptr, int next_groups = 0) {
     {
+        constexpr bool kVy = kStore == 1;
         const int cbase = ch * 64;
         // kUp: lanes 2i and 2i+1 are the two x-neighbours of ONE half-resolution pixel (tiles start at even pixels, W is even), i.e.
         // they need the same 64 bytes per 16-channel group: each holds HALF of them (32 B) and the pair swaps halves with shuffles.
@@ -214,6 +217,7 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const EpiShared& e, uint32_t
         group_bar_sync(e.bar_id);
         if (e.leader) {
             tma_store_4d(e.tm_y, e.s_out, tl.n0 + cbase, tl.x0, tl.y0, tl.img);          // rows past the image (dummy rows, the next image's) are clipped
+            if (kStore == 2) tma_store_4d(e.tm_y, e.s_out + 64u * 128u, tl.n0 + cbase, tl.x1, tl.y1, tl.img1);
             if (kVy)                                         // the next image's rows, two by two (TMA stores reject negative coordinates)
                 for (int j = tl.vh - tl.y0; j < 16; j += 2)
                     tma_store_4d(e.tm_y_row, e.s_out + (uint32_t)j * 1024u, tl.n0 + cbase, tl.x0, j - (tl.vh - tl.y0), tl.img + 1);

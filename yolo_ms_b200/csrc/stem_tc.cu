@@ -263,8 +263,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__
 // ------------------------------------------------------------------------------------------------------------------
 // TMA-fed variant (default when the image width is a multiple of 4).  The gather kernel above is bound by the latency of
 // its per-thread loads (27 scalar loads per output pixel, one tile in flight per warp).  Here the raw image rows of a
-// tile travel through their own TMA ring: a tile is 128 consecutive output pixels of ONE output row, i.e. input rows
-// 2*oy-1 .. 2*oy+1 and input columns 2*x0-1 .. 2*x0+256, fetched as two boxes (one per 64-pixel half, each starting at a
+// tile travel through their own TMA ring.  A tile is TWO independent half tiles of 64 consecutive output pixels of one output
+// row each (half h of tile t = half 2t + h of the row-major list of halves: a 320-pixel row is five halves, so whole-row tiles
+// of 128 pixels would leave a sixth of the MMA rows, converter threads and epilogue lanes idle); a half needs input rows
+// 2*oy-1 .. 2*oy+1 and input columns 2*x0-1 .. 2*x0+128, fetched as one box (starting at a
 // 16-byte aligned column 4 elements / bytes before the first tap so that TMA alignment rules hold); padding is the TMA
 // zero fill (fp32 input) or an explicit post-normalisation zero (uint8 input).  12 converter warps (3 tiles in flight) read
 // their 27 taps from shared memory, convert to bf16 and build the K-major UMMA tile exactly like the gather producers; the
@@ -288,7 +290,7 @@ constexpr int kRawBoxU8 = 3 * kU8BoxW * 4;  // 3 rows x 512 B
 
 struct StemTmaParams {
     float scale[3], shift[3];
-    int batch, in_h, in_w, out_h, out_w, c_out, nxb, nyp, total_tiles;     // nxb: 128-pixel tiles per output row; nyp = out_h
+    int batch, in_h, in_w, out_h, out_w, c_out, nh, nyp, total_tiles;      // nh: 64-pixel half tiles per output row; nyp = out_h
     const float* weight; const float* bias;
 };
 
@@ -342,10 +344,12 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // a tile = 128 consecutive output pixels of one output row; half h = pixels [64h, 64h+64) = one TMA box of raw rows
-    auto tile_coord = [&](long long t, int& b, int& oy, int& x0) {
-        const uint32_t q = (uint32_t)t / (uint32_t)p.nxb;
-        x0 = (int)((uint32_t)t - q * (uint32_t)p.nxb) * 128;
+    // half h of tile t = half 2t + h of the row-major list: 64 consecutive output pixels of one output row = one TMA box of raw
+    // rows (a half past the end of the list has b == batch: its loads are zero fill, its store is clipped)
+    auto half_coord = [&](long long t, int h, int& b, int& oy, int& x0) {
+        const uint32_t idx = (uint32_t)(2 * t + h);
+        const uint32_t q = idx / (uint32_t)p.nh;
+        x0 = (int)(idx - q * (uint32_t)p.nh) * 64;
         b = (int)(q / (uint32_t)p.out_h);
         oy = (int)(q - (uint32_t)b * (uint32_t)p.out_h);
     };
@@ -357,15 +361,15 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++seq) {
                 const int stage = seq % kRawStages;
                 const uint32_t phase = (uint32_t)(seq / kRawStages) & 1u;
-                int b, oy, x0; tile_coord(t, b, oy, x0);
                 mbar_wait(rempty_bar(stage), phase ^ 1u);
                 mbar_expect_tx(rfull_bar(stage), kU8 ? 2u * (uint32_t)kRawBoxU8 : 2u * 4896u);
                 const uint32_t dst = smem_raw + stage * kRawStage;
                 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    int b, oy, x0; half_coord(t, h, b, oy, x0);
                     // box origin 16 B before the first tap (TMA needs a 16-byte aligned origin): 4 floats / 16 bytes
-                    if (kU8) tma_load_4d(dst + h * kRawBox, &tm_in, rfull_bar(stage), (6 * x0 - 16) / 4 + 96 * h, 2 * oy - 1, 0, b);
-                    else tma_load_4d(dst + h * kRawBox, &tm_in, rfull_bar(stage), 2 * x0 - 4 + 128 * h, 2 * oy - 1, 0, b);
+                    if (kU8) tma_load_4d(dst + h * kRawBox, &tm_in, rfull_bar(stage), (6 * x0 - 16) / 4, 2 * oy - 1, 0, b);
+                    else tma_load_4d(dst + h * kRawBox, &tm_in, rfull_bar(stage), 2 * x0 - 4, 2 * oy - 1, 0, b);
                 }
             }
         }
@@ -379,13 +383,14 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         for (long long t = (long long)blockIdx.x + (long long)grp * gridDim.x; t < p.total_tiles; t += (long long)kConvGroups * gridDim.x, seq += kConvGroups) {
             const int rstage = seq % kRawStages;
             const uint32_t rphase = (uint32_t)(seq / kRawStages) & 1u;
-            int b, oy, x0; tile_coord(t, b, oy, x0);
+            int b, oy, x0; half_coord(t, half, b, oy, x0);           // this thread's half tile
+            (void)b;
             mbar_wait(rfull_bar(rstage), rphase);
             const unsigned char* raw = g_raw + rstage * kRawStage + half * kRawBox;
             float v[27];
             if (kU8) {
                 const int off = 6 * rl + 13, off4 = off & ~3, sh = (off & 3) * 8;    // window starts 16 bytes before byte 3*(2*xh - 1) + 3
-                const bool left = (x0 + r == 0);
+                const bool left = (x0 + rl == 0);
                 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + ky * (kU8BoxW * 4) + off4);
@@ -479,12 +484,13 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const int n_chunks = (n_pad + 63) >> 6;
         uint32_t res_phase = 0u, acc_phase = 0u;
         for (long long t = (long long)blockIdx.x + (long long)grp * gridDim.x; t < p.total_tiles; t += (long long)kTmaEpiGroups * gridDim.x) {
-            int b, oy, x0; tile_coord(t, b, oy, x0);
-            EpiTile tl; tl.n0 = 0; tl.x0 = x0; tl.y0 = oy; tl.img = b;
+            EpiTile tl; tl.n0 = 0;
+            half_coord(t, 0, tl.img, tl.y0, tl.x0);
+            half_coord(t, 1, tl.img1, tl.y1, tl.x1);
             mbar_wait(tfull_bar(grp), acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
-            for (int ch = 0; ch < n_chunks; ++ch) epilogue_chunk_bf16(e, res_phase, t_row, tl, ch);
+            for (int ch = 0; ch < n_chunks; ++ch) epilogue_chunk_bf16<false, 2>(e, res_phase, t_row, tl, ch);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(grp));
@@ -514,7 +520,7 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
         static thread_local struct Cache2 { const void* in; const void* y; int64_t ps; int b, h, w, c, u8; CUtensorMap min, my; bool ok; } c2 = {};
         const void* in = xu8 ? (const void*)xu8 : (const void*)x;
         if (!(c2.ok && c2.in == in && c2.y == y && c2.ps == y_ps && c2.b == batch && c2.h == in_h && c2.w == in_w && c2.c == c_out && c2.u8 == (xu8 ? 1 : 0))) {
-            int rc = encode_act(&c2.my, y, c_out, y_ps, batch, out_h, out_w, /*flat=*/false, out_w < 128 ? out_w : 128, 1, 1, "stem y");
+            int rc = encode_act(&c2.my, y, c_out, y_ps, batch, out_h, out_w, /*flat=*/false, out_w < 64 ? out_w : 64, 1, 1, "stem y (half tile)");
             if (rc) return rc;
             auto fn = get_encode();
             if (!fn) return fail(YMS_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
@@ -539,20 +545,19 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
         memset(&q, 0, sizeof(q));
         if (xu8) for (int c = 0; c < 3; ++c) { q.scale[c] = 1.0f / (255.0f * stdv[c]); q.shift[c] = -mean[c] / stdv[c]; }
         q.batch = batch; q.in_h = in_h; q.in_w = in_w; q.out_h = out_h; q.out_w = out_w; q.c_out = c_out;
-        q.nxb = (out_w + 127) / 128; q.nyp = out_h;
-        const long long tiles = (long long)q.nxb * out_h * batch;
+        q.nh = (out_w + 63) / 64; q.nyp = out_h;
+        const long long tiles = ((long long)q.nh * out_h * batch + 1) / 2;
         if (tiles >= (1LL << 31)) return fail(YMS_E_UNSUPPORTED, "stem: too many tiles");
         q.total_tiles = (int)tiles;
         q.weight = weight; q.bias = bias;
         const size_t raw = (size_t)kRawStages * 2 * (xu8 ? kRawBoxU8 : kRawBoxF32);
         const size_t smem2 = 1024 + kTmaStages * kATile + 8192 + kTmaEpiGroups * kStageOutBytes + raw + 192 * 4 +
                              (2 * kTmaStages + 2 * kTmaEpiGroups + 2 * kRawStages) * 8 + 16;
-        static bool attr2 = false;
-        if (!attr2) {
+        static std::atomic<unsigned long long> attr2_seen{0};
+        if (first_use_on_device(attr2_seen)) {
             cudaError_t e = cudaFuncSetAttribute(stem_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return fail((int)e, "stem: smem attribute: %s", cudaGetErrorString(e));
-            attr2 = true;
         }
         const int grid2 = q.total_tiles < kNumSMs ? q.total_tiles : kNumSMs;
         if (xu8) stem_tma_kernel<true><<<grid2, kStemTmaThreads, smem2, stream>>>(c2.min, c2.my, q);
