@@ -28,6 +28,7 @@ print("kept per image (first 4):", cnt[:4].tolist())
 for i, nm in enumerate(names):
     col = d[:, i][b[:, i + 1] > 0]
     if nm != "-" and len(col): print(f"{nm:24s} mean {col.mean()/1e3:8.1f} kcyc  max {col.max()/1e3:8.1f} kcyc")
+srt = b[:, 12] - b[:, 2]; print("sort: warp sorts of segments / runs mean %.1f max %.1f kcyc, rank merges mean %.1f max %.1f kcyc" % (srt.mean()/1e3, srt.max()/1e3, (b[:, 3] - b[:, 12]).mean()/1e3, (b[:, 3] - b[:, 12]).max()/1e3))
 tot = (b[:, 7] - b[:, 0]); print("per-CTA total kcyc (first 16 CTAs = 4 images):", [round(float(v) / 1e3) for v in tot[:16]]); print("total to stamp7: mean %.1f max %.1f kcyc" % (tot.mean()/1e3, tot.max()/1e3))
 
 # chunk trace of the largest class of CTA 0 (profiling build): start of the chunk's scan, predecessors final, own result published

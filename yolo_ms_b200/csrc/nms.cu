@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(NmsArgs a) {
             }
         }
         __syncthreads();
+        NMS_STAMP(12);
         if (maxlen) {
             bool in_scratch = false;
             for (int w = kWarpSortMax; w < maxlen; w <<= 1) {
