@@ -233,10 +233,11 @@ def test_stem_conv(ops, cout):
     assert rel_l2(y, ref32) < 1e-2
 
 
-@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 256, 32), (1, 96, 320, 48), (2, 32, 640, 32), (1, 64, 260, 16)])
+@pytest.mark.parametrize("B,H,W,cout", [(2, 64, 256, 32), (1, 96, 320, 48), (2, 32, 640, 32), (1, 64, 260, 16),
+                                          (1, 6, 320, 16)])      # nine half tiles: the last tile has one half past the end of the batch
 def test_stem_tma_variant_fp32_and_u8(ops, B, H, W, cout, monkeypatch):
-    """Image widths >= 256 take the TMA-fed stem (raw rows through a TMA ring, row-aligned tiles, partial last tile when
-    W/2 is not a multiple of 128): vs plain PyTorch, fp32 and uint8 inputs, and vs the gather kernel (library option stem_gather)."""
+    """Image widths >= 256 take the TMA-fed stem (raw rows through a TMA ring, tiles of two 64-pixel half rows, partial last half when
+    W/2 is not a multiple of 64): vs plain PyTorch, fp32 and uint8 inputs, and vs the gather kernel (library option stem_gather)."""
     g = torch.Generator().manual_seed(W + cout)
     img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
     mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
