@@ -516,7 +516,7 @@ int yms_stem_tc_launch(const float* x, const unsigned char* xu8, const float* me
                        int c_out, const float* weight, const float* bias, void* y, int64_t y_ps, cudaStream_t stream) {
     const int out_h = in_h / 2, out_w = in_w / 2;
     if (in_w >= 256 && (in_w % (xu8 ? 16 : 4)) == 0 && ((uintptr_t)(xu8 ? (const void*)xu8 : (const void*)x) & 15) == 0 && !g_opt.stem_gather) {
-        // ---- TMA-fed variant: raw rows through a TMA ring, row-aligned tiles ----
+        // ---- TMA-fed variant: raw rows through a TMA ring, tiles of two 64-pixel half rows ----
         static thread_local struct Cache2 { const void* in; const void* y; int64_t ps; int b, h, w, c, u8; CUtensorMap min, my; bool ok; } c2 = {};
         const void* in = xu8 ? (const void*)xu8 : (const void*)x;
         if (!(c2.ok && c2.in == in && c2.y == y && c2.ps == y_ps && c2.b == batch && c2.h == in_h && c2.w == in_w && c2.c == c_out && c2.u8 == (xu8 ? 1 : 0))) {
